@@ -1,0 +1,301 @@
+// extern "C" surface of libvit3d_sm100.so (declared in include/vit3d.h): argument checks and
+// dispatch between the tcgen05 kernels and the shape-generic fp32 kernels.
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tc.cuh"
+
+namespace vit3d {
+
+static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;   // kernels launched by this library (bench.py's gpu_launches)
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return VIT3D_ERR_CUDA;
+}
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
+    cached = p.multiProcessorCount;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+static inline int act_f32(int prec) { return prec != VIT3D_PREC_BF16; }
+
+}  // namespace vit3d
+
+using namespace vit3d;
+
+extern "C" {
+
+int vit3d_version(void) { return VIT3D_VERSION; }
+const char* vit3d_last_error(void) { return g_err; }
+
+int vit3d_device_info(int* sms, int* cc) {
+  int dev = 0;
+  V3_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  V3_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sms) *sms = p.multiProcessorCount;
+  if (cc) *cc = p.major * 10 + p.minor;
+  return VIT3D_OK;
+}
+unsigned long long vit3d_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+int vit3d_act_bytes(int prec) { return prec == VIT3D_PREC_BF16 ? 2 : 4; }
+int vit3d_tc_supported(int prec, int M, int N, int K) { return tc_linear_supported(prec, M, N, K) ? 1 : 0; }
+
+// ------------------------------------------------------------------------- a1
+int vit3d_patch_gather(const float* x, float* patches, int B, int X, int Y, int Z, int p0, int p1, int p2,
+                       vit3d_stream_t stream) {
+  V3_REQUIRE(x && patches, "patch_gather: null pointer");
+  V3_REQUIRE(B >= 0 && p0 > 0 && p1 > 0 && p2 > 0 && X >= p0 && Y >= p1 && Z >= p2, "patch_gather: bad shape");
+  return launch_patch_gather(x, patches, B, X, Y, Z, p0, p1, p2, as_stream(stream));
+}
+
+size_t vit3d_patch_embed_ws_bytes(int B, int X, int Y, int Z, int p0, int p1, int p2, int H, int prec) {
+  (void)prec;
+  const size_t P = (size_t)(X / p0) * (Y / p1) * (Z / p2);
+  const size_t Kp = (size_t)p0 * p1 * p2;
+  // patches [B*P,Kp] + compacted dY [B*P,H] (backward), fp32
+  return sizeof(float) * ((size_t)B * P * Kp + (size_t)B * P * H) + 256;
+}
+
+int vit3d_patch_embed_fwd(const float* x, const float* w, const float* bias, const float* cls, const float* pos,
+                          float* tokens, int B, int X, int Y, int Z, int p0, int p1, int p2, int H, int prec, void* ws,
+                          size_t ws_bytes, vit3d_stream_t stream) {
+  V3_REQUIRE(x && w && bias && cls && pos && tokens, "patch_embed_fwd: null pointer");
+  V3_REQUIRE(B >= 0 && p0 > 0 && p1 > 0 && p2 > 0 && X >= p0 && Y >= p1 && Z >= p2 && H > 0, "patch_embed_fwd: bad shape");
+  cudaStream_t st = as_stream(stream);
+  const int P = (X / p0) * (Y / p1) * (Z / p2), Kp = p0 * p1 * p2, S = P + 1;
+  if (B == 0) return VIT3D_OK;
+  if (prec != VIT3D_PREC_FP32 && tc_patch_embed_supported(B, X, Y, Z, p0, p1, p2, H)) {
+    int rc = tc_patch_embed_fwd(x, w, bias, pos, tokens, B, X, Y, Z, p0, p1, p2, H, st);
+    if (rc != VIT3D_OK) return rc;
+    return launch_cls_rows(cls, pos, tokens, B, S, H, st);
+  }
+  V3_REQUIRE(ws && ws_bytes >= vit3d_patch_embed_ws_bytes(B, X, Y, Z, p0, p1, p2, H, prec), "patch_embed_fwd: workspace too small");
+  float* patches = reinterpret_cast<float*>(ws);
+  int rc = launch_patch_gather(x, patches, B, X, Y, Z, p0, p1, p2, st);
+  if (rc != VIT3D_OK) return rc;
+  SgemmArgs g;
+  g.A = patches; g.sa_m = Kp; g.sa_k = 1;
+  g.B = w; g.sb_k = 1; g.sb_n = Kp;
+  g.C = tokens; g.ldc = H;
+  g.bias = bias; g.rowadd = pos; g.row_group = P;
+  g.M = B * P; g.N = H; g.K = Kp;
+  rc = launch_sgemm(g, st);
+  if (rc != VIT3D_OK) return rc;
+  return launch_cls_rows(cls, pos, tokens, B, S, H, st);
+}
+
+int vit3d_patch_embed_bwd(const float* x, const float* dtokens, float* dw, float* dbias, float* dcls, float* dpos, int B,
+                          int X, int Y, int Z, int p0, int p1, int p2, int H, int prec, void* ws, size_t ws_bytes,
+                          vit3d_stream_t stream) {
+  V3_REQUIRE(x && dtokens && dw && dbias && dcls && dpos, "patch_embed_bwd: null pointer");
+  V3_REQUIRE(ws && ws_bytes >= vit3d_patch_embed_ws_bytes(B, X, Y, Z, p0, p1, p2, H, prec), "patch_embed_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int P = (X / p0) * (Y / p1) * (Z / p2), Kp = p0 * p1 * p2, S = P + 1;
+  if (B == 0) return VIT3D_OK;
+  float* patches = reinterpret_cast<float*>(ws);
+  float* dY = patches + (size_t)B * P * Kp;
+  int rc = launch_patch_gather(x, patches, B, X, Y, Z, p0, p1, p2, st);
+  if (rc != VIT3D_OK) return rc;
+  rc = launch_gather_patch_rows(dtokens, dY, B, P, H, st);
+  if (rc != VIT3D_OK) return rc;
+  // dw[H,Kp] += dY^T[H, BP] @ patches[BP, Kp]
+  SgemmArgs g;
+  g.A = dY; g.sa_m = 1; g.sa_k = H;
+  g.B = patches; g.sb_k = Kp; g.sb_n = 1;
+  g.C = dw; g.ldc = Kp; g.accumulate = 1;
+  g.M = H; g.N = Kp; g.K = B * P;
+  g.splitk = pick_splitk(g.M, g.N, g.K);
+  rc = launch_sgemm(g, st);
+  if (rc != VIT3D_OK) return rc;
+  rc = launch_colsum(dY, 1, dbias, B * P, H, st);
+  if (rc != VIT3D_OK) return rc;
+  return launch_embed_param_grads(dtokens, dpos, dcls, B, S, H, st);
+}
+
+// ------------------------------------------------------------------------- LayerNorm
+int vit3d_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_bf16, float* mean, float* rstd,
+                 int M, int H, float eps, vit3d_stream_t stream) {
+  V3_REQUIRE(x && gamma && beta && y, "ln_fwd: null pointer");
+  V3_REQUIRE(M >= 0 && H > 0, "ln_fwd: bad shape");
+  return launch_ln_fwd(x, gamma, beta, y, y_bf16, mean, rstd, M, H, eps, as_stream(stream));
+}
+int vit3d_ln_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                 const float* dres, float* dx, float* dgamma, float* dbeta, int M, int H, vit3d_stream_t stream) {
+  V3_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, "ln_bwd: null pointer");
+  V3_REQUIRE(M >= 0 && H > 0 && H <= 8192, "ln_bwd: bad shape");
+  return launch_ln_bwd(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, M, H, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------- Linear
+int vit3d_linear_fwd(const void* x, int ldx, int x_f32, const float* w, const void* w_lp, const float* bias,
+                     const float* residual, void* y, int y_f32, void* pre, int act, int M, int N, int K, int prec,
+                     vit3d_stream_t stream) {
+  V3_REQUIRE(x && w && y, "linear_fwd: null pointer");
+  V3_REQUIRE(M >= 0 && N > 0 && K > 0 && ldx >= K, "linear_fwd: bad shape M=%d N=%d K=%d ldx=%d", M, N, K, ldx);
+  V3_REQUIRE(!(pre && residual), "linear_fwd: pre-activation output and residual are exclusive");
+  cudaStream_t st = as_stream(stream);
+  if (M == 0) return VIT3D_OK;
+  const int xf = x_f32 || act_f32(prec);
+  const int yf = y_f32 || residual != nullptr || act_f32(prec);
+  if (prec != VIT3D_PREC_FP32 && tc_linear_supported(prec, M, N, K) && (prec == VIT3D_PREC_TF32 ? xf : !xf) &&
+      (prec == VIT3D_PREC_TF32 || w_lp) && ldx == K) {
+    TcLinear t;
+    t.x = x; t.w = prec == VIT3D_PREC_BF16 ? w_lp : (const void*)w; t.bias = bias; t.residual = residual;
+    t.y = y; t.y_f32 = yf; t.pre = pre; t.act = act; t.M = M; t.N = N; t.K = K; t.prec = prec;
+    return tc_linear_fwd(t, st);
+  }
+  SgemmArgs g;
+  g.A = x; g.sa_m = ldx; g.sa_k = 1; g.a_f32 = xf;
+  g.B = w; g.sb_k = 1; g.sb_n = K; g.b_f32 = 1;
+  g.C = y; g.ldc = N; g.c_f32 = yf;
+  g.bias = bias; g.residual = residual; g.ldr = N; g.pre = pre; g.act = act;
+  g.M = M; g.N = N; g.K = K;
+  return launch_sgemm(g, st);
+}
+
+int vit3d_linear_bwd(const void* dy, int dy_f32, const void* x, int ldx, int x_f32, const float* w, const void* w_lp,
+                     void* dx, int lddx, int dx_f32, float* dw, float* db, int M, int N, int K, int prec,
+                     vit3d_stream_t stream) {
+  V3_REQUIRE(dy && w, "linear_bwd: null pointer");
+  V3_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_bwd: bad shape");
+  V3_REQUIRE(!dw || x, "linear_bwd: dw needs x");
+  cudaStream_t st = as_stream(stream);
+  if (M == 0) return VIT3D_OK;
+  const int dyf = dy_f32 || act_f32(prec);
+  const int xf = x_f32 || act_f32(prec);
+  const int dxf = dx_f32 || act_f32(prec);
+  (void)w_lp;
+  int rc;
+  if (dx) {
+    // dx[M,K] = dy[M,N] @ w[N,K]
+    SgemmArgs g;
+    g.A = dy; g.sa_m = N; g.sa_k = 1; g.a_f32 = dyf;
+    g.B = w; g.sb_k = K; g.sb_n = 1; g.b_f32 = 1;
+    g.C = dx; g.ldc = lddx > 0 ? lddx : K; g.c_f32 = dxf;
+    g.M = M; g.N = K; g.K = N;
+    rc = launch_sgemm(g, st);
+    if (rc != VIT3D_OK) return rc;
+  }
+  if (dw) {
+    // dw[N,K] += dy^T[N,M] @ x[M,K]
+    SgemmArgs g;
+    g.A = dy; g.sa_m = 1; g.sa_k = N; g.a_f32 = dyf;
+    g.B = x; g.sb_k = ldx; g.sb_n = 1; g.b_f32 = xf;
+    g.C = dw; g.ldc = K; g.c_f32 = 1; g.accumulate = 1;
+    g.M = N; g.N = K; g.K = M;
+    g.splitk = pick_splitk(g.M, g.N, g.K);
+    rc = launch_sgemm(g, st);
+    if (rc != VIT3D_OK) return rc;
+  }
+  if (db) {
+    rc = launch_colsum(dy, dyf, db, M, N, st);
+    if (rc != VIT3D_OK) return rc;
+  }
+  return VIT3D_OK;
+}
+
+// ------------------------------------------------------------------------- attention core
+int vit3d_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int heads, int D, int prec,
+                   vit3d_stream_t stream) {
+  V3_REQUIRE(qkv && ctx, "attn_fwd: null pointer");
+  V3_REQUIRE(B >= 0 && S > 0 && heads > 0 && D > 0, "attn_fwd: bad shape");
+  cudaStream_t st = as_stream(stream);
+  if (prec == VIT3D_PREC_BF16 && tc_attn_supported(S, heads, D)) return tc_attn_fwd(qkv, ctx, probs, B, S, heads, D, st);
+  return launch_attn_fwd_generic(qkv, act_f32(prec), ctx, probs, B, S, heads, D, st);
+}
+int vit3d_attn_bwd(const void* dctx, const void* qkv, void* dqkv, int B, int S, int heads, int D, int prec,
+                   vit3d_stream_t stream) {
+  V3_REQUIRE(dctx && qkv && dqkv, "attn_bwd: null pointer");
+  V3_REQUIRE(B >= 0 && S > 0 && heads > 0 && D > 0, "attn_bwd: bad shape");
+  return launch_attn_bwd_generic(dctx, qkv, act_f32(prec), dqkv, B, S, heads, D, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------- elementwise
+int vit3d_gelu_fwd(const void* h, void* a, long long n, int prec, vit3d_stream_t stream) {
+  V3_REQUIRE(h && a && n >= 0, "gelu_fwd: bad argument");
+  return launch_gelu_fwd(h, a, n, act_f32(prec), as_stream(stream));
+}
+int vit3d_gelu_bwd(const void* da, const void* h, void* dh, long long n, int prec, vit3d_stream_t stream) {
+  V3_REQUIRE(da && h && dh && n >= 0, "gelu_bwd: bad argument");
+  return launch_gelu_bwd(da, h, dh, n, act_f32(prec), as_stream(stream));
+}
+int vit3d_dropout(const void* x, const void* residual, void* y, long long n, int is_f32, float p,
+                  unsigned long long seed, unsigned site, unsigned step, vit3d_stream_t stream) {
+  V3_REQUIRE(x && y && n >= 0 && p >= 0.f && p < 1.f, "dropout: bad argument");
+  return launch_dropout(x, residual, y, n, is_f32, p, seed, site, step, as_stream(stream));
+}
+int vit3d_dropout_mask(unsigned char* mask, long long n, float p, unsigned long long seed, unsigned site, unsigned step,
+                       vit3d_stream_t stream) {
+  V3_REQUIRE(mask && n >= 0 && p >= 0.f && p < 1.f, "dropout_mask: bad argument");
+  return launch_dropout_mask(mask, n, p, seed, site, step, as_stream(stream));
+}
+int vit3d_dropout_masked(const void* x, const unsigned char* mask, const void* residual, void* y, long long n,
+                         int is_f32, float p, vit3d_stream_t stream) {
+  V3_REQUIRE(x && mask && y && n >= 0 && p >= 0.f && p < 1.f, "dropout_masked: bad argument");
+  return launch_dropout_masked(x, mask, residual, y, n, is_f32, p, as_stream(stream));
+}
+int vit3d_cast_f32_to_bf16(const float* x, void* y, long long n, vit3d_stream_t stream) {
+  V3_REQUIRE(x && y && n >= 0, "cast: bad argument");
+  return launch_cast(x, 1, y, 0, n, as_stream(stream));
+}
+int vit3d_cast_bf16_to_f32(const void* x, float* y, long long n, vit3d_stream_t stream) {
+  V3_REQUIRE(x && y && n >= 0, "cast: bad argument");
+  return launch_cast(x, 0, y, 1, n, as_stream(stream));
+}
+int vit3d_add_inplace(float* y, const float* x, long long n, vit3d_stream_t stream) {
+  V3_REQUIRE(x && y && n >= 0, "add_inplace: bad argument");
+  return launch_add_inplace(y, x, n, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------- loss / meta / optimizers
+int vit3d_bce_logits_fwd(const float* logits, const float* labels, float pos_weight, float* loss, int n,
+                         vit3d_stream_t stream) {
+  V3_REQUIRE(logits && labels && loss && n > 0, "bce_fwd: bad argument");
+  return launch_bce_fwd(logits, labels, pos_weight, loss, n, as_stream(stream));
+}
+int vit3d_bce_logits_bwd(const float* logits, const float* labels, float pos_weight, const float* dloss, float* dlogits,
+                         int n, vit3d_stream_t stream) {
+  V3_REQUIRE(logits && labels && dlogits && n > 0, "bce_bwd: bad argument");
+  return launch_bce_bwd(logits, labels, pos_weight, dloss, dlogits, n, as_stream(stream));
+}
+int vit3d_meta_fwd(const float* feats, const float* w, const float* b, float* out, int B, int F, int C,
+                   vit3d_stream_t stream) {
+  V3_REQUIRE(feats && w && b && out && B >= 0 && F > 0 && C > 0, "meta_fwd: bad argument");
+  return launch_meta_fwd(feats, w, b, out, B, F, C, as_stream(stream));
+}
+int vit3d_meta_bwd(const float* dout, const float* out, const float* feats, const float* w, float* dfeats, float* dw,
+                   float* db, int B, int F, int C, vit3d_stream_t stream) {
+  V3_REQUIRE(dout && out && feats && w && dfeats && dw && db && B >= 0 && F > 0 && C > 0, "meta_bwd: bad argument");
+  return launch_meta_bwd(dout, out, feats, w, dfeats, dw, db, B, F, C, as_stream(stream));
+}
+int vit3d_sgd_step(float* p, const float* g, float* mom, long long n, float lr, float momentum, float weight_decay,
+                   int first_step, float grad_scale, vit3d_stream_t stream) {
+  V3_REQUIRE(p && g && n >= 0 && (momentum == 0.f || mom), "sgd_step: bad argument");
+  return launch_sgd(p, g, mom, n, lr, momentum, weight_decay, first_step, grad_scale, as_stream(stream));
+}
+int vit3d_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, float grad_scale, vit3d_stream_t stream) {
+  V3_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "adam_step: bad argument");
+  return launch_adam(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, as_stream(stream));
+}
+
+}  // extern "C"

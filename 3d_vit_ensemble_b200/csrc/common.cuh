@@ -1,0 +1,114 @@
+// Shared device/host helpers for libvit3d_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/vit3d.h"
+
+namespace vit3d {
+
+// ----------------------------------------------------------------------------- errors
+// Thread-local last-error text; every extern "C" entry returns an int code and never throws.
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define V3_CUDA(call)                                                         \
+  do {                                                                        \
+    cudaError_t e__ = (call);                                                 \
+    if (e__ != cudaSuccess) return ::vit3d::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+void count_launch();
+#define V3_LAUNCH_CHECK()                                                     \
+  do {                                                                        \
+    ::vit3d::count_launch();                                                  \
+    cudaError_t e__ = cudaPeekAtLastError();                                  \
+    if (e__ != cudaSuccess) return ::vit3d::cuda_fail(e__, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+#define V3_REQUIRE(cond, ...)                                                 \
+  do {                                                                        \
+    if (!(cond)) {                                                            \
+      ::vit3d::set_error(__VA_ARGS__);                                        \
+      return VIT3D_ERR_INVALID;                                               \
+    }                                                                         \
+  } while (0)
+
+#define V3_UNSUPPORTED(...)                                                   \
+  do {                                                                        \
+    ::vit3d::set_error(__VA_ARGS__);                                          \
+    return VIT3D_ERR_UNSUPPORTED;                                             \
+  } while (0)
+
+static inline cudaStream_t as_stream(vit3d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+int sm_count();
+
+// ----------------------------------------------------------------------------- device math
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// exact (erf) GELU, as torch.nn.functional.gelu default (modeling.py:52,107)
+__device__ __forceinline__ float gelu_f(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// ----------------------------------------------------------------------------- Philox4x32-10
+// Counter-based RNG for dropout: the mask of element i at (site, step) is a pure function
+// of (seed, site, step, i), so backward regenerates it instead of storing it.
+struct Philox4 {
+  uint32_t v[4];
+};
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  Philox4 o;
+  o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
+  return o;
+}
+// keep-decision for element index i (64-bit) of dropout site `site` at step `step`
+__host__ __device__ __forceinline__ bool dropout_keep(unsigned long long seed, uint32_t site, uint32_t step,
+                                                      unsigned long long i, uint32_t thresh) {
+  const unsigned long long blk = i >> 2;
+  Philox4 r = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), site, step, (uint32_t)seed, (uint32_t)(seed >> 32));
+  return r.v[i & 3] >= thresh;   // P(keep) = 1 - thresh / 2^32
+}
+static inline uint32_t dropout_thresh(float p) {
+  double t = (double)p * 4294967296.0;
+  if (t < 0) t = 0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  return (uint32_t)t;
+}
+
+}  // namespace vit3d

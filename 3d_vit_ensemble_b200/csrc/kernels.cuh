@@ -1,0 +1,56 @@
+// Internal launcher declarations shared by the translation units of libvit3d_sm100.so.
+#pragma once
+#include "common.cuh"
+
+namespace vit3d {
+
+struct SgemmArgs {
+  const void* A = nullptr; long long sa_m = 0, sa_k = 0; int a_f32 = 1;
+  const void* B = nullptr; long long sb_k = 0, sb_n = 0; int b_f32 = 1;
+  void* C = nullptr; long long ldc = 0; int c_f32 = 1; int accumulate = 0;
+  const float* bias = nullptr;       // per output column
+  const float* rowadd = nullptr;     // [row_group+1, N] position table (needs row_group > 0)
+  const float* residual = nullptr; long long ldr = 0;
+  void* pre = nullptr;               // pre-activation copy (same type as C)
+  int act = 0;
+  int row_group = 0;                 // >0: output row = m + m/row_group + 1 (leave room for the cls rows)
+  int splitk = 1;
+  int M = 0, N = 0, K = 0;
+};
+
+int launch_sgemm(const SgemmArgs& a, cudaStream_t st);
+int pick_splitk(int M, int N, int K);
+int launch_patch_gather(const float* x, float* out, int B, int X, int Y, int Z, int p0, int p1, int p2, cudaStream_t st);
+int launch_cls_rows(const float* cls, const float* pos, float* tokens, int B, int S, int H, cudaStream_t st);
+int launch_embed_param_grads(const float* dtok, float* dpos, float* dcls, int B, int S, int H, cudaStream_t st);
+int launch_gather_patch_rows(const float* dtok, float* out, int B, int P, int H, cudaStream_t st);
+int launch_ln_fwd(const float* x, const float* g, const float* b, void* y, int y_bf16, float* mean, float* rstd, int M,
+                  int H, float eps, cudaStream_t st);
+int launch_ln_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                  const float* dres, float* dx, float* dgamma, float* dbeta, int M, int H, cudaStream_t st);
+int launch_colsum(const void* dy, int f32, float* db, int M, int N, cudaStream_t st);
+int launch_attn_fwd_generic(const void* qkv, int f32, void* ctx, float* probs, int B, int S, int heads, int D,
+                            cudaStream_t st);
+int launch_attn_bwd_generic(const void* dctx, const void* qkv, int f32, void* dqkv, int B, int S, int heads, int D,
+                            cudaStream_t st);
+int launch_gelu_fwd(const void* h, void* a, long long n, int f32, cudaStream_t st);
+int launch_gelu_bwd(const void* da, const void* h, void* dh, long long n, int f32, cudaStream_t st);
+int launch_dropout(const void* x, const void* residual, void* y, long long n, int f32, float p,
+                   unsigned long long seed, unsigned site, unsigned step, cudaStream_t st);
+int launch_dropout_mask(unsigned char* mask, long long n, float p, unsigned long long seed, unsigned site, unsigned step,
+                        cudaStream_t st);
+int launch_dropout_masked(const void* x, const unsigned char* mask, const void* residual, void* y, long long n,
+                          int f32, float p, cudaStream_t st);
+int launch_cast(const void* x, int x_f32, void* y, int y_f32, long long n, cudaStream_t st);
+int launch_add_inplace(float* y, const float* x, long long n, cudaStream_t st);
+int launch_bce_fwd(const float* z, const float* y, float pw, float* loss, int n, cudaStream_t st);
+int launch_bce_bwd(const float* z, const float* y, float pw, const float* dloss, float* dz, int n, cudaStream_t st);
+int launch_meta_fwd(const float* f, const float* w, const float* b, float* out, int B, int F, int C, cudaStream_t st);
+int launch_meta_bwd(const float* dout, const float* out, const float* f, const float* w, float* df, float* dw, float* db,
+                    int B, int F, int C, cudaStream_t st);
+int launch_sgd(float* p, const float* g, float* mom, long long n, float lr, float momentum, float wd, int first,
+               float gscale, cudaStream_t st);
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                float wd, int step, float gscale, cudaStream_t st);
+
+}  // namespace vit3d

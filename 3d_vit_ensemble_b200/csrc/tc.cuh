@@ -1,0 +1,29 @@
+// tcgen05 / TMA / mma.sync tensor-core kernels (sm_100a): internal interface.
+#pragma once
+#include "common.cuh"
+
+namespace vit3d {
+
+struct TcLinear {
+  const void* x = nullptr;       // [M,K] bf16 (BF16) or fp32 (TF32), row-major, dense
+  const void* w = nullptr;       // [N,K] same element type as x
+  const float* bias = nullptr;   // [N] or null
+  const float* residual = nullptr;  // [M,N] fp32 or null
+  void* y = nullptr;             // [M,N] fp32 (y_f32) or bf16
+  int y_f32 = 0;
+  void* pre = nullptr;           // optional pre-activation copy, same type as y
+  int act = 0;
+  int M = 0, N = 0, K = 0, prec = 0;
+};
+
+bool tc_linear_supported(int prec, int M, int N, int K);
+int tc_linear_fwd(const TcLinear& t, cudaStream_t st);
+
+bool tc_patch_embed_supported(int B, int X, int Y, int Z, int p0, int p1, int p2, int H);
+int tc_patch_embed_fwd(const float* x, const float* w, const float* bias, const float* pos, float* tokens, int B, int X,
+                       int Y, int Z, int p0, int p1, int p2, int H, cudaStream_t st);
+
+bool tc_attn_supported(int S, int heads, int D);
+int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int heads, int D, cudaStream_t st);
+
+}  // namespace vit3d

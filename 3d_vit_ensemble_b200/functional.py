@@ -1,0 +1,384 @@
+"""torch.autograd.Function wrappers over the C ABI (one Function per operator of the path).
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every
+arithmetic operation is a kernel of libvit3d_sm100.so.  Reference line numbers cite
+evapachetti/3d_vit_ensemble `models/modeling.py`.
+"""
+from __future__ import annotations
+
+import os
+import weakref
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, PREC, call, ptr, stream
+
+_STATE = {"precision": os.environ.get("VIT3D_PRECISION", "bf16"), "step": 0, "mask_override": None}
+
+
+def set_precision(p: str) -> None:
+    """'fp32' (exact FMA path), 'tf32' or 'bf16' (tcgen05 paths); default for new models."""
+    if p not in PREC:
+        raise ValueError(f"unknown precision {p!r}; choose from {list(PREC)}")
+    _STATE["precision"] = p
+
+
+def get_precision() -> str:
+    return _STATE["precision"]
+
+
+def act_dtype(prec: str) -> torch.dtype:
+    return torch.bfloat16 if prec == "bf16" else torch.float32
+
+
+def next_dropout_step() -> int:
+    _STATE["step"] += 1
+    return _STATE["step"]
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.Vit3dError("vit3d operators run on CUDA tensors only (no CPU fallback); "
+                                  "move the model and its inputs to a cuda device")
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# bf16 shadow copies of fp32 master weights (parameters only), refreshed when the parameter
+# changes (optimizer step / load_state_dict bump _version, .to() changes data_ptr).  Keyed by the
+# parameter object itself so that a freed-and-reallocated address can never alias a stale copy.
+_LP_CACHE = {}   # id(param) -> (weakref(param), version, data_ptr, bf16 copy)
+
+
+def lp_weight(w: torch.Tensor) -> torch.Tensor:
+    cacheable = isinstance(w, torch.nn.Parameter)
+    if cacheable:
+        ent = _LP_CACHE.get(id(w))
+        if ent is not None and ent[0]() is w and ent[1] == w._version and ent[2] == w.data_ptr():
+            return ent[3]
+    out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+    call("vit3d_cast_f32_to_bf16", ptr(w.detach()), ptr(out), w.numel(), stream())
+    if cacheable:
+        key = id(w)
+        _LP_CACHE[key] = (weakref.ref(w, lambda _r, key=key: _LP_CACHE.pop(key, None)), w._version, w.data_ptr(), out)
+    return out
+
+
+# ----------------------------------------------------------------------------- a1
+class PatchEmbedFn(torch.autograd.Function):
+    """Conv3d(kernel=stride=patch) + flatten/transpose + cls concat + position add
+    (Embeddings.forward, modeling.py:162-173) as one gather-GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, cls, pos, prec):
+        _need_cuda(x, w, bias, cls, pos)
+        x = _c(x.float())
+        B, Cc, X, Y, Z = x.shape
+        if Cc != 1:
+            raise _lib.Vit3dError("patch embedding expects a single input channel")
+        H = w.shape[0]
+        p0, p1, p2 = w.shape[2:]
+        P = (X // p0) * (Y // p1) * (Z // p2)
+        if pos.shape[1] != P + 1:
+            raise _lib.Vit3dError(f"position_embeddings has {pos.shape[1]} rows, input gives {P + 1} tokens")
+        tokens = torch.empty(B, P + 1, H, device=x.device, dtype=torch.float32)
+        pid = PREC[prec]
+        wsb = _lib.lib().vit3d_patch_embed_ws_bytes(B, X, Y, Z, p0, p1, p2, H, pid)
+        ws = torch.empty(wsb, device=x.device, dtype=torch.uint8)
+        call("vit3d_patch_embed_fwd", ptr(x), ptr(_c(w)), ptr(_c(bias)), ptr(_c(cls)), ptr(_c(pos)), ptr(tokens),
+             B, X, Y, Z, p0, p1, p2, H, pid, ptr(ws), wsb, stream())
+        ctx.save_for_backward(x)
+        ctx.meta = (w.shape, cls.shape, pos.shape, prec)
+        return tokens
+
+    @staticmethod
+    def backward(ctx, dtok):
+        (x,) = ctx.saved_tensors
+        wshape, cshape, pshape, prec = ctx.meta
+        B, _, X, Y, Z = x.shape
+        H, _, p0, p1, p2 = wshape
+        dev = x.device
+        dw = torch.zeros(wshape, device=dev)
+        db = torch.zeros(H, device=dev)
+        dcls = torch.zeros(cshape, device=dev)
+        dpos = torch.zeros(pshape, device=dev)
+        pid = PREC[prec]
+        wsb = _lib.lib().vit3d_patch_embed_ws_bytes(B, X, Y, Z, p0, p1, p2, H, pid)
+        ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
+        call("vit3d_patch_embed_bwd", ptr(x), ptr(_c(dtok.float())), ptr(dw), ptr(db), ptr(dcls), ptr(dpos),
+             B, X, Y, Z, p0, p1, p2, H, pid, ptr(ws), wsb, stream())
+        return None, dw, db, dcls, dpos, None
+
+
+def patch_gather(x: torch.Tensor, patch) -> torch.Tensor:
+    """Bit-exact im2col permutation used by the embedding (for tests / inspection)."""
+    _need_cuda(x)
+    x = _c(x.float())
+    B, _, X, Y, Z = x.shape
+    p0, p1, p2 = patch
+    P = (X // p0) * (Y // p1) * (Z // p2)
+    out = torch.empty(B, P, p0 * p1 * p2, device=x.device)
+    call("vit3d_patch_gather", ptr(x), ptr(out), B, X, Y, Z, p0, p1, p2, stream())
+    return out
+
+
+# ----------------------------------------------------------------------------- LayerNorm
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm(H, eps) forward/backward (modeling.py:189,194,253)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, out_bf16):
+        _need_cuda(x, gamma, beta)
+        x = _c(x.float())
+        H = x.shape[-1]
+        M = x.numel() // H
+        od = torch.bfloat16 if out_bf16 else torch.float32
+        y = torch.empty(x.shape, device=x.device, dtype=od)
+        mean = torch.empty(M, device=x.device)
+        rstd = torch.empty(M, device=x.device)
+        call("vit3d_ln_fwd", ptr(x), ptr(_c(gamma)), ptr(_c(beta)), ptr(y), int(od == torch.bfloat16), ptr(mean),
+             ptr(rstd), M, H, float(eps), stream())
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        H = x.shape[-1]
+        M = x.numel() // H
+        dy = _c(dy.float())
+        dx = torch.empty_like(x)
+        dg = torch.zeros_like(gamma)
+        db = torch.zeros_like(gamma)
+        call("vit3d_ln_bwd", ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(_c(gamma)), None, ptr(dx), ptr(dg), ptr(db),
+             M, H, stream())
+        return dx, dg, db, None, None
+
+
+# ----------------------------------------------------------------------------- Linear
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) (+ residual): nn.Linear at modeling.py:63-67,105-106,277 with the GELU
+    (modeling.py:120) and the residual add (modeling.py:191,196) folded into the epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, residual, act, prec, out_f32):
+        _need_cuda(x, w, b, residual)
+        N, K = w.shape
+        lead = x.shape[:-1]
+        ad = act_dtype(prec)
+        if x.dtype not in (torch.float32, torch.bfloat16) or (x.dtype == torch.bfloat16 and prec != "bf16"):
+            x = x.float()
+        if x.dim() == 2 and x.stride(1) == 1 and x.stride(0) >= K:
+            x2, ldx = x, x.stride(0)           # strided rows (the head reads token 0 of each volume)
+        else:
+            x2, ldx = _c(x).reshape(-1, K), K
+        M = x2.shape[0]
+        yd = torch.float32 if (residual is not None or out_f32) else ad
+        y = torch.empty(M, N, device=x.device, dtype=yd)
+        pre = torch.empty(M, N, device=x.device, dtype=yd) if act == ACT_GELU else None
+        w_lp = lp_weight(w) if (prec == "bf16" and w.is_contiguous()) else None
+        w = _c(w)
+        if prec == "bf16" and w_lp is None:
+            w_lp = lp_weight(w)
+        res = None if residual is None else _c(residual.float()).reshape(M, N)
+        call("vit3d_linear_fwd", ptr(x2), ldx, int(x2.dtype == torch.float32), ptr(w), ptr(w_lp),
+             ptr(None if b is None else _c(b)), ptr(res), ptr(y), int(yd == torch.float32), ptr(pre), act, M, N, K,
+             PREC[prec], stream())
+        ctx.save_for_backward(x2, w, w_lp, pre)
+        ctx.meta = (ldx, act, prec, b is not None, residual is not None, x.shape, x.dtype)
+        return y.reshape(*lead, N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, w_lp, pre = ctx.saved_tensors
+        ldx, act, prec, has_b, has_res, xshape, xdtype = ctx.meta
+        N, K = w.shape
+        M = x2.shape[0]
+        dy2 = _c(dy).reshape(M, N)
+        d_res = dy2.reshape(*xshape[:-1], N) if has_res else None
+        if act == ACT_GELU:
+            if dy2.dtype != pre.dtype:
+                dy2 = dy2.to(pre.dtype)
+            dh = torch.empty_like(pre)
+            # gelu'(pre) * dy, exact erf form
+            call("vit3d_gelu_bwd", ptr(dy2), ptr(pre), ptr(dh), dh.numel(),
+                 PREC["fp32"] if pre.dtype == torch.float32 else PREC["bf16"], stream())
+            dy2 = dh
+        need_dx = ctx.needs_input_grad[0]
+        dx = torch.empty(M, K, device=dy.device, dtype=x2.dtype) if need_dx else None
+        dw = torch.zeros_like(w) if ctx.needs_input_grad[1] else None
+        db = torch.zeros(N, device=dy.device) if (has_b and ctx.needs_input_grad[2]) else None
+        call("vit3d_linear_bwd", ptr(dy2), int(dy2.dtype == torch.float32), ptr(x2), ldx,
+             int(x2.dtype == torch.float32), ptr(w), ptr(w_lp), ptr(dx), K, int(x2.dtype == torch.float32), ptr(dw),
+             ptr(db), M, N, K, PREC[prec], stream())
+        if dx is not None:
+            dx = dx.reshape(xshape).to(xdtype)
+        return dx, dw, db, d_res, None, None, None
+
+
+def linear(x, w, b=None, residual=None, act=ACT_NONE, prec=None, out_f32=False):
+    return LinearFn.apply(x, w, b, residual, act, prec or get_precision(), out_f32)
+
+
+# ----------------------------------------------------------------------------- attention core
+class AttnCoreFn(torch.autograd.Function):
+    """softmax(q k^T / sqrt(D)) v per (volume, head) (modeling.py:83-96) on the packed qkv matrix."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads, vis, prec):
+        _need_cuda(qkv)
+        B, S, A3 = qkv.shape
+        A = A3 // 3
+        D = A // heads
+        ad = act_dtype(prec)
+        qkv = _c(qkv.to(ad))
+        out = torch.empty(B, S, A, device=qkv.device, dtype=ad)
+        probs = torch.empty(B, heads, S, S, device=qkv.device) if vis else None
+        call("vit3d_attn_fwd", ptr(qkv), ptr(out), ptr(probs), B, S, heads, D, PREC[prec], stream())
+        ctx.save_for_backward(qkv)
+        ctx.meta = (heads, D, prec)
+        if probs is None:
+            return out, None
+        ctx.mark_non_differentiable(probs)
+        return out, probs
+
+    @staticmethod
+    def backward(ctx, dctx, _dprobs):
+        (qkv,) = ctx.saved_tensors
+        heads, D, prec = ctx.meta
+        B, S, _ = qkv.shape
+        dctx = _c(dctx.to(qkv.dtype))
+        dqkv = torch.empty_like(qkv)
+        call("vit3d_attn_bwd", ptr(dctx), ptr(qkv), ptr(dqkv), B, S, heads, D, PREC[prec], stream())
+        return dqkv, None, None, None
+
+
+# ----------------------------------------------------------------------------- dropout
+class DropoutFn(torch.autograd.Function):
+    """Inverted dropout with a counter-based mask (modeling.py:121,123,174), optionally fused with the
+    residual add that follows it (modeling.py:196)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, p, seed, site, step, mask):
+        _need_cuda(x, residual)
+        x = _c(x)
+        if residual is not None:
+            residual = _c(residual.to(x.dtype))
+        y = torch.empty_like(x)
+        f32 = int(x.dtype == torch.float32)
+        if mask is not None:
+            mask = _c(mask.to(device=x.device, dtype=torch.uint8))
+            if mask.numel() != x.numel():
+                raise _lib.Vit3dError("dropout mask has the wrong number of elements")
+            call("vit3d_dropout_masked", ptr(x), ptr(mask), ptr(residual), ptr(y), x.numel(), f32, float(p), stream())
+        else:
+            call("vit3d_dropout", ptr(x), ptr(residual), ptr(y), x.numel(), f32, float(p), seed, site, step, stream())
+        ctx.meta = (p, seed, site, step, mask, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, seed, site, step, mask, has_res = ctx.meta
+        dy = _c(dy)
+        dx = torch.empty_like(dy)
+        f32 = int(dy.dtype == torch.float32)
+        if mask is not None:
+            call("vit3d_dropout_masked", ptr(dy), ptr(mask), None, ptr(dx), dy.numel(), f32, float(p), stream())
+        else:
+            call("vit3d_dropout", ptr(dy), None, ptr(dx), dy.numel(), f32, float(p), seed, site, step, stream())
+        return dx, (dy if has_res else None), None, None, None, None, None
+
+
+def dropout(x, p: float, training: bool, site: int, step: int, mask=None, residual=None):
+    if not training or p <= 0.0:
+        assert residual is None
+        return x
+    if mask is None and _STATE["mask_override"] is not None:
+        mask = _STATE["mask_override"].get(site)
+    seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    return DropoutFn.apply(x, residual, p, seed, site, step, mask)
+
+
+def dropout_mask(n: int, p: float, site: int, step: int, device) -> torch.Tensor:
+    """The keep-mask DropoutFn draws for (current torch seed, site, step): for parity tests."""
+    m = torch.empty(n, device=device, dtype=torch.uint8)
+    call("vit3d_dropout_mask", ptr(m), n, float(p), torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, site, step, stream())
+    return m
+
+
+class mask_injection:
+    """Context manager: replay explicit dropout keep-masks {site: mask} (parity with the reference's RNG
+    stream is impossible; its masks are injected instead)."""
+
+    def __init__(self, masks):
+        self.masks = masks
+
+    def __enter__(self):
+        _STATE["mask_override"] = self.masks
+
+    def __exit__(self, *a):
+        _STATE["mask_override"] = None
+
+
+# ----------------------------------------------------------------------------- loss
+class BceLogitsFn(torch.autograd.Function):
+    """BCEWithLogitsLoss(pos_weight)(logits.view(-1,1), labels.view(-1,1)) mean (modeling.py:283-286)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, pos_weight):
+        _need_cuda(logits, labels)
+        z = _c(logits.float()).reshape(-1)
+        y = _c(labels.to(device=z.device, dtype=torch.float32)).reshape(-1)
+        if y.numel() != z.numel():
+            raise _lib.Vit3dError("BCE: logits and labels differ in size")
+        loss = torch.empty((), device=z.device)
+        pw = -1.0 if pos_weight is None else float(pos_weight)
+        call("vit3d_bce_logits_fwd", ptr(z), ptr(y), pw, ptr(loss), z.numel(), stream())
+        ctx.save_for_backward(z, y)
+        ctx.meta = (pw, logits.shape)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        z, y = ctx.saved_tensors
+        pw, shape = ctx.meta
+        dz = torch.empty_like(z)
+        dl = _c(dloss.float())
+        call("vit3d_bce_logits_bwd", ptr(z), ptr(y), pw, ptr(dl), ptr(dz), z.numel(), stream())
+        return dz.reshape(shape), None, None
+
+
+# ----------------------------------------------------------------------------- meta classifier
+class MetaFn(torch.autograd.Function):
+    """sigmoid(Linear(cat(member logits))) (TransformerEnsemble.forward, modeling.py:355-356)."""
+
+    @staticmethod
+    def forward(ctx, feats, w, b):
+        _need_cuda(feats, w, b)
+        feats = _c(feats.float())
+        B, F = feats.shape
+        Cn = w.shape[0]
+        if w.shape[1] != F:
+            raise _lib.Vit3dError(f"meta-classifier expects {w.shape[1]} features, members give {F} "
+                                  "(use in_features == num_classes of the members)")
+        out = torch.empty(B, Cn, device=feats.device)
+        call("vit3d_meta_fwd", ptr(feats), ptr(_c(w)), ptr(_c(b)), ptr(out), B, F, Cn, stream())
+        ctx.save_for_backward(feats, w, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        feats, w, out = ctx.saved_tensors
+        B, F = feats.shape
+        Cn = w.shape[0]
+        df = torch.empty_like(feats)
+        dw = torch.zeros_like(w)
+        db = torch.zeros(Cn, device=w.device)
+        call("vit3d_meta_bwd", ptr(_c(dout.float())), ptr(out), ptr(feats), ptr(_c(w)), ptr(df), ptr(dw), ptr(db),
+             B, F, Cn, stream())
+        return df, dw, db

@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Headline benchmark: 3D-ViT (conf 5 by default) inference volumes/s on N B200s.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+    python bench.py --impl reference ...       # the reference's CPU path (oracle port) on the host cores
+
+One JSON line on stdout (rank 0).  A "step" = one forward pass of `model(x)` (eval, no_grad, reference
+call pattern train_baseline_cv.py:79) over one batch of `--batch` synthetic volumes per GPU.
+`value` = volumes/s with the batch resident in HBM; `e2e` = the same through the public module call
+with pinned HOST input, H2D copy and D2H read of the logits inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ensemble volumes/sec (inference, fwd+bwd train) at 1/2/4/8 B200 vs CPU ref"
+UNIT = "volumes/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="conf5_infer",
+                    choices=["conf5_infer", "conf18_train", "ensemble_infer"])
+    ap.add_argument("--batch", type=int, default=0, help="volumes per GPU per step (0 = workload default)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--vis", type=int, default=1, help="materialise attention probabilities (reference default vis=True)")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="volumes per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [v.strip() for v in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_arm(args, workload_cfgs, train, steps, warmup, sample):
+    """Times the reference's algorithm on the host cores: the oracle's functional restatement of
+    models/modeling.py (torch CPU fp32, all threads).  Bounded sample of the same workload."""
+    import torch
+    from oracle import vit3d_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    cfgs = workload_cfgs
+    sds = [O.init_state_dict(c, seed=42 + j) for j, c in enumerate(cfgs)]
+    x = O.synth_volumes(sample, seed=42)
+    y = O.synth_labels(sample)
+    w = O.balanced_pos_weight(y)
+    ens_sd = O.ensemble_state_dict(sds) if len(cfgs) > 1 else None
+
+    def step():
+        if train:
+            O.vit_loss_and_grads(sds[0], cfgs[0], x, y, w)
+        elif ens_sd is not None:
+            with torch.no_grad():
+                O.ensemble_forward(ens_sd, cfgs, x)
+        else:
+            with torch.no_grad():
+                O.vit_forward(sds[0], cfgs[0], x)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return sample * steps / dt, dt / steps * 1e3
+
+
+def workload(args):
+    import vit3d_b200
+    if args.workload == "conf5_infer":
+        return dict(name="conf5 (d2048 L6 8x32 H256) inference, model(x) eval/no_grad", confs=[5], train=False,
+                    batch=args.batch or 1024)
+    if args.workload == "conf18_train":
+        return dict(name="conf18 (d3072 L8 16x16 H256) training fwd+bwd", confs=[18], train=True,
+                    batch=args.batch or 256)
+    return dict(name="ensemble conf 5+9+11 + meta-classifier inference", confs=[5, 9, 11], train=False,
+                batch=args.batch or 512)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = workload(args)
+    import torch
+    import vit3d_b200
+    from oracle import vit3d_oracle as O
+    cfgs = [vit3d_b200.north_star_config(c) for c in wl["confs"]]
+    flops_per_vol = sum(O.fwd_flops_per_volume(c) for c in cfgs) * (3.0 if wl["train"] else 1.0)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = min(args.cpu_sample, wl["batch"])
+        steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+        v, ms = cpu_arm(args, cfgs, wl["train"], steps, warm, sample)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "batch_per_step": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{steps} steps x {sample} volumes, oracle port of models/modeling.py, torch CPU fp32"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from vit3d_b200.models.modeling import TransformerEnsemble, VisionTransformer
+    L = vit3d_b200._lib.lib()
+
+    B = wl["batch"]
+    members = []
+    for j, c in enumerate(cfgs):
+        m = VisionTransformer(c, 128, zero_head=True, num_classes=1, vis=bool(args.vis), precision=args.precision)
+        m.load_state_dict(O.init_state_dict(c, seed=42 + j))
+        members.append(m)
+    model = members[0] if len(members) == 1 else TransformerEnsemble(*members, in_features=1)
+    model.to(dev)
+    train = wl["train"]
+    model.train(train)
+    x_host = O.synth_volumes(B, seed=42 + rank).pin_memory()
+    y_host = O.synth_labels(B).pin_memory()
+    pw = O.balanced_pos_weight(y_host)
+    x_dev = x_host.to(dev)
+    y_dev = y_host.to(dev)
+
+    def step_dev(x, y):
+        if train:
+            model.zero_grad(set_to_none=True)
+            loss = model(x, y, pw)
+            loss.backward()
+            return loss
+        with torch.no_grad():
+            out = model(x)
+        return out[0] if isinstance(out, tuple) else out
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = L.vit3d_launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        n1 = L.vit3d_launch_count()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+            dist.barrier()
+        return ms, n1 - n0
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms_dev, launches = timed(lambda: step_dev(x_dev, y_dev), args.steps, args.warmup)
+    clk = clocks.stop() if rank == 0 else None
+
+    res_host = torch.empty((B, 1) if not train else (), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        yd = y_host.to(dev, non_blocking=True) if train else None
+        out = step_dev(xd, yd)
+        res_host.copy_(out.detach().reshape(res_host.shape), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ms_e2e, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+
+    value = world * B * args.steps / (ms_dev * 1e-3)
+    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (fc1/fc2 GEMM pair = 75-82 % of the FLOPs), timed alone
+    roof = None
+    cpu_base = None
+    if rank == 0:
+        roof = roofline_probe(args, cfgs[0], B, dev)
+        if not args.no_cpu_baseline:
+            sample = min(args.cpu_sample, B)
+            v, ms = cpu_arm(args, cfgs, train, 3, 1, sample)
+            cpu_base = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                        "sample": f"3 steps x {sample} volumes of the same workload, oracle port of models/modeling.py, "
+                                  f"torch CPU fp32, {os.cpu_count()} threads"}
+    if rank == 0:
+        peaks = load_peaks()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": wl["name"], "batch_per_gpu": B, "global_batch": B * world, "vis": bool(args.vis),
+                       "precision": args.precision, "l2": "inputs larger than L2 (batch of fp32 volumes = %.0f MB)" % (B * 327680 / 1e6),
+                       "parallelism": f"dp{world} (independent volumes, no data-path collective)"},
+            "model_tflops": value * flops_per_vol / 1e12,
+            "model_frac_of_bf16_sustained": value * flops_per_vol / 1e12 / (world * peaks["bf16_tflops_sustained"]),
+            "clocks": clk,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * 327680 + (B * 4 if train else 0)),
+                    "d2h_bytes_per_step": int(res_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["source"] = "measured (MEASURED_PEAKS.json)"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def roofline_probe(args, cfg, B, dev):
+    """Times the dominant kernel (the fc1 GELU GEMM, [B*65,256]x[256,d]) alone with CUDA events on the
+    launching stream and reports achieved TFLOP/s against the measured burst bf16 peak."""
+    import torch
+    from vit3d_b200 import _lib
+    from vit3d_b200._lib import PREC, call, ptr, stream
+    peaks = load_peaks()
+    M, K, N = B * 65, cfg.hidden_size, cfg.transformer["mlp_dim"]
+    prec = args.precision
+    adt = torch.bfloat16 if prec == "bf16" else torch.float32
+    x = (torch.randn(M, K, device=dev) * 0.5).to(adt)
+    w = torch.randn(N, K, device=dev) * 0.05
+    wl = w.to(torch.bfloat16) if prec == "bf16" else None
+    b = torch.randn(N, device=dev) * 0.01
+    y = torch.empty(M, N, device=dev, dtype=adt)
+    tc = bool(_lib.lib().vit3d_tc_supported(PREC[prec], M, N, K))
+
+    def run():
+        call("vit3d_linear_fwd", ptr(x), K, int(adt == torch.float32), ptr(w), ptr(wl), ptr(b), None, ptr(y),
+             int(adt == torch.float32), None, 1, M, N, K, PREC[prec], stream())
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 10
+    e0.record()
+    for _ in range(iters):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 2.0 * M * N * K
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"kernel": "fc1+GELU GEMM (vit3d_linear_fwd, M=%d N=%d K=%d, %s)" % (M, N, K, "tcgen05" if tc else "fp32 FMA fallback"),
+            "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": ach / peaks["bf16_tflops"], "traffic": None, "ms_per_launch": ms,
+            "peak_source": peaks.get("source"), "how": "kernel timed alone, 10 launches, CUDA events (burst peak applies)"}
+
+
+if __name__ == "__main__":
+    main()

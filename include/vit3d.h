@@ -1,0 +1,162 @@
+/* vit3d.h — C ABI of libvit3d_sm100.so
+ *
+ * B200 (sm_100a) kernels for the 3D-ViT stacking-ensemble forward/backward path of
+ * evapachetti/3d_vit_ensemble `models/modeling.py`.  The reference has no FFI for this
+ * path (it is pure PyTorch): the drop-in boundary is the Python class
+ * surface of `models/modeling.py`, and these entry points are what that surface binds
+ * underneath (ctypes stub: 3d_vit_ensemble_b200/_lib.py).
+ * Each function cites the reference code whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes; all pointers are DEVICE pointers unless stated otherwise.
+ *   - ownership: the caller allocates every input, output, saved-for-backward buffer and
+ *     workspace.  The library owns no device memory.
+ *   - every call is asynchronous on `stream` (a cudaStream_t), never synchronises, never
+ *     uses the default stream implicitly and is CUDA-graph capturable.
+ *   - return 0 on success, negative on error; message via vit3d_last_error() (thread local).
+ *   - "token matrix": activations are row-major [M, H] with M = B*S rows (S = patches+1,
+ *     row b*S is the cls token of volume b) exactly as the reference's (B,S,H) tensors.
+ *   - precision modes (`prec`):
+ *        VIT3D_PREC_FP32  every contraction in fp32 FMA (any shape; the exact path)
+ *        VIT3D_PREC_TF32  tcgen05 kind::tf32, fp32 storage
+ *        VIT3D_PREC_BF16  tcgen05 kind::f16 (bf16 operands, fp32 accumulate in TMEM);
+ *                         GEMM operand activations are stored bf16, the residual stream,
+ *                         LayerNorm statistics, softmax and every gradient of a parameter fp32.
+ *     "act" below means: float for FP32/TF32, __nv_bfloat16 for BF16 (vit3d_act_bytes()).
+ *   - parameter gradients are ACCUMULATED (+=) into the buffers passed in.
+ */
+#ifndef VIT3D_H_
+#define VIT3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VIT3D_VERSION 100
+
+typedef void* vit3d_stream_t; /* cudaStream_t */
+
+enum { VIT3D_OK = 0, VIT3D_ERR_INVALID = -1, VIT3D_ERR_UNSUPPORTED = -2, VIT3D_ERR_CUDA = -3 };
+enum { VIT3D_PREC_FP32 = 0, VIT3D_PREC_TF32 = 1, VIT3D_PREC_BF16 = 2 };
+enum { VIT3D_ACT_NONE = 0, VIT3D_ACT_GELU = 1 };
+
+int vit3d_version(void);
+const char* vit3d_last_error(void);
+/* sm count and compute capability (major*10+minor) of the current device */
+int vit3d_device_info(int* sm_count, int* cc);
+/* number of kernels this library has launched in this process so far */
+unsigned long long vit3d_launch_count(void);
+/* bytes per "act" element for a precision mode */
+int vit3d_act_bytes(int prec);
+/* 1 if the tcgen05 path serves a [M,N,K] linear in this precision, else the fp32 FMA path is used */
+int vit3d_tc_supported(int prec, int M, int N, int K);
+
+/* ---------------------------------------------------------------- a1: Embeddings
+ * Conv3d(1->H, kernel=stride=(p0,p1,p2)) + flatten(2).transpose + cat(cls) + position add
+ * (modeling.py:153-156,162-173).  x is (B,1,X,Y,Z) fp32 contiguous. */
+
+/* bit-exact im2col permutation: patches[(b*P+p), (i*p1+j)*p2+z], p=(px*ny+py)*nz+pz */
+int vit3d_patch_gather(const float* x, float* patches, int B, int X, int Y, int Z, int p0, int p1, int p2,
+                       vit3d_stream_t stream);
+/* tokens[B,S,H] = cat(cls, patches @ w^T + bias) + pos ; w is the Conv3d weight viewed [H, p0*p1*p2].
+ * ws: >= vit3d_patch_embed_ws_bytes() scratch. */
+size_t vit3d_patch_embed_ws_bytes(int B, int X, int Y, int Z, int p0, int p1, int p2, int H, int prec);
+int vit3d_patch_embed_fwd(const float* x, const float* w, const float* bias, const float* cls, const float* pos,
+                          float* tokens, int B, int X, int Y, int Z, int p0, int p1, int p2, int H, int prec,
+                          void* ws, size_t ws_bytes, vit3d_stream_t stream);
+/* grads of a1 w.r.t. w, bias, cls, pos (accumulated) from dtokens[B,S,H] */
+int vit3d_patch_embed_bwd(const float* x, const float* dtokens, float* dw, float* dbias, float* dcls, float* dpos,
+                          int B, int X, int Y, int Z, int p0, int p1, int p2, int H, int prec,
+                          void* ws, size_t ws_bytes, vit3d_stream_t stream);
+
+/* ---------------------------------------------------------------- a4/a5: LayerNorm(eps, biased var, affine)
+ * nn.LayerNorm(H, eps=1e-6) at modeling.py:182-183,189,194,242,253.
+ * y is [M,H] in fp32 (y_bf16=0) or bf16 (y_bf16=1); mean/rstd [M] may be NULL in inference. */
+int vit3d_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_bf16, float* mean,
+                 float* rstd, int M, int H, float eps, vit3d_stream_t stream);
+/* dx = (dres ? dres : 0) + LN'(dy); dgamma/dbeta accumulated.  dy fp32 [M,H]. */
+int vit3d_ln_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                 const float* dres, float* dx, float* dgamma, float* dbeta, int M, int H, vit3d_stream_t stream);
+
+/* ---------------------------------------------------------------- nn.Linear (modeling.py:63-67,105-106,277,351)
+ * y[M,N] = act(x[M,K] @ w[N,K]^T + bias) (+ residual).  x/y/pre are "act" typed unless noted.
+ *   w        fp32 master weight [N,K];   w_lp  bf16 copy of w (BF16 mode, else NULL)
+ *   residual fp32 [M,N] or NULL (then y is "act"); with residual, y is fp32 (residual stream)
+ *   pre      optional [M,N] "act": pre-activation saved for backward (act==GELU)
+ *   ldx      row stride of x in elements (lets the head read rows b*S of the token matrix)
+ *   y_f32    force fp32 output even without residual (logits, dgrad into LayerNorm backward) */
+int vit3d_linear_fwd(const void* x, int ldx, int x_f32, const float* w, const void* w_lp, const float* bias,
+                     const float* residual, void* y, int y_f32, void* pre, int act, int M, int N, int K, int prec,
+                     vit3d_stream_t stream);
+/* dx[M,K] = dy[M,N] @ w[N,K]  (dx_f32: write fp32);  dw[N,K] += dy^T @ x ; db[N] += colsum(dy).
+ * Any of dx / dw / db may be NULL.  dy is "act" typed unless dy_f32. */
+int vit3d_linear_bwd(const void* dy, int dy_f32, const void* x, int ldx, int x_f32, const float* w, const void* w_lp,
+                     void* dx, int lddx, int dx_f32, float* dw, float* db, int M, int N, int K, int prec,
+                     vit3d_stream_t stream);
+
+/* ---------------------------------------------------------------- a2: scaled-dot-product attention core
+ * scores = q k^T / sqrt(D); probs = softmax(scores); ctx = probs v  (modeling.py:83-96).
+ * qkv is the packed [M, 3*k*D] matrix (q | k | v column blocks, head h at columns h*D..),
+ * ctx [M, k*D] "act"; probs (optional, vis=True) fp32 [B,k,S,S]. */
+int vit3d_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int heads, int D, int prec,
+                   vit3d_stream_t stream);
+/* dqkv from dctx (probabilities are recomputed from qkv) */
+int vit3d_attn_bwd(const void* dctx, const void* qkv, void* dqkv, int B, int S, int heads, int D, int prec,
+                   vit3d_stream_t stream);
+
+/* ---------------------------------------------------------------- elementwise pieces
+ * exact-erf GELU (modeling.py:52,107,120): a = gelu(h); da -> dh */
+int vit3d_gelu_fwd(const void* h, void* a, long long n, int prec, vit3d_stream_t stream);
+int vit3d_gelu_bwd(const void* da, const void* h, void* dh, long long n, int prec, vit3d_stream_t stream);
+/* Dropout(p) in training (modeling.py:121,123,174): y = x * keep / (1-p) (+ residual, same type, may be
+ * NULL: the x + Mlp(..) add of modeling.py:196) with a counter-based Philox mask keyed by
+ * (seed, site, step, element index); the same call on dy (residual NULL) gives dx. */
+int vit3d_dropout(const void* x, const void* residual, void* y, long long n, int is_f32, float p,
+                  unsigned long long seed, unsigned site, unsigned step, vit3d_stream_t stream);
+/* export the keep mask (1 byte per element) for mask-injection parity tests */
+int vit3d_dropout_mask(unsigned char* mask, long long n, float p, unsigned long long seed, unsigned site,
+                       unsigned step, vit3d_stream_t stream);
+/* y = x * mask / (1-p) with an explicit mask (parity mode) */
+int vit3d_dropout_masked(const void* x, const unsigned char* mask, const void* residual, void* y, long long n,
+                         int is_f32, float p, vit3d_stream_t stream);
+int vit3d_cast_f32_to_bf16(const float* x, void* y, long long n, vit3d_stream_t stream);
+int vit3d_cast_bf16_to_f32(const void* x, float* y, long long n, vit3d_stream_t stream);
+/* y += x (fp32) */
+int vit3d_add_inplace(float* y, const float* x, long long n, vit3d_stream_t stream);
+
+/* ---------------------------------------------------------------- a7: head loss
+ * BCEWithLogitsLoss(pos_weight)(logits.view(-1,1), labels.view(-1,1)), mean (modeling.py:283-286).
+ * pos_weight < 0 means None.  loss: 1 float.  dlogits = dloss * dL/dlogits (dloss: device scalar or NULL=1). */
+int vit3d_bce_logits_fwd(const float* logits, const float* labels, float pos_weight, float* loss, int n,
+                         vit3d_stream_t stream);
+int vit3d_bce_logits_bwd(const float* logits, const float* labels, float pos_weight, const float* dloss,
+                         float* dlogits, int n, vit3d_stream_t stream);
+
+/* ---------------------------------------------------------------- a9: meta-classifier
+ * out[B,C] = sigmoid(cat(member logits)[B,F] @ w[C,F]^T + b) (modeling.py:355-356) */
+int vit3d_meta_fwd(const float* feats, const float* w, const float* b, float* out, int B, int F, int C,
+                   vit3d_stream_t stream);
+int vit3d_meta_bwd(const float* dout, const float* out, const float* feats, const float* w, float* dfeats, float* dw,
+                   float* db, int B, int F, int C, vit3d_stream_t stream);
+
+/* ---------------------------------------------------------------- N1: optimizer steps on a flat fp32 arena
+ * torch.optim.SGD(momentum, weight_decay) (train_baseline_cv.py:111-114) and Adam (train_ensemble_whole_dataset.py:53)
+ * semantics of torch 2.x (first momentum step copies the gradient). */
+int vit3d_sgd_step(float* p, const float* g, float* mom, long long n, float lr, float momentum, float weight_decay,
+                   int first_step, float grad_scale, vit3d_stream_t stream);
+int vit3d_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, float grad_scale, vit3d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#endif /* VIT3D_H_ */
