@@ -62,8 +62,9 @@ int vit3d_tc_supported(int prec, int M, int N, int K) { return tc_linear_support
 // ------------------------------------------------------------------------- a1
 int vit3d_patch_gather(const float* x, float* patches, int B, int X, int Y, int Z, int p0, int p1, int p2,
                        vit3d_stream_t stream) {
-  V3_REQUIRE(x && patches, "patch_gather: null pointer");
   V3_REQUIRE(B >= 0 && p0 > 0 && p1 > 0 && p2 > 0 && X >= p0 && Y >= p1 && Z >= p2, "patch_gather: bad shape");
+  if (B == 0) return VIT3D_OK;
+  V3_REQUIRE(x && patches, "patch_gather: null pointer");
   return launch_patch_gather(x, patches, B, X, Y, Z, p0, p1, p2, as_stream(stream));
 }
 

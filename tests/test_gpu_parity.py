@@ -64,14 +64,15 @@ def test_forward_fp32_vs_oracle_and_golden(name):
     np.testing.assert_allclose(lu.cpu().numpy(), g["logits_unit"], atol=1e-3, rtol=0)
 
 
-def _grad_check(m, grads_oracle, rtol, what):
+def _grad_check(m, grads_oracle, rtol, what, atol_scale=1e-6):
+    # atol_scale * (largest gradient norm): the key.bias gradients are exactly 0 in exact arithmetic
     gscale = max(float(v.norm()) for v in grads_oracle.values())
     for k, p in m.named_parameters():
         assert p.grad is not None, k
         a, b = p.grad.detach().cpu(), grads_oracle[k]
         err = float((a - b).norm())
         ref = float(b.norm())
-        assert err <= rtol * ref + 1e-6 * gscale, (what, k, err, ref)
+        assert err <= rtol * ref + atol_scale * gscale, (what, k, err, ref)
 
 
 @pytest.mark.parametrize("name", ["tiny", "shipped", "shipped_p8", "conf5", "conf18"])
@@ -169,7 +170,8 @@ def test_grads_low_precision(name, prec):
     lo, go, _ = O.vit_loss_and_grads(sd, cfg, x, y, w, dtype=torch.float64)
     tol = LOGIT_TOL[prec]
     assert abs(float(loss) - float(lo)) < tol
-    _grad_check(m, {k: v.float() for k, v in go.items()}, 0.02 if prec == "tf32" else 0.08, f"{name}/{prec}")
+    _grad_check(m, {k: v.float() for k, v in go.items()}, 0.02 if prec == "tf32" else 0.08, f"{name}/{prec}",
+                atol_scale=2e-4)
 
 
 # ----------------------------------------------------------------------------- a9 ensemble
@@ -211,6 +213,11 @@ def test_submodules_standalone_fp32():
     blk.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
     blk.precision = blk.attn.precision = blk.ffn.precision = "fp32"
     blk.to(DEV).eval()
+    with torch.no_grad():
+        _standalone_checks(blk, cfg, sd, h, pre)
+
+
+def _standalone_checks(blk, cfg, sd, h, pre):
     out, wts = blk(h.to(DEV))
     ro, rp = O.block(sd, cfg, h, pre)
     np.testing.assert_allclose(out.cpu().numpy(), ro.numpy(), atol=2e-5)
