@@ -1,0 +1,252 @@
+// Fused softmax attention for the 65-token sequences of the 3D ViT (a2, modeling.py:83-96), bf16.
+//
+// One persistent CTA per SM walks over volumes.  The packed qkv rows of a volume (65 x 768 bf16,
+// contiguous in HBM) are pulled into shared memory with bulk async copies (UBLKCP, mbarrier
+// completion), double buffered so the next volume streams in while this one is computed.  Each warp
+// takes (head, 16-row tile) tasks: S = Q K^T with mma.sync.m16n8k16 (bf16, fp32 accumulate), the
+// softmax runs in registers with quad shuffles, P (bf16) feeds the P V mma straight from the
+// accumulator registers, the context tile overwrites the Q tile it came from in shared memory and the
+// whole [65 x 256] context block leaves with bulk async stores.  With vis=True the fp32 probabilities
+// (B,k,65,65) are written from registers.  HBM traffic per volume: 99.8 KB in, 33.3 KB out
+// (+ k*65*65*4 B of probabilities) - the kernel is bandwidth bound.
+#include "ptx.cuh"
+#include "tc.cuh"
+
+namespace vit3d {
+
+using namespace ptx;
+
+constexpr int AT_S = 65;           // tokens per volume
+constexpr int AT_A = 256;          // all-head size (heads * D)
+constexpr int AT_ROWB = 3 * AT_A * 2;       // 1536 bytes of qkv per token
+constexpr int AT_PITCH = AT_ROWB + 16;      // padded smem row pitch: conflict-free ldmatrix
+constexpr int AT_BUF = AT_S * AT_PITCH;     // 100,880 bytes per volume buffer
+constexpr int AT_THREADS = 256;
+constexpr int AT_SMEM = 2 * AT_BUF + 64 + 128;
+
+__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(sdst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(gdst)),
+               "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+template <int D>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, float* __restrict__ probs,
+                   int B, float scale_log2e) {
+  constexpr int HEADS = AT_A / D;
+  constexpr int KSTEPS = D / 16;      // k-steps of the Q K^T product
+  constexpr int NT = 10;              // key n-tiles of 8 (80 >= 65; tiles 8.. are partly / fully padding)
+  constexpr int DT = D / 8;           // output n-tiles of the P V product
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * AT_BUF);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  auto issue_load = [&](int b, int buf) {   // warp 0, all lanes
+    if (lane == 0) mbar_arrive_expect_tx(&full[buf], AT_S * AT_ROWB);
+    __syncwarp();
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(qkv) + (size_t)b * AT_S * AT_ROWB;
+    uint8_t* dst = smem + buf * AT_BUF;
+    for (int r = lane; r < AT_S; r += 32) bulk_g2s(dst + r * AT_PITCH, src + (size_t)r * AT_ROWB, AT_ROWB, &full[buf]);
+  };
+
+  if (warp == 0 && (int)blockIdx.x < B) issue_load(blockIdx.x, 0);
+
+  int it = 0;
+  for (int b = blockIdx.x; b < B; b += gridDim.x, ++it) {
+    const int buf = it & 1;
+    if (warp == 0) {
+      const int nb = b + gridDim.x;
+      bulk_wait_read0();                 // the context stores that read buffer buf^1 have drained
+      if (nb < B) issue_load(nb, buf ^ 1);
+    }
+    mbar_wait(&full[buf], (it >> 1) & 1);
+    const uint32_t sb = smem_u32(smem + buf * AT_BUF);
+
+    for (int task = warp; task < HEADS * 5; task += AT_THREADS / 32) {
+      const int h = task / 5, rt = task % 5;
+      const int r0 = rt * 16;
+      // ---- Q fragments (A operand), rows clamped to the last token
+      uint32_t qa[KSTEPS][4];
+      {
+        const int row = min(r0 + (lane & 7) + ((lane >> 3) & 1) * 8, AT_S - 1);
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const uint32_t addr = sb + row * AT_PITCH + (h * D + ks * 16 + (lane >> 4) * 8) * 2;
+          ldsm_x4(addr, qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+        }
+      }
+      // ---- S = Q K^T
+      float s[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        if (nt < 9) {
+          const int key = min(nt * 8 + (lane & 7), AT_S - 1);
+#pragma unroll
+          for (int ks = 0; ks < KSTEPS; ++ks) {
+            uint32_t b0, b1;
+            const uint32_t addr = sb + key * AT_PITCH + (AT_A + h * D + ks * 16 + ((lane >> 3) & 1) * 8) * 2;
+            ldsm_x2(addr, b0, b1);
+            mma_bf16(s[nt], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
+          }
+        }
+      }
+      // ---- softmax over the 65 valid keys (rows g and g+8 of the tile)
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 9; ++nt) {
+        const int c = nt * 8 + 2 * t;
+        if (c < AT_S) { mx0 = fmaxf(mx0, s[nt][0]); mx1 = fmaxf(mx1, s[nt][2]); }
+        if (c + 1 < AT_S) { mx0 = fmaxf(mx0, s[nt][1]); mx1 = fmaxf(mx1, s[nt][3]); }
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int c = nt * 8 + 2 * t;
+        const bool v0 = c < AT_S, v1 = c + 1 < AT_S;
+        s[nt][0] = v0 ? exp2f((s[nt][0] - mx0) * scale_log2e) : 0.f;
+        s[nt][1] = v1 ? exp2f((s[nt][1] - mx0) * scale_log2e) : 0.f;
+        s[nt][2] = v0 ? exp2f((s[nt][2] - mx1) * scale_log2e) : 0.f;
+        s[nt][3] = v1 ? exp2f((s[nt][3] - mx1) * scale_log2e) : 0.f;
+        sum0 += s[nt][0] + s[nt][1];
+        sum1 += s[nt][2] + s[nt][3];
+      }
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+      const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+      const int row0 = r0 + g, row1 = r0 + g + 8;
+      if (probs) {
+        float* p0 = probs + (((size_t)b * HEADS + h) * AT_S + row0) * AT_S;
+        float* p1 = probs + (((size_t)b * HEADS + h) * AT_S + row1) * AT_S;
+#pragma unroll
+        for (int nt = 0; nt < 9; ++nt) {
+          const int c = nt * 8 + 2 * t;
+          if (row0 < AT_S) {
+            if (c < AT_S) p0[c] = s[nt][0] * inv0;
+            if (c + 1 < AT_S) p0[c + 1] = s[nt][1] * inv0;
+          }
+          if (row1 < AT_S) {
+            if (c < AT_S) p1[c] = s[nt][2] * inv1;
+            if (c + 1 < AT_S) p1[c + 1] = s[nt][3] * inv1;
+          }
+        }
+      }
+      // ---- O = P V  (P from the accumulator registers; keys 65..79 carry p = 0)
+      float o[DT][4];
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) {
+        const uint32_t a0 = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+        const uint32_t a1 = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+        const uint32_t a2 = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        const uint32_t a3 = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        const int key = min(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, AT_S - 1);
+#pragma unroll
+        for (int dt = 0; dt < DT; ++dt) {
+          uint32_t b0, b1;
+          const uint32_t addr = sb + key * AT_PITCH + (2 * AT_A + h * D + dt * 8) * 2;
+          ldsm_x2_t(addr, b0, b1);
+          mma_bf16(o[dt], a0, a1, a2, a3, b0, b1);
+        }
+      }
+      // ---- context tile overwrites the Q tile it came from (only this task reads that block)
+      __syncwarp();
+      uint8_t* base = smem + buf * AT_BUF;
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) {
+        const int col = h * D + dt * 8 + 2 * t;
+        if (row0 < AT_S) *reinterpret_cast<uint32_t*>(base + row0 * AT_PITCH + col * 2) = pack_bf16(o[dt][0] * inv0, o[dt][1] * inv0);
+        if (row1 < AT_S) *reinterpret_cast<uint32_t*>(base + row1 * AT_PITCH + col * 2) = pack_bf16(o[dt][2] * inv1, o[dt][3] * inv1);
+      }
+    }
+    fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the bulk-copy engine
+    __syncthreads();
+    if (warp == 0) {
+      uint8_t* dst = reinterpret_cast<uint8_t*>(ctx) + (size_t)b * AT_S * AT_A * 2;
+      const uint8_t* src = smem + buf * AT_BUF;
+      for (int r = lane; r < AT_S; r += 32) bulk_s2g(dst + (size_t)r * AT_A * 2, src + r * AT_PITCH, AT_A * 2);
+      bulk_commit();
+    }
+  }
+  if (warp == 0) bulk_wait0();
+}
+
+bool tc_attn_supported(int S, int heads, int D) {
+  return S == AT_S && heads * D == AT_A && (D == 16 || D == 32 || D == 64);
+}
+
+template <int D>
+static int launch_attn(const void* qkv, void* ctx, float* probs, int B, cudaStream_t st) {
+  auto kern = attn_fwd_tc_kernel<D>;
+  V3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+  const int grid = B < sm_count() ? B : sm_count();
+  const float scale_log2e = 1.4426950408889634f / sqrtf((float)D);
+  kern<<<grid, AT_THREADS, AT_SMEM, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                           reinterpret_cast<__nv_bfloat16*>(ctx), probs, B, scale_log2e);
+  V3_LAUNCH_CHECK();
+  return VIT3D_OK;
+}
+
+int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int heads, int D, cudaStream_t st) {
+  if (!tc_attn_supported(S, heads, D)) V3_UNSUPPORTED("tc attention: unsupported shape S=%d heads=%d D=%d", S, heads, D);
+  if (B <= 0) return VIT3D_OK;
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(ctx) & 15)) {
+    set_error("tc attention: qkv/ctx must be 16-byte aligned");
+    return VIT3D_ERR_INVALID;
+  }
+  if (D == 16) return launch_attn<16>(qkv, ctx, probs, B, st);
+  if (D == 32) return launch_attn<32>(qkv, ctx, probs, B, st);
+  return launch_attn<64>(qkv, ctx, probs, B, st);
+}
+
+}  // namespace vit3d

@@ -383,7 +383,5 @@ int tc_patch_embed_fwd(const float*, const float*, const float*, const float*, f
                        int, int, cudaStream_t) {
   return VIT3D_ERR_UNSUPPORTED;
 }
-bool tc_attn_supported(int, int, int) { return false; }
-int tc_attn_fwd(const void*, void*, float*, int, int, int, int, cudaStream_t) { return VIT3D_ERR_UNSUPPORTED; }
 
 }  // namespace vit3d
