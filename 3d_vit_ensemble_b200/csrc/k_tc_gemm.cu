@@ -3,8 +3,8 @@
 //
 //   * persistent, warp-specialised CTA of 192 threads (1 CTA / SM):
 //       warp 0   TMA producer (one lane)        warp 1   TMEM allocator + tcgen05.mma issuer (one lane)
-//       warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> bias / GELU / residual /
-//                 position-embedding add -> global stores
+//       warps 2-9 epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> bias / GELU / residual /
+//                 position-embedding add, transposed through swizzled smem -> 128-byte-line global stores
 //   * tile 128 x BLOCK_N, BLOCK_K = 128 bytes of K (64 bf16 / 32 tf32); the accumulator is double
 //     buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   * kind::f16 (bf16 operands) or kind::tf32 (fp32 operands read directly, no conversion pass).
@@ -32,147 +32,257 @@ struct TcEpilogue {
 };
 
 constexpr int TC_BLOCK_M = 128;
-constexpr int TC_THREADS = 192;
+// warp 0 TMA, warp 1 MMA, then the epilogue warps (4 per TMEM lane quarter for BN >= 128, 2 for BN = 64)
+constexpr int tc_epi_warps(int bn) { return bn >= 128 ? 16 : 8; }
+constexpr int tc_threads(int bn) { return 64 + 32 * tc_epi_warps(bn); }
 
+// Two operand schedules share the kernel:
+//   streaming   : ring of STAGES x (A k-block 16 KB + B k-block BN*128 B); any K, optional split-K.
+//   B-stationary: when the whole [BN x K] weight slab fits in 128 KB (K <= 256 bf16 at BN = 256) a CTA
+//                 keeps ONE n-tile for its lifetime, loads that slab once and streams only A k-blocks
+//                 (ring of 4 x 16 KB).  L2->SM operand traffic per tile drops from 192 KB to 64 KB, which
+//                 is what bounds the K = 256 GEMMs (qkv, out-proj, fc1) at ~42 B/clk/SM of L2 bandwidth.
+constexpr int TC_SLAB_BYTES = 128 * 1024;
+constexpr int TC_STAT_STAGES = 4;
 template <int BN> struct TcCfg {
   static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int A_BYTES = TC_BLOCK_M * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OPER_BYTES = STAGES * STAGE_BYTES;     // == TC_SLAB_BYTES + TC_STAT_STAGES * A_BYTES
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_WARPS = tc_epi_warps(BN);
+  static constexpr int THREADS = tc_threads(BN);
+  static constexpr int EPI_BYTES = EPI_WARPS * 2048;   // one 32-row x 64-byte transpose tile per epilogue warp
+  static constexpr int SMEM_BYTES = OPER_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(OPER_BYTES >= TC_SLAB_BYTES + TC_STAT_STAGES * A_BYTES, "operand region too small for the stationary schedule");
 };
 
-__device__ __forceinline__ void epi_store_chunk(const TcEpilogue& ep, float (&v)[32], int m, int n, int N, bool full) {
-  // v: 32 consecutive columns n..n+31 of row m (fp32 accumulators)
-  const long long orow = ep.row_group > 0 ? (long long)m + m / ep.row_group + 1 : (long long)m;
-  if (full) {
-    if (ep.bias) {
+// ----------------------------------------------------------------------------- epilogue
+// fast GELU for bf16 outputs: x * sigmoid(2u), u = x (c0 + c1 x^2 + c2 x^4) fitted to the exact erf
+// GELU (max abs error 3e-5, far below the bf16 rounding of the result): 7 FMA-pipe ops + 2 MUFU.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float x2 = fminf(x * x, 100.f);                // the fitted polynomial is monotone up to |x| = 10
+  // -2*log2(e) * {0.797458471, 0.0370503451, -3.58732362e-4}
+  float p = fmaf(x2, 1.03506367e-3f, -0.106903009f);
+  p = fmaf(x2, p, -2.30099750f);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * p));          // exp(-2u)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return x * r;
+}
+
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// Each epilogue warp owns 32 accumulator rows (one TMEM lane quarter) x CW columns.  TMEM hands every
+// thread one ROW (tcgen05.ld 32x32b); rows are transposed through a 2 KB swizzled shared-memory tile
+// (32 rows x 64 bytes) so that global loads/stores are whole 32-byte sectors, 64 contiguous bytes per row.
+//   fp32 output : 16 columns per round; raw accumulators are staged, bias / position rows / GELU /
+//                 residual are applied in the coalesced phase (element-wise, layout does not matter).
+//   bf16 output : 32 columns per round; bias (+GELU) are applied in the row-owner phase, packed to bf16
+//                 and staged; the coalesced phase is a pure copy.
+// staging position of 16-byte chunk j of row r: r*64 + ((j ^ ((r >> 1) & 3)) << 4)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int CW, bool FAST_GELU>
+__device__ __forceinline__ void epilogue_rows(const TcEpilogue& ep, const CUtensorMap* tmC, const CUtensorMap* tmPre,
+                                              uint32_t taddr, uint32_t stage, int lane, int m_base, int n_base, int M,
+                                              int N) {
+  const uint32_t my_row = stage + lane * 64;
+  const int sw = (lane >> 1) & 3;
+  const int chunk = lane & 3, rsub = lane >> 2;       // coalesced phase: 4 lanes per row, 8 rows per instruction
+  if (ep.out_f32) {
+#pragma unroll 1
+    for (int c = 0; c < CW; c += 16) {
+      if (n_base + c >= N) break;
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(taddr + c, r);
+      const int col = n_base + c + chunk * 4;
+      const bool colok = col < N;
+      // issue every global read of this round before the TMEM wait / the stores (out may alias residual)
+      float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 res[4], radd[4];
+      if (colok) {
+        if (ep.bias) bias = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n + j));
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        for (int i = 0; i < 4; ++i) {
+          const int m = m_base + i * 8 + rsub;
+          res[i] = radd[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m < M) {
+            if (ep.residual) res[i] = __ldg(reinterpret_cast<const float4*>(ep.residual + (long long)m * N + col));
+            if (ep.rowadd)
+              radd[i] = __ldg(reinterpret_cast<const float4*>(ep.rowadd + (long long)((m % ep.row_group) + 1) * N + col));
+          }
+        }
       }
-    }
-    if (ep.rowadd) {
-      const float* ra = ep.rowadd + (long long)((m % ep.row_group) + 1) * N + n;
+      tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(ra + j));
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      for (int j = 0; j < 4; ++j) st_shared_v4(my_row + ((j ^ sw) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      __syncwarp();
+      if (colok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = i * 8 + rsub;
+          const int m = m_base + row;
+          if (m < M) {
+            const uint4 u = ld_shared_v4(stage + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+            float4 v = make_float4(__uint_as_float(u.x) + bias.x + radd[i].x, __uint_as_float(u.y) + bias.y + radd[i].y,
+                                   __uint_as_float(u.z) + bias.z + radd[i].z, __uint_as_float(u.w) + bias.w + radd[i].w);
+            const long long orow = ep.row_group > 0 ? (long long)m + m / ep.row_group + 1 : (long long)m;
+            float* o = reinterpret_cast<float*>(ep.out) + orow * N + col;
+            if (ep.atomic) {
+              atomicAdd(o, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w);
+            } else {
+              if (ep.pre) *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.pre) + orow * N + col) = v;
+              if (ep.act == VIT3D_ACT_GELU) { v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w); }
+              v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w;
+              *reinterpret_cast<float4*>(o) = v;
+            }
+          }
+        }
       }
+      __syncwarp();
     }
-    if (ep.atomic) {
-      float* o = reinterpret_cast<float*>(ep.out) + orow * N + n;
+  } else {
+    // bf16 output: 32 columns (64 B per row) per round, staged in the TMA SWIZZLE_64B layout and written
+    // with one bulk tensor store per round (rows >= M / columns >= N are clipped by the TMA unit).
+#pragma unroll 1
+    for (int c = 0; c < CW; c += 32) {
+      if (n_base + c >= N) break;
+      float v[32];
+      {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c, r);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j]);
-      return;
-    }
-    if (ep.pre) {
-      if (ep.out_f32) {
-        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.pre) + orow * N + n);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      }
+      if (ep.bias) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      } else {
-        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.pre) + orow * N + n);
+        for (int j = 0; j < 32; j += 4) {
+          if (n_base + c + j < N) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n_base + c + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+      }
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        // pass 0: pre-activation copy (training), pass 1: output
+        if (pass == 0 && ep.pre == nullptr) continue;
+        if (pass == 1 && ep.act == VIT3D_ACT_GELU) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
-          __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-          __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-          __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-          uint4 u;
-          u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-          u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-          o[j] = u;
+          for (int j = 0; j < 32; ++j) v[j] = FAST_GELU ? gelu_fast(v[j]) : gelu_f(v[j]);
+        }
+        if (lane == 0) bulk_store_wait_read();      // the previous round's store has finished reading the tile
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_shared_v4(my_row + ((j ^ sw) << 4), pack2_bf16(v[8 * j], v[8 * j + 1]), pack2_bf16(v[8 * j + 2], v[8 * j + 3]),
+                       pack2_bf16(v[8 * j + 4], v[8 * j + 5]), pack2_bf16(v[8 * j + 6], v[8 * j + 7]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(pass == 0 ? tmPre : tmC, stage, n_base + c, m_base);
+          bulk_store_commit();
         }
       }
     }
-    if (ep.act == VIT3D_ACT_GELU) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
-    }
-    if (ep.residual) {
-      const float4* r = reinterpret_cast<const float4*>(ep.residual + (long long)m * N + n);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b = __ldg(r + j);
-        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-      }
-    }
-    if (ep.out_f32) {
-      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + orow * N + n);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    } else {
-      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + orow * N + n);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
-        __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-        __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-        uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-        u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-        o[j] = u;
-      }
-    }
-    return;
-  }
-  // ragged right edge (N not a multiple of 32): element-wise
-#pragma unroll 1
-  for (int j = 0; j < 32; ++j) {
-    const int nn = n + j;
-    if (nn >= N) break;
-    float x = v[j];
-    if (ep.bias) x += ep.bias[nn];
-    if (ep.rowadd) x += ep.rowadd[(long long)((m % ep.row_group) + 1) * N + nn];
-    const long long oi = orow * N + nn;
-    if (ep.atomic) { atomicAdd(reinterpret_cast<float*>(ep.out) + oi, x); continue; }
-    if (ep.pre) {
-      if (ep.out_f32) reinterpret_cast<float*>(ep.pre)[oi] = x;
-      else reinterpret_cast<__nv_bfloat16*>(ep.pre)[oi] = __float2bfloat16(x);
-    }
-    if (ep.act == VIT3D_ACT_GELU) x = gelu_f(x);
-    if (ep.residual) x += ep.residual[(long long)m * N + nn];
-    if (ep.out_f32) reinterpret_cast<float*>(ep.out)[oi] = x;
-    else reinterpret_cast<__nv_bfloat16*>(ep.out)[oi] = __float2bfloat16(x);
   }
 }
 
+// work-item sequence of a CTA (identical in the producer, MMA and epilogue roles)
+struct TileIter {
+  int tiles_m, tiles_n, splits, total, w, tm, tn, split;
+  bool stat;
+  int cpn, g;
+  __device__ TileIter(bool stationary, int tiles_m_, int tiles_n_, int splits_)
+      : tiles_m(tiles_m_), tiles_n(tiles_n_), splits(splits_), stat(stationary) {
+    total = tiles_m * tiles_n * splits;
+    if (stat) {
+      tn = blockIdx.x % tiles_n;
+      g = blockIdx.x / tiles_n;
+      cpn = gridDim.x / tiles_n;
+      tm = g - cpn;
+      split = 0;
+    } else {
+      w = (int)blockIdx.x - (int)gridDim.x;
+    }
+  }
+  __device__ bool next() {
+    if (stat) {
+      tm += cpn;
+      return tm < tiles_m;
+    }
+    w += gridDim.x;
+    if (w >= total) return false;
+    split = w % splits;
+    const int tile = w / splits;
+    tn = tile % tiles_n;
+    tm = tile / tiles_n;
+    return true;
+  }
+};
+
 template <bool TF32, int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcEpilogue ep, int M,
-               int N, int K, int tiles_m, int tiles_n, int splits) {
+__global__ void __launch_bounds__(tc_threads(BN), 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmPre, TcEpilogue ep, int M,
+               int N, int K, int tiles_m, int tiles_n, int splits, int stationary) {
   using Cfg = TcCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
   constexpr int BLOCK_K = TF32 ? 32 : 64;   // 128 bytes of K per stage row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + STAGES;
-  uint64_t* tmem_full = bars + 2 * STAGES;
-  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint8_t* epi_stage = smem + Cfg::OPER_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + Cfg::EPI_BYTES);
+  constexpr int MAXST = 8;
+  uint64_t* full_bar = bars;                 // [MAXST]
+  uint64_t* empty_bar = bars + MAXST;        // [MAXST]
+  uint64_t* tmem_full = bars + 2 * MAXST;    // [2]
+  uint64_t* tmem_empty = bars + 2 * MAXST + 2;
+  uint64_t* slab_full = bars + 2 * MAXST + 4;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAXST + 5);
+
+  const bool stat = stationary != 0;
+  const int STAGES = stat ? TC_STAT_STAGES : Cfg::STAGES;
+  const int stage_bytes = stat ? Cfg::A_BYTES : Cfg::STAGE_BYTES;
+  uint8_t* ring = stat ? smem + TC_SLAB_BYTES : smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (K + BLOCK_K - 1) / BLOCK_K;
   const int kb_per = (nkb + splits - 1) / splits;
-  const int total = tiles_m * tiles_n * splits;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < MAXST; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 128);
+      mbar_init(&tmem_empty[b], 32 * Cfg::EPI_WARPS);
     }
+    mbar_init(slab_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
@@ -184,19 +294,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
+      TileIter ti(stat, tiles_m, tiles_n, splits);
+      if (stat && ti.g < tiles_m) {
+        mbar_arrive_expect_tx(slab_full, nkb * Cfg::B_BYTES);
+        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem + kb * Cfg::B_BYTES, &tmB, slab_full, kb * BLOCK_K, ti.tn * BN);
+      }
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const int split = w % splits, tile = w / splits;
-        const int tn = tile % tiles_n, tm = tile / tiles_n;
-        const int kb0 = split * kb_per, kb1 = min(nkb, kb0 + kb_per);
+      while (ti.next()) {
+        const int kb0 = ti.split * kb_per, kb1 = min(nkb, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, tm * TC_BLOCK_M);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, tn * BN);
+          uint8_t* sa = ring + stage * stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, ti.tm * TC_BLOCK_M);
+          if (!stat) tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, ti.tn * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -206,21 +318,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(TF32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16, TC_BLOCK_M, BN, 0, 0);
+      TileIter ti(stat, tiles_m, tiles_n, splits);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-        const int split = w % splits;
-        const int kb0 = split * kb_per, kb1 = min(nkb, kb0 + kb_per);
+      bool slab_ready = !stat;
+      for (; ti.next(); ++it) {
+        const int kb0 = ti.split * kb_per, kb1 = min(nkb, kb0 + kb_per);
         const int buf = it & 1;
         mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+        if (!slab_ready) { mbar_wait(slab_full, 0); slab_ready = true; }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint32_t sa = smem_u32(ring + stage * stage_bytes);
+          const uint32_t sb = stat ? smem_u32(smem + kb * Cfg::B_BYTES) : sa + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {   // 4 x 32 bytes of K per stage
             const uint64_t ad = make_smem_desc(sa + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
@@ -235,34 +349,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else {
-    // ===================================================== epilogue (warps 2..5)
+    // ===================================================== epilogue warps
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int part = (warp - 2) >> 2;       // which slice of the tile's columns
+    constexpr int CW = BN / (Cfg::EPI_WARPS / 4);
+    const uint32_t stage = smem_u32(epi_stage + (warp - 2) * 2048);
+    TileIter ti(stat, tiles_m, tiles_n, splits);
     int it = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-      const int tile = w / splits;
-      const int tn = tile % tiles_n, tm = tile / tiles_n;
+    for (; ti.next(); ++it) {
       const int buf = it & 1;
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
-      const int m = tm * TC_BLOCK_M + q * 32 + lane;
-      const int n0 = tn * BN;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        if (n0 + c >= N) break;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c, r);
-        tmem_ld_wait();
-        if (m < M) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epi_store_chunk(ep, v, m, n0 + c, N, n0 + c + 32 <= N);
-        }
-      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + part * CW;
+      epilogue_rows<CW, !TF32>(ep, &tmC, &tmPre, taddr, stage, lane, ti.tm * TC_BLOCK_M + q * 32, ti.tn * BN + part * CW,
+                               M, N);
       tc_fence_before();
       mbar_arrive(&tmem_empty[buf]);
     }
+    if (lane == 0) bulk_store_wait_all();   // bulk tensor stores must complete before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -287,19 +391,20 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D row-major [rows, cols] tensor, box = [box_rows, 128 bytes of columns], 128B swizzle, OOB -> 0
+// 2-D row-major [rows, cols] tensor map; box = [box_rows, box_cols]; swizzle 128B (operands, box_cols*elem
+// = 128 B) or 64B (bf16 output tiles, 64 B); out-of-bounds reads give 0, out-of-bounds writes are dropped.
 int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld_elems,
-                 int box_rows) {
+                 int box_rows, int box_cols, int swizzle_bytes) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return VIT3D_ERR_CUDA; }
-  struct Key { const void* p; long long r, c, ld; int e, b; };
+  struct Key { const void* p; long long r, c, ld; int e, br, bc, sw; };
   struct Hash { size_t operator()(const Key& k) const {
     size_t h = (size_t)k.p; h = h * 1000003u ^ (size_t)k.r; h = h * 1000003u ^ (size_t)k.c;
-    h = h * 1000003u ^ (size_t)k.ld; h = h * 1000003u ^ (size_t)(k.e * 1024 + k.b); return h; } };
+    h = h * 1000003u ^ (size_t)k.ld; h = h * 1000003u ^ (size_t)(((k.e * 512 + k.br) * 512 + k.bc) * 4 + k.sw / 64); return h; } };
   struct Eq { bool operator()(const Key& a, const Key& b) const {
-    return a.p == b.p && a.r == b.r && a.c == b.c && a.ld == b.ld && a.e == b.e && a.b == b.b; } };
+    return a.p == b.p && a.r == b.r && a.c == b.c && a.ld == b.ld && a.e == b.e && a.br == b.br && a.bc == b.bc && a.sw == b.sw; } };
   static thread_local std::unordered_map<Key, CUtensorMap, Hash, Eq> cache;
-  const Key key{ptr, rows, cols, ld_elems, elem_bytes, box_rows};
+  const Key key{ptr, rows, cols, ld_elems, elem_bytes, box_rows, box_cols, swizzle_bytes};
   auto itc = cache.find(key);
   if (itc != cache.end()) { *out = itc->second; return VIT3D_OK; }
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld_elems * elem_bytes) & 15)) {
@@ -308,11 +413,12 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long ro
   }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)(ld_elems * elem_bytes)};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return VIT3D_ERR_CUDA; }
   if (cache.size() > 2048) cache.clear();
   cache.emplace(key, *out);
@@ -320,8 +426,8 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long ro
 }
 
 template <bool TF32, int BN>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcEpilogue& ep, int M, int N, int K, int splits,
-                     cudaStream_t st) {
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
+                     const TcEpilogue& ep, int M, int N, int K, int splits, bool stationary, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   auto kern = tc_gemm_kernel<TF32, BN>;
   static thread_local int configured_dev = -1;
@@ -333,8 +439,14 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcEpilo
   }
   const int tiles_m = ceil_div(M, TC_BLOCK_M), tiles_n = ceil_div(N, BN);
   const int total = tiles_m * tiles_n * splits;
-  const int grid = total < sm_count() ? total : sm_count();
-  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, ep, M, N, K, tiles_m, tiles_n, splits);
+  const int sms = sm_count();
+  int grid = total < sms ? total : sms;
+  if (stationary) {
+    int cpn = sms / tiles_n;            // CTAs per n-tile
+    if (cpn > tiles_m) cpn = tiles_m;
+    grid = cpn * tiles_n;
+  }
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tp, ep, M, N, K, tiles_m, tiles_n, splits, stationary ? 1 : 0);
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
@@ -343,25 +455,41 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcEpilo
 int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const TcEpilogue& ep, int splits,
             cudaStream_t st) {
   const int eb = tf32 ? 4 : 2;
-  // pick the widest N tile that still gives every SM work
   const int sms = sm_count();
   const int tm = ceil_div(M, TC_BLOCK_M);
+  const int nkb = ceil_div(K, 128 / eb);
+  // widest N tile that still gives every SM work
   int bn = 256;
   if (N <= 64 || (long long)tm * ceil_div(N, 256) * splits < sms) bn = 128;
   if (N <= 64 || (bn == 128 && (long long)tm * ceil_div(N, 128) * splits < sms)) bn = 64;
-  CUtensorMap ta, tb;
-  int rc = make_tmap_2d(&ta, A, eb, M, K, K, TC_BLOCK_M);
+  // stationary-B schedule when the [bn x K] weight slab fits (shrink the tile once if that makes it fit)
+  auto fits = [&](int b) { return splits == 1 && (long long)nkb * b * 128 <= TC_SLAB_BYTES && ceil_div(N, b) <= sms; };
+  bool stationary = fits(bn);
+  if (!stationary && bn == 256 && fits(128)) { bn = 128; stationary = true; }
+  CUtensorMap ta, tb, tc, tp;
+  int rc = make_tmap_2d(&ta, A, eb, M, K, K, TC_BLOCK_M, 128 / eb, 128);
   if (rc != VIT3D_OK) return rc;
-  rc = make_tmap_2d(&tb, B, eb, N, K, K, bn);
+  rc = make_tmap_2d(&tb, B, eb, N, K, K, bn, 128 / eb, 128);
   if (rc != VIT3D_OK) return rc;
-  if (tf32) {
-    if (bn == 256) return launch_tc<true, 256>(ta, tb, ep, M, N, K, splits, st);
-    if (bn == 128) return launch_tc<true, 128>(ta, tb, ep, M, N, K, splits, st);
-    return launch_tc<true, 64>(ta, tb, ep, M, N, K, splits, st);
+  tc = ta;
+  tp = ta;
+  if (!ep.out_f32) {   // bf16 outputs leave through bulk tensor stores
+    if (ep.row_group > 0 || ep.atomic) { set_error("tc_gemm: bf16 output with row remap / atomics is not supported"); return VIT3D_ERR_INVALID; }
+    rc = make_tmap_2d(&tc, ep.out, 2, M, N, N, 32, 32, 64);
+    if (rc != VIT3D_OK) return rc;
+    if (ep.pre) {
+      rc = make_tmap_2d(&tp, ep.pre, 2, M, N, N, 32, 32, 64);
+      if (rc != VIT3D_OK) return rc;
+    }
   }
-  if (bn == 256) return launch_tc<false, 256>(ta, tb, ep, M, N, K, splits, st);
-  if (bn == 128) return launch_tc<false, 128>(ta, tb, ep, M, N, K, splits, st);
-  return launch_tc<false, 64>(ta, tb, ep, M, N, K, splits, st);
+  if (tf32) {
+    if (bn == 256) return launch_tc<true, 256>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
+    if (bn == 128) return launch_tc<true, 128>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
+    return launch_tc<true, 64>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
+  }
+  if (bn == 256) return launch_tc<false, 256>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
+  if (bn == 128) return launch_tc<false, 128>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
+  return launch_tc<false, 64>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
 }
 
 bool tc_linear_supported(int prec, int M, int N, int K) {
