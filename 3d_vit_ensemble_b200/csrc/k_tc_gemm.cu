@@ -29,6 +29,7 @@ struct TcEpilogue {
   int act = 0;
   int row_group = 0;                // >0: out row = m + m / row_group + 1
   int atomic = 0;                   // accumulate with fp32 atomics (split-K)
+  int vols_per_tile = 0;            // patch-embedding mode: volumes per 128-row tile
 };
 
 constexpr int TC_BLOCK_M = 128;
@@ -247,7 +248,7 @@ template <bool TF32, int BN>
 __global__ void __launch_bounds__(tc_threads(BN), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmPre, TcEpilogue ep, int M,
-               int N, int K, int tiles_m, int tiles_n, int splits, int stationary) {
+               int N, int K, int tiles_m, int tiles_n, int splits, int stationary, int patch_blocks) {
   using Cfg = TcCfg<BN>;
   constexpr int BLOCK_K = TF32 ? 32 : 64;   // 128 bytes of K per stage row
   extern __shared__ uint8_t smem_raw[];
@@ -268,7 +269,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* ring = stat ? smem + TC_SLAB_BYTES : smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int nkb = patch_blocks > 0 ? K : (K + BLOCK_K - 1) / BLOCK_K;   // patch mode passes the k-block count as K
   const int kb_per = (nkb + splits - 1) / splits;
 
   if (warp == 0 && lane == 0) {
@@ -307,8 +308,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = ring + stage * stage_bytes;
           mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, ti.tm * TC_BLOCK_M);
-          if (!stat) tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, ti.tn * BN);
+          if (patch_blocks > 0) {
+            // patch-embedding mode (a1): the A tile is gathered straight from the (B,1,X,Y,Z) volume by a 5-D
+            // box {32 floats of a patch row, ny patches, 1 row, nx patches, 128/P volumes}; k-block kb covers
+            // patch row i = kb / patch_blocks, floats [32*(kb % patch_blocks), +32) of that row (zero-filled
+            // past the row end in both operands).
+            const int i = kb / patch_blocks, c0 = (kb % patch_blocks) * 32;
+            tma_load_5d(sa, &tmA, &full_bar[stage], c0, 0, i, 0, ti.tm * ep.vols_per_tile);
+            tma_load_3d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], c0, i, ti.tn * BN);
+          } else {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, ti.tm * TC_BLOCK_M);
+            if (!stat) tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, ti.tn * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -427,7 +438,8 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long ro
 
 template <bool TF32, int BN>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
-                     const TcEpilogue& ep, int M, int N, int K, int splits, bool stationary, cudaStream_t st) {
+                     const TcEpilogue& ep, int M, int N, int K, int splits, bool stationary, cudaStream_t st,
+                     int patch_blocks = 0) {
   using Cfg = TcCfg<BN>;
   auto kern = tc_gemm_kernel<TF32, BN>;
   static thread_local int configured_dev = -1;
@@ -446,7 +458,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     if (cpn > tiles_m) cpn = tiles_m;
     grid = cpn * tiles_n;
   }
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tp, ep, M, N, K, tiles_m, tiles_n, splits, stationary ? 1 : 0);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tp, ep, M, N, K, tiles_m, tiles_n, splits, stationary ? 1 : 0,
+                                                      patch_blocks);
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
@@ -505,11 +518,65 @@ int tc_linear_fwd(const TcLinear& t, cudaStream_t st) {
   return tc_gemm(t.prec == VIT3D_PREC_TF32, t.x, t.w, t.M, t.N, t.K, ep, 1, st);
 }
 
-// placeholders until the dedicated kernels land
-bool tc_patch_embed_supported(int, int, int, int, int, int, int, int) { return false; }
-int tc_patch_embed_fwd(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int,
-                       int, int, cudaStream_t) {
-  return VIT3D_ERR_UNSUPPORTED;
+// ----------------------------------------------------------------------------- a1: patch embedding
+// Conv3d(kernel = stride = patch) as an im2col-by-TMA GEMM in TF32: the fp32 volume is read exactly once,
+// straight into the swizzled A tiles (no gather pass, no conversion pass); bias, position rows and the
+// "skip the cls row" output remap are fused in the epilogue.
+static int make_tmap_nd(CUtensorMap* out, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                        const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return VIT3D_ERR_CUDA; }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(rank %d) failed (%d)", rank, (int)r); return VIT3D_ERR_CUDA; }
+  return VIT3D_OK;
+}
+
+bool tc_patch_embed_supported(int B, int X, int Y, int Z, int p0, int p1, int p2, int H) {
+  if (B <= 0 || p2 != Z || X % p0 || Y % p1) return false;
+  const int nx = X / p0, ny = Y / p1, P = nx * ny;
+  const int inner = p1 * p2;                       // contiguous floats of one patch row
+  if (P > 128 || 128 % P) return false;            // whole volumes per 128-row tile
+  if (ny > 256 || nx > 256 || 128 / P > 256) return false;
+  if ((inner * 4) % 16 || (Y * Z * 4) % 16) return false;
+  return H % 64 == 0 && H >= 64;
+}
+
+int tc_patch_embed_fwd(const float* x, const float* w, const float* bias, const float* pos, float* tokens, int B, int X,
+                       int Y, int Z, int p0, int p1, int p2, int H, cudaStream_t st) {
+  if (!tc_patch_embed_supported(B, X, Y, Z, p0, p1, p2, H)) V3_UNSUPPORTED("tc patch embedding: unsupported geometry");
+  const int nx = X / p0, ny = Y / p1, P = nx * ny, inner = p1 * p2;
+  const int vpt = 128 / P;
+  const int pblocks = ceil_div(inner, 32);
+  const int nkb = p0 * pblocks;
+  const int M = B * P, N = H;
+  const int sms = sm_count();
+  const int tm = ceil_div(M, TC_BLOCK_M);
+  int bn = 256;
+  if (N % 256 || (long long)tm * (N / 256) < sms) bn = 128;
+  if (N % 128 || (bn == 128 && (long long)tm * (N / 128) < sms)) bn = 64;
+  CUtensorMap ta, tb;
+  {
+    // x viewed (innermost first): [inner floats][ny patches][p0 rows][nx patches][B volumes]
+    cuuint64_t dims[5] = {(cuuint64_t)inner, (cuuint64_t)ny, (cuuint64_t)p0, (cuuint64_t)nx, (cuuint64_t)B};
+    cuuint64_t str[4] = {(cuuint64_t)inner * 4, (cuuint64_t)Y * Z * 4, (cuuint64_t)p0 * Y * Z * 4, (cuuint64_t)X * Y * Z * 4};
+    cuuint32_t box[5] = {32, (cuuint32_t)ny, 1, (cuuint32_t)nx, (cuuint32_t)vpt};
+    int rc = make_tmap_nd(&ta, x, 5, dims, str, box);
+    if (rc != VIT3D_OK) return rc;
+    // w viewed: [inner floats][p0 rows][H filters]
+    cuuint64_t wd[3] = {(cuuint64_t)inner, (cuuint64_t)p0, (cuuint64_t)H};
+    cuuint64_t ws[2] = {(cuuint64_t)inner * 4, (cuuint64_t)p0 * inner * 4};
+    cuuint32_t wb[3] = {32, 1, (cuuint32_t)bn};
+    rc = make_tmap_nd(&tb, w, 3, wd, ws, wb);
+    if (rc != VIT3D_OK) return rc;
+  }
+  TcEpilogue ep;
+  ep.bias = bias; ep.rowadd = pos; ep.row_group = P; ep.out = tokens; ep.out_f32 = 1; ep.vols_per_tile = vpt;
+  if (bn == 256) return launch_tc<true, 256>(ta, tb, ta, ta, ep, M, N, nkb, 1, false, st, pblocks);
+  if (bn == 128) return launch_tc<true, 128>(ta, tb, ta, ta, ep, M, N, nkb, 1, false, st, pblocks);
+  return launch_tc<true, 64>(ta, tb, ta, ta, ep, M, N, nkb, 1, false, st, pblocks);
 }
 
 }  // namespace vit3d

@@ -56,3 +56,29 @@ def test_tc_linear_matches_fp64(prec, shape, mode):
     if pre is not None:
         errp = float((pre.double() - ref_pre).abs().max())
         assert errp <= tol, (errp, tol)
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 37])
+@pytest.mark.parametrize("H", [256, 64])
+def test_tc_patch_embedding_matches_oracle(B, H):
+    """TMA-im2col TF32 patch embedding (+bias, +position rows, cls rows) vs the fp64 oracle."""
+    from oracle import vit3d_oracle as O
+    from vit3d_b200.models.modeling import Embeddings
+    cfg = vit3d_b200.get_config(16, 128, 1, H, 4)
+    sd = O.init_state_dict(cfg, seed=5)
+    pre = "transformer.embeddings."
+    emb = Embeddings(cfg, 128)
+    emb.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+    emb.precision = "bf16"
+    emb.to(DEV).eval()
+    x = O.synth_volumes(B, seed=B)
+    with torch.no_grad():
+        got = emb(x.to(DEV)).cpu().double()
+    ref = O.embeddings({k: v.double() for k, v in sd.items()}, cfg, x.double())
+    scale = float(ref.abs().max())
+    err = float((got - ref).abs().max())
+    assert got.shape == ref.shape and np.isfinite(err)
+    assert err <= 2e-3 * scale, (err, scale)       # tf32 operands (10-bit mantissa), K = 1280
+    # cls rows are exact fp32 adds
+    cls_ref = (sd[pre + "cls_token"][0, 0] + sd[pre + "position_embeddings"][0, 0]).double()
+    assert float((got[:, 0] - cls_ref).abs().max()) < 1e-6
