@@ -1,0 +1,253 @@
+"""Multi-GPU execution of the path on one 8xB200 box: one process per GPU, torch.distributed (NCCL over
+NVLink 5 / NVSwitch; gloo in the CPU tests).  SURVEY.md §8e.
+
+  * inference of one ViT      - volumes are independent: shard the batch, no data-path collective.
+  * data-parallel training    - `GradReducer`: parameters' gradients live in ONE flat fp32 arena; a bucket
+                                (one encoder Block, the embeddings, the head) is all-reduced as soon as
+                                autograd has produced its last gradient, on a side stream, overlapping the
+                                rest of backward.  `global_pos_weight` makes the per-batch class weight
+                                (train_baseline_cv.py:168-169) that of the GLOBAL batch.
+  * stacking ensemble         - `ShardedEnsemble`: the (member, volume) work list is cut into world_size
+                                contiguous chunks of equal FLOPs (3 members do not divide 2/4/8 GPUs), each
+                                rank runs its chunk, one all-gather of the (B,1) member logits rebuilds the
+                                (B, m) matrix everywhere and the 3->1 meta-classifier runs redundantly.
+  * CV / bootstrap sweep      - `pack_jobs`: independent jobs, replicas only, no collective.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+# ----------------------------------------------------------------------------- DP training
+def global_pos_weight(labels: torch.Tensor, group=None) -> Optional[torch.Tensor]:
+    """sklearn 'balanced' class-weight ratio n_neg/n_pos (train_baseline_cv.py:168-169) computed over the
+    global batch (one 2-float all-reduce), so DP-N equals single-GPU training on the concatenated batch."""
+    y = labels.reshape(-1).float()
+    cnt = torch.stack([y.sum(), torch.tensor(float(y.numel()), device=y.device)]).to(torch.float64)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(cnt, group=group)
+    n_pos, n = float(cnt[0]), float(cnt[1])
+    if n_pos == 0 or n_pos == n:
+        return None
+    return torch.tensor((n - n_pos) / n_pos, dtype=torch.float64)
+
+
+class GradReducer:
+    """Flat-arena gradient all-reduce with per-bucket overlap.
+
+    Usage per step::
+
+        reducer.prepare()                 # zero the arena and point every p.grad into it
+        loss = model(x, y, w); loss.backward()
+        reducer.finish()                  # wait for the in-flight buckets; grads are now the global mean
+        optimizer.step()
+
+    Buckets are ordered as backward produces them (head first, embeddings last)."""
+
+    def __init__(self, model: torch.nn.Module, group=None, bucket_of: Optional[Callable[[str], str]] = None,
+                 overlap: bool = True, arena=None):
+        """`arena`: an `optim.FlatArena` (e.g. `FusedSGD(...).arena`) to share its flat gradient buffer;
+        otherwise the reducer allocates its own.  Buckets are runs of consecutive parameters (registration
+        order) with the same bucket key, so each bucket is one contiguous slice of the arena."""
+        self.model = model
+        self.group = group
+        self.overlap = overlap
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        if not named:
+            raise ValueError("model has no trainable parameters")
+        dev = named[0][1].device
+        bucket_of = bucket_of or self.default_bucket
+        total = sum(p.numel() for _, p in named)
+        if arena is not None:
+            if [id(p) for p in arena.params] != [id(p) for _, p in named]:
+                raise ValueError("arena and model parameters differ")
+            self.flat = arena.flat_grad
+        else:
+            self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.arena = arena
+        self.views = {}
+        self.ranges = {}
+        self.bucket_names = []
+        self._bucket_params = {}
+        self._param_bucket = {}
+        off = 0
+        for n, p in named:
+            key = bucket_of(n)
+            if not self.bucket_names or not self.bucket_names[-1].startswith(key + "#"):
+                self.bucket_names.append(f"{key}#{len(self.bucket_names)}")
+                self.ranges[self.bucket_names[-1]] = (off, off)
+                self._bucket_params[self.bucket_names[-1]] = []
+            b = self.bucket_names[-1]
+            self.views[n] = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+            self.ranges[b] = (self.ranges[b][0], off)
+            self._bucket_params[b].append(p)
+            self._param_bucket[id(p)] = b
+        self._pending = {}
+        self._named = named
+        self._handles: List = []
+        self._stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for _, p in named]
+
+    @staticmethod
+    def default_bucket(name: str) -> str:
+        parts = name.split(".")
+        if "layer" in parts:
+            i = parts.index("layer")
+            return ".".join(parts[:i + 2])          # one bucket per encoder Block
+        if "embeddings" in parts:
+            return "embeddings"
+        return "head+norm"
+
+    def prepare(self):
+        self.flat.zero_()
+        for n, p in self._named:
+            p.grad = self.views[n]
+        self._pending = {b: len(ps) for b, ps in self._bucket_params.items()}
+        self._handles = []
+
+    def _on_grad(self, p):
+        b = self._param_bucket[id(p)]
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and self.overlap:
+            self._launch(b)
+
+    def _launch(self, b):
+        _, ws = world()
+        if ws <= 1:
+            return
+        s, e = self.ranges[b]
+        chunk = self.flat[s:e]
+        if self._stream is not None:
+            self._stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._stream):
+                h = dist.all_reduce(chunk, group=self.group, async_op=True)
+        else:
+            h = dist.all_reduce(chunk, group=self.group, async_op=True)
+        self._handles.append(h)
+
+    def finish(self, scale: bool = True):
+        """Waits for every bucket.  scale=True divides by world_size here (plain torch optimizers);
+        scale=False leaves the SUM in the arena for a fused optimizer's `grad_scale=1/world_size`."""
+        _, ws = world()
+        if ws <= 1:
+            return
+        if not self.overlap:
+            self._handles.append(dist.all_reduce(self.flat, group=self.group, async_op=True))
+        else:
+            for b, left in self._pending.items():
+                if left != 0:          # parameters without a gradient this step (unused): reduce anyway
+                    self._launch(b)
+        for h in self._handles:
+            h.wait()
+        if self._stream is not None:
+            torch.cuda.current_stream().wait_stream(self._stream)
+        if scale:
+            self.flat.mul_(1.0 / ws)
+        self._handles = []
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+
+
+# ----------------------------------------------------------------------------- ensemble sharding
+def partition_work(costs: Sequence[float], batch: int, parts: int) -> List[List[Tuple[int, int, int]]]:
+    """Cut the (member, volume) work list - member j's `batch` volumes cost `costs[j]` each, members laid
+    end to end - into `parts` contiguous chunks of (nearly) equal cost.  Returns, per part, a list of
+    (member, b0, b1) slices.  Every (member, volume) pair appears in exactly one part."""
+    total = float(sum(costs)) * batch
+    bounds = [total * r / parts for r in range(parts + 1)]
+    out: List[List[Tuple[int, int, int]]] = [[] for _ in range(parts)]
+    # position of pair (j, b) on the cost axis: sum_{i<j} costs[i]*batch + b*costs[j]
+    cuts = []   # integer pair index boundaries
+    flat_prefix = [0.0]
+    for c in costs:
+        flat_prefix.append(flat_prefix[-1] + c * batch)
+    for r in range(parts + 1):
+        t = bounds[r]
+        j = 0
+        while j < len(costs) - 1 and flat_prefix[j + 1] <= t:
+            j += 1
+        b = int(round((t - flat_prefix[j]) / costs[j])) if costs[j] > 0 else 0
+        b = max(0, min(batch, b))
+        cuts.append(j * batch + b)
+    cuts[0], cuts[-1] = 0, len(costs) * batch
+    for r in range(parts):
+        lo, hi = cuts[r], max(cuts[r], cuts[r + 1])
+        while lo < hi:
+            j = lo // batch
+            b0 = lo - j * batch
+            b1 = min(batch, b0 + (hi - lo))
+            out[r].append((j, b0, b1))
+            lo += b1 - b0
+    return out
+
+
+class ShardedEnsemble:
+    """TransformerEnsemble.forward (modeling.py:353-356) with members x batch-slices spread over the ranks.
+
+    `ensemble` is a `TransformerEnsemble` whose members all live on this rank's device (weights are small:
+    <= 60 MB per member); every rank receives the same input batch `x`."""
+
+    def __init__(self, ensemble, costs: Optional[Sequence[float]] = None, group=None):
+        self.ensemble = ensemble
+        self.group = group
+        m = len(ensemble.transformers)
+        self.costs = list(costs) if costs is not None else [1.0] * m
+
+    @torch.no_grad()
+    def member_logits(self, x: torch.Tensor) -> torch.Tensor:
+        rank, ws = world()
+        B = x.shape[0]
+        m = len(self.ensemble.transformers)
+        parts = partition_work(self.costs, B, ws)
+        maxlen = max(sum(b1 - b0 for _, b0, b1 in p) for p in parts)
+        mine = torch.zeros(max(maxlen, 1), device=x.device, dtype=torch.float32)
+        off = 0
+        for j, b0, b1 in parts[rank]:
+            if b1 > b0:
+                lg = self.ensemble.transformers[j](x[b0:b1])[0]
+                mine[off:off + (b1 - b0)] = lg.reshape(-1).float()
+                off += b1 - b0
+        if ws > 1:
+            gathered = torch.empty(ws * mine.numel(), device=x.device, dtype=torch.float32)
+            dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        else:
+            gathered = mine
+        out = torch.empty(B, m, device=x.device, dtype=torch.float32)
+        for r, p in enumerate(parts):
+            off = r * mine.numel()
+            for j, b0, b1 in p:
+                out[b0:b1, j] = gathered[off:off + (b1 - b0)]
+                off += b1 - b0
+        return out
+
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        from . import functional as F
+        feats = self.member_logits(x)
+        return F.MetaFn.apply(feats, self.ensemble.classifier.weight, self.ensemble.classifier.bias)
+
+
+# ----------------------------------------------------------------------------- sweep packing
+def pack_jobs(costs: Sequence[float], n_workers: int) -> List[List[int]]:
+    """Longest-processing-time-first packing of independent jobs (the 18 configs x folds of
+    train_baseline_cv.py, or bootstrap replicas) onto workers; returns job indices per worker."""
+    order = sorted(range(len(costs)), key=lambda i: -costs[i])
+    load = [0.0] * n_workers
+    out: List[List[int]] = [[] for _ in range(n_workers)]
+    for i in order:
+        w = min(range(n_workers), key=lambda k: load[k])
+        out[w].append(i)
+        load[w] += costs[i]
+    return out

@@ -52,20 +52,27 @@ def _c(t):
 # bf16 shadow copies of fp32 master weights (parameters only), refreshed when the parameter
 # changes (optimizer step / load_state_dict bump _version, .to() changes data_ptr).  Keyed by the
 # parameter object itself so that a freed-and-reallocated address can never alias a stale copy.
-_LP_CACHE = {}   # id(param) -> (weakref(param), version, data_ptr, bf16 copy)
+_LP_CACHE = {}   # id(param) -> (weakref(param), version, data_ptr, bf16 copy, epoch)
+
+
+def invalidate_weight_shadows() -> None:
+    """Call after weights were modified by a kernel torch does not know about (fused optimizers)."""
+    _STATE["epoch"] = _STATE.get("epoch", 0) + 1
 
 
 def lp_weight(w: torch.Tensor) -> torch.Tensor:
     cacheable = isinstance(w, torch.nn.Parameter)
     if cacheable:
         ent = _LP_CACHE.get(id(w))
-        if ent is not None and ent[0]() is w and ent[1] == w._version and ent[2] == w.data_ptr():
+        if (ent is not None and ent[0]() is w and ent[1] == w._version and ent[2] == w.data_ptr()
+                and ent[4] == _STATE.get("epoch", 0)):
             return ent[3]
     out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
     call("vit3d_cast_f32_to_bf16", ptr(w.detach()), ptr(out), w.numel(), stream())
     if cacheable:
         key = id(w)
-        _LP_CACHE[key] = (weakref.ref(w, lambda _r, key=key: _LP_CACHE.pop(key, None)), w._version, w.data_ptr(), out)
+        _LP_CACHE[key] = (weakref.ref(w, lambda _r, key=key: _LP_CACHE.pop(key, None)), w._version, w.data_ptr(), out,
+                          _STATE.get("epoch", 0))
     return out
 
 
