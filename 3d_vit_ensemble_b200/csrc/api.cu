@@ -84,7 +84,10 @@ int vit3d_patch_embed_fwd(const float* x, const float* w, const float* bias, con
   cudaStream_t st = as_stream(stream);
   const int P = (X / p0) * (Y / p1) * (Z / p2), Kp = p0 * p1 * p2, S = P + 1;
   if (B == 0) return VIT3D_OK;
-  if (prec != VIT3D_PREC_FP32 && tc_patch_embed_supported(B, X, Y, Z, p0, p1, p2, H)) {
+  // BF16 mode: TF32 tensor-core embedding straight from the volume (5e-4 relative error, far inside the
+  // bf16 budget).  TF32 mode is the 1e-3-logit accuracy mode: the raw input cannot be pre-rounded (the
+  // tensor core truncates it to 10 mantissa bits), so it keeps the exact fp32 gather + FMA embedding.
+  if (prec == VIT3D_PREC_BF16 && tc_patch_embed_supported(B, X, Y, Z, p0, p1, p2, H)) {
     int rc = tc_patch_embed_fwd(x, w, bias, pos, tokens, B, X, Y, Z, p0, p1, p2, H, st);
     if (rc != VIT3D_OK) return rc;
     return launch_cls_rows(cls, pos, tokens, B, S, H, st);
@@ -160,7 +163,7 @@ int vit3d_linear_fwd(const void* x, int ldx, int x_f32, const float* w, const vo
   if (prec != VIT3D_PREC_FP32 && tc_linear_supported(prec, M, N, K) && (prec == VIT3D_PREC_TF32 ? xf : !xf) &&
       (prec == VIT3D_PREC_TF32 || w_lp) && ldx == K) {
     TcLinear t;
-    t.x = x; t.w = prec == VIT3D_PREC_BF16 ? w_lp : (const void*)w; t.bias = bias; t.residual = residual;
+    t.x = x; t.w = w_lp ? w_lp : (const void*)w; t.bias = bias; t.residual = residual;
     t.y = y; t.y_f32 = yf; t.pre = pre; t.act = act; t.M = M; t.N = N; t.K = K; t.prec = prec;
     return tc_linear_fwd(t, st);
   }
@@ -221,7 +224,7 @@ int vit3d_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int h
   V3_REQUIRE(B >= 0 && S > 0 && heads > 0 && D > 0, "attn_fwd: bad shape");
   cudaStream_t st = as_stream(stream);
   if (prec == VIT3D_PREC_BF16 && tc_attn_supported(S, heads, D)) return tc_attn_fwd(qkv, ctx, probs, B, S, heads, D, st);
-  return launch_attn_fwd_generic(qkv, act_f32(prec), ctx, probs, B, S, heads, D, st);
+  return launch_attn_fwd_generic(qkv, act_f32(prec), ctx, probs, B, S, heads, D, prec == VIT3D_PREC_TF32, st);
 }
 int vit3d_attn_bwd(const void* dctx, const void* qkv, void* dqkv, int B, int S, int heads, int D, int prec,
                    vit3d_stream_t stream) {
@@ -257,6 +260,10 @@ int vit3d_dropout_masked(const void* x, const unsigned char* mask, const void* r
 int vit3d_cast_f32_to_bf16(const float* x, void* y, long long n, vit3d_stream_t stream) {
   V3_REQUIRE(x && y && n >= 0, "cast: bad argument");
   return launch_cast(x, 1, y, 0, n, as_stream(stream));
+}
+int vit3d_round_tf32(const float* x, float* y, long long n, vit3d_stream_t stream) {
+  V3_REQUIRE(x && y && n >= 0, "round_tf32: bad argument");
+  return launch_round_tf32(x, y, n, as_stream(stream));
 }
 int vit3d_cast_bf16_to_f32(const void* x, float* y, long long n, vit3d_stream_t stream) {
   V3_REQUIRE(x && y && n >= 0, "cast: bad argument");

@@ -59,6 +59,14 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// round-to-nearest fp32 -> tf32 (10-bit mantissa) kept in an fp32 container.  tcgen05 kind::tf32 ignores
+// the low 13 mantissa bits (truncation); pre-rounding GEMM operands halves the error and removes its bias.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 // exact (erf) GELU, as torch.nn.functional.gelu default (modeling.py:52,107)
 __device__ __forceinline__ float gelu_f(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));

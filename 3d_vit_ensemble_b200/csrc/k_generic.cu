@@ -219,7 +219,7 @@ int launch_gather_patch_rows(const float* dtok, float* out, int B, int P, int H,
 // One warp per row.  Rows with H <= 32*LN_MAXV live in registers, wider rows are re-read.
 constexpr int LN_MAXV = 8;
 
-template <bool OUT_BF16>
+template <int OUT_MODE>   // 0 fp32, 1 bf16, 2 fp32 rounded to tf32
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, void* __restrict__ y,
                                                      float* __restrict__ mean, float* __restrict__ rstd, int M, int H,
@@ -264,15 +264,15 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
       const int c = lane + 32 * i;
       if (c < H) {
         const float o = (v[i] - mu) * rs * gamma[c] + beta[c];
-        if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(y)[(long long)row * H + c] = __float2bfloat16(o);
-        else reinterpret_cast<float*>(y)[(long long)row * H + c] = o;
+        if (OUT_MODE == 1) reinterpret_cast<__nv_bfloat16*>(y)[(long long)row * H + c] = __float2bfloat16(o);
+        else reinterpret_cast<float*>(y)[(long long)row * H + c] = OUT_MODE == 2 ? round_tf32(o) : o;
       }
     }
   } else {
     for (int c = lane; c < H; c += 32) {
       const float o = (xr[c] - mu) * rs * gamma[c] + beta[c];
-      if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(y)[(long long)row * H + c] = __float2bfloat16(o);
-      else reinterpret_cast<float*>(y)[(long long)row * H + c] = o;
+      if (OUT_MODE == 1) reinterpret_cast<__nv_bfloat16*>(y)[(long long)row * H + c] = __float2bfloat16(o);
+      else reinterpret_cast<float*>(y)[(long long)row * H + c] = OUT_MODE == 2 ? round_tf32(o) : o;
     }
   }
 }
@@ -281,8 +281,9 @@ int launch_ln_fwd(const float* x, const float* g, const float* b, void* y, int y
   if (M <= 0) return VIT3D_OK;
   const int rows_per_block = 8;
   const int blocks = ceil_div(M, rows_per_block);
-  if (y_bf16) ln_fwd_kernel<true><<<blocks, 256, 0, st>>>(x, g, b, y, mean, rstd, M, H, eps);
-  else ln_fwd_kernel<false><<<blocks, 256, 0, st>>>(x, g, b, y, mean, rstd, M, H, eps);
+  if (y_bf16 == 1) ln_fwd_kernel<1><<<blocks, 256, 0, st>>>(x, g, b, y, mean, rstd, M, H, eps);
+  else if (y_bf16 == 2) ln_fwd_kernel<2><<<blocks, 256, 0, st>>>(x, g, b, y, mean, rstd, M, H, eps);
+  else ln_fwd_kernel<0><<<blocks, 256, 0, st>>>(x, g, b, y, mean, rstd, M, H, eps);
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
@@ -382,7 +383,7 @@ constexpr int ATT_MAXJ = 9;  // S <= 288 (the as-shipped patch-8 models have S =
 
 __global__ void __launch_bounds__(256) attn_fwd_generic_kernel(const void* __restrict__ qkv, int f32,
                                                                void* __restrict__ ctx, float* __restrict__ probs, int B,
-                                                               int S, int heads, int D, float scale) {
+                                                               int S, int heads, int D, float scale, int round_out) {
   extern __shared__ float sm[];
   const int A = heads * D;
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
@@ -441,7 +442,7 @@ __global__ void __launch_bounds__(256) attn_fwd_generic_kernel(const void* __res
     for (int d = lane; d < D; d += 32) {
       float acc = 0.f;
       for (int j = 0; j < S; ++j) acc = fmaf(p[j], Vs[j * D + d], acc);
-      st_any(ctx, ((long long)b * S + i) * A + h * D + d, f32, acc);
+      st_any(ctx, ((long long)b * S + i) * A + h * D + d, f32, round_out ? round_tf32(acc) : acc);
     }
     __syncwarp();
   }
@@ -451,7 +452,7 @@ size_t attn_generic_smem(int S, int D, int nwarps, bool bwd) {
   return sizeof(float) * ((size_t)6 * S * D + (size_t)2 * nwarps * S);
 }
 int launch_attn_fwd_generic(const void* qkv, int f32, void* ctx, float* probs, int B, int S, int heads, int D,
-                            cudaStream_t st) {
+                            int round_out, cudaStream_t st) {
   if (B <= 0) return VIT3D_OK;
   if (S > 32 * ATT_MAXJ) V3_UNSUPPORTED("generic attention supports S <= %d (got %d)", 32 * ATT_MAXJ, S);
   const int threads = 256;
@@ -459,7 +460,8 @@ int launch_attn_fwd_generic(const void* qkv, int f32, void* ctx, float* probs, i
   if (smem > 200 * 1024) V3_UNSUPPORTED("generic attention: S*D too large for shared memory (S=%d D=%d)", S, D);
   if (smem > 48 * 1024)
     V3_CUDA(cudaFuncSetAttribute(attn_fwd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  attn_fwd_generic_kernel<<<B * heads, threads, smem, st>>>(qkv, f32, ctx, probs, B, S, heads, D, 1.0f / sqrtf((float)D));
+  attn_fwd_generic_kernel<<<B * heads, threads, smem, st>>>(qkv, f32, ctx, probs, B, S, heads, D, 1.0f / sqrtf((float)D),
+                                                            round_out);
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
@@ -639,6 +641,12 @@ int launch_dropout_masked(const void* x, const unsigned char* mask, const void* 
 int launch_cast(const void* x, int x_f32, void* y, int y_f32, long long n, cudaStream_t st) {
   if (n <= 0) return VIT3D_OK;
   ew_kernel<<<ew_blocks(n), 256, 0, st>>>(n, [=] __device__(long long i) { st_any(y, i, y_f32, ld_any(x, i, x_f32)); });
+  V3_LAUNCH_CHECK();
+  return VIT3D_OK;
+}
+int launch_round_tf32(const float* x, float* y, long long n, cudaStream_t st) {
+  if (n <= 0) return VIT3D_OK;
+  ew_kernel<<<ew_blocks(n), 256, 0, st>>>(n, [=] __device__(long long i) { y[i] = round_tf32(x[i]); });
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }

@@ -30,6 +30,7 @@ struct TcEpilogue {
   int row_group = 0;                // >0: out row = m + m / row_group + 1
   int atomic = 0;                   // accumulate with fp32 atomics (split-K)
   int vols_per_tile = 0;            // patch-embedding mode: volumes per 128-row tile
+  int round_tf32 = 0;               // fp32 output is the operand of a TF32 GEMM: round to nearest tf32
 };
 
 constexpr int TC_BLOCK_M = 128;
@@ -156,6 +157,7 @@ __device__ __forceinline__ void epilogue_rows(const TcEpilogue& ep, const CUtens
               if (ep.pre) *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.pre) + orow * N + col) = v;
               if (ep.act == VIT3D_ACT_GELU) { v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w); }
               v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w;
+              if (ep.round_tf32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
               *reinterpret_cast<float4*>(o) = v;
             }
           }
@@ -515,6 +517,7 @@ bool tc_linear_supported(int prec, int M, int N, int K) {
 int tc_linear_fwd(const TcLinear& t, cudaStream_t st) {
   TcEpilogue ep;
   ep.bias = t.bias; ep.residual = t.residual; ep.out = t.y; ep.pre = t.pre; ep.out_f32 = t.y_f32; ep.act = t.act;
+  ep.round_tf32 = (t.prec == VIT3D_PREC_TF32 && t.act == VIT3D_ACT_GELU && !t.residual) ? 1 : 0;
   return tc_gemm(t.prec == VIT3D_PREC_TF32, t.x, t.w, t.M, t.N, t.K, ep, 1, st);
 }
 

@@ -60,17 +60,22 @@ def invalidate_weight_shadows() -> None:
     _STATE["epoch"] = _STATE.get("epoch", 0) + 1
 
 
-def lp_weight(w: torch.Tensor) -> torch.Tensor:
+def lp_weight(w: torch.Tensor, prec: str = "bf16") -> torch.Tensor:
+    """bf16 copy (BF16 mode) or TF32-rounded fp32 copy (TF32 mode) of an fp32 weight."""
     cacheable = isinstance(w, torch.nn.Parameter)
     if cacheable:
-        ent = _LP_CACHE.get(id(w))
+        ent = _LP_CACHE.get((id(w), prec))
         if (ent is not None and ent[0]() is w and ent[1] == w._version and ent[2] == w.data_ptr()
                 and ent[4] == _STATE.get("epoch", 0)):
             return ent[3]
-    out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
-    call("vit3d_cast_f32_to_bf16", ptr(w.detach()), ptr(out), w.numel(), stream())
+    if prec == "bf16":
+        out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+        call("vit3d_cast_f32_to_bf16", ptr(w.detach()), ptr(out), w.numel(), stream())
+    else:
+        out = torch.empty(w.shape, dtype=torch.float32, device=w.device)
+        call("vit3d_round_tf32", ptr(w.detach()), ptr(out), w.numel(), stream())
     if cacheable:
-        key = id(w)
+        key = (id(w), prec)
         _LP_CACHE[key] = (weakref.ref(w, lambda _r, key=key: _LP_CACHE.pop(key, None)), w._version, w.data_ptr(), out,
                           _STATE.get("epoch", 0))
     return out
@@ -97,7 +102,10 @@ class PatchEmbedFn(torch.autograd.Function):
         pid = PREC[prec]
         wsb = _lib.lib().vit3d_patch_embed_ws_bytes(B, X, Y, Z, p0, p1, p2, H, pid)
         ws = torch.empty(wsb, device=x.device, dtype=torch.uint8)
-        call("vit3d_patch_embed_fwd", ptr(x), ptr(_c(w)), ptr(_c(bias)), ptr(_c(cls)), ptr(_c(pos)), ptr(tokens),
+        # BF16 mode runs the embedding on the tensor cores in TF32: give it round-to-nearest weights
+        # (fp32 / TF32 modes use the exact fp32 embedding, see vit3d_patch_embed_fwd)
+        w_use = lp_weight(w, "tf32") if (prec == "bf16" and w.is_contiguous()) else _c(w)
+        call("vit3d_patch_embed_fwd", ptr(x), ptr(w_use), ptr(_c(bias)), ptr(_c(cls)), ptr(_c(pos)), ptr(tokens),
              B, X, Y, Z, p0, p1, p2, H, pid, ptr(ws), wsb, stream())
         ctx.save_for_backward(x)
         ctx.meta = (w.shape, cls.shape, pos.shape, prec)
@@ -139,16 +147,18 @@ class LayerNormFn(torch.autograd.Function):
     """nn.LayerNorm(H, eps) forward/backward (modeling.py:189,194,253)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, out_bf16):
+    def forward(ctx, x, gamma, beta, eps, out_mode):
+        """out_mode: 0 fp32, 1 bf16, 2 fp32 rounded to TF32 (operand of a TF32 GEMM)."""
         _need_cuda(x, gamma, beta)
         x = _c(x.float())
         H = x.shape[-1]
         M = x.numel() // H
-        od = torch.bfloat16 if out_bf16 else torch.float32
+        out_mode = int(out_mode)
+        od = torch.bfloat16 if out_mode == 1 else torch.float32
         y = torch.empty(x.shape, device=x.device, dtype=od)
         mean = torch.empty(M, device=x.device)
         rstd = torch.empty(M, device=x.device)
-        call("vit3d_ln_fwd", ptr(x), ptr(_c(gamma)), ptr(_c(beta)), ptr(y), int(od == torch.bfloat16), ptr(mean),
+        call("vit3d_ln_fwd", ptr(x), ptr(_c(gamma)), ptr(_c(beta)), ptr(y), out_mode, ptr(mean),
              ptr(rstd), M, H, float(eps), stream())
         ctx.save_for_backward(x, gamma, mean, rstd)
         return y
@@ -188,10 +198,11 @@ class LinearFn(torch.autograd.Function):
         yd = torch.float32 if (residual is not None or out_f32) else ad
         y = torch.empty(M, N, device=x.device, dtype=yd)
         pre = torch.empty(M, N, device=x.device, dtype=yd) if act == ACT_GELU else None
-        w_lp = lp_weight(w) if (prec == "bf16" and w.is_contiguous()) else None
+        shadow = prec in ("bf16", "tf32")
+        w_lp = lp_weight(w, prec) if (shadow and w.is_contiguous()) else None
         w = _c(w)
-        if prec == "bf16" and w_lp is None:
-            w_lp = lp_weight(w)
+        if shadow and w_lp is None:
+            w_lp = lp_weight(w, prec)
         res = None if residual is None else _c(residual.float()).reshape(M, N)
         call("vit3d_linear_fwd", ptr(x2), ldx, int(x2.dtype == torch.float32), ptr(w), ptr(w_lp),
              ptr(None if b is None else _c(b)), ptr(res), ptr(y), int(yd == torch.float32), ptr(pre), act, M, N, K,

@@ -150,7 +150,7 @@ class Block(nn.Module):
         prec = self.precision
         x = x.float()
         h = x
-        lp = prec == "bf16"
+        lp = {"bf16": 1, "tf32": 2}.get(prec, 0)     # LayerNorm output feeds a GEMM: bf16 / TF32-rounded / fp32
         xn = F.LayerNormFn.apply(x, self.attention_norm.weight, self.attention_norm.bias, self.attention_norm.eps, lp)
         x, weights = self.attn(xn, residual=h)
         h = x
@@ -183,7 +183,7 @@ class Encoder(nn.Module):
             if self.vis:
                 attn_weights.append(weights)
         encoded = F.LayerNormFn.apply(hidden_states, self.encoder_norm.weight, self.encoder_norm.bias,
-                                      self.encoder_norm.eps, False)
+                                      self.encoder_norm.eps, 0)
         return encoded, attn_weights
 
 

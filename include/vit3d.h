@@ -77,7 +77,8 @@ int vit3d_patch_embed_bwd(const float* x, const float* dtokens, float* dw, float
 
 /* ---------------------------------------------------------------- a4/a5: LayerNorm(eps, biased var, affine)
  * nn.LayerNorm(H, eps=1e-6) at modeling.py:182-183,189,194,242,253.
- * y is [M,H] in fp32 (y_bf16=0) or bf16 (y_bf16=1); mean/rstd [M] may be NULL in inference. */
+ * y is [M,H] in fp32 (y_bf16=0), bf16 (y_bf16=1) or fp32 rounded to TF32 (y_bf16=2, operand of a TF32
+ * GEMM); mean/rstd [M] may be NULL in inference. */
 int vit3d_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_bf16, float* mean,
                  float* rstd, int M, int H, float eps, vit3d_stream_t stream);
 /* dx = (dres ? dres : 0) + LN'(dy); dgamma/dbeta accumulated.  dy fp32 [M,H]. */
@@ -86,7 +87,8 @@ int vit3d_ln_bwd(const float* dy, const float* x, const float* mean, const float
 
 /* ---------------------------------------------------------------- nn.Linear (modeling.py:63-67,105-106,277,351)
  * y[M,N] = act(x[M,K] @ w[N,K]^T + bias) (+ residual).  x/y/pre are "act" typed unless noted.
- *   w        fp32 master weight [N,K];   w_lp  bf16 copy of w (BF16 mode, else NULL)
+ *   w        fp32 master weight [N,K];   w_lp  bf16 copy of w (BF16 mode) / TF32-rounded fp32 copy (TF32
+ *            mode, optional) / NULL
  *   residual fp32 [M,N] or NULL (then y is "act"); with residual, y is fp32 (residual stream)
  *   pre      optional [M,N] "act": pre-activation saved for backward (act==GELU)
  *   ldx      row stride of x in elements (lets the head read rows b*S of the token matrix)
@@ -127,6 +129,8 @@ int vit3d_dropout_masked(const void* x, const unsigned char* mask, const void* r
                          int is_f32, float p, vit3d_stream_t stream);
 int vit3d_cast_f32_to_bf16(const float* x, void* y, long long n, vit3d_stream_t stream);
 int vit3d_cast_bf16_to_f32(const void* x, float* y, long long n, vit3d_stream_t stream);
+/* y = x rounded to nearest TF32 (fp32 container): shadow weights for the TF32 mode */
+int vit3d_round_tf32(const float* x, float* y, long long n, vit3d_stream_t stream);
 /* y += x (fp32) */
 int vit3d_add_inplace(float* y, const float* x, long long n, vit3d_stream_t stream);
 
