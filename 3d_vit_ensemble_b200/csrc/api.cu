@@ -176,7 +176,7 @@ int vit3d_linear_fwd(const void* x, int ldx, int x_f32, const float* w, const vo
   return launch_sgemm(g, st);
 }
 
-int vit3d_linear_bwd(const void* dy, int dy_f32, const void* x, int ldx, int x_f32, const float* w, const void* w_lp,
+int vit3d_linear_bwd(const void* dy, int dy_f32, const void* x, int ldx, int x_f32, const float* w, const void* w_t_lp,
                      void* dx, int lddx, int dx_f32, float* dw, float* db, int M, int N, int K, int prec,
                      vit3d_stream_t stream) {
   V3_REQUIRE(dy && w, "linear_bwd: null pointer");
@@ -187,27 +187,36 @@ int vit3d_linear_bwd(const void* dy, int dy_f32, const void* x, int ldx, int x_f
   const int dyf = dy_f32 || act_f32(prec);
   const int xf = x_f32 || act_f32(prec);
   const int dxf = dx_f32 || act_f32(prec);
-  (void)w_lp;
   int rc;
   if (dx) {
     // dx[M,K] = dy[M,N] @ w[N,K]
-    SgemmArgs g;
-    g.A = dy; g.sa_m = N; g.sa_k = 1; g.a_f32 = dyf;
-    g.B = w; g.sb_k = K; g.sb_n = 1; g.b_f32 = 1;
-    g.C = dx; g.ldc = lddx > 0 ? lddx : K; g.c_f32 = dxf;
-    g.M = M; g.N = K; g.K = N;
-    rc = launch_sgemm(g, st);
+    if (prec == VIT3D_PREC_BF16 && !dyf && w_t_lp && (lddx <= 0 || lddx == K) && tc_linear_supported(prec, M, K, N)) {
+      TcLinear t;
+      t.x = dy; t.w = w_t_lp; t.y = dx; t.y_f32 = dxf; t.M = M; t.N = K; t.K = N; t.prec = prec;
+      rc = tc_linear_fwd(t, st);
+    } else {
+      SgemmArgs g;
+      g.A = dy; g.sa_m = N; g.sa_k = 1; g.a_f32 = dyf;
+      g.B = w; g.sb_k = K; g.sb_n = 1; g.b_f32 = 1;
+      g.C = dx; g.ldc = lddx > 0 ? lddx : K; g.c_f32 = dxf;
+      g.M = M; g.N = K; g.K = N;
+      rc = launch_sgemm(g, st);
+    }
     if (rc != VIT3D_OK) return rc;
   }
   if (dw) {
     // dw[N,K] += dy^T[N,M] @ x[M,K]
-    SgemmArgs g;
-    g.A = dy; g.sa_m = 1; g.sa_k = N; g.a_f32 = dyf;
-    g.B = x; g.sb_k = ldx; g.sb_n = 1; g.b_f32 = xf;
-    g.C = dw; g.ldc = K; g.c_f32 = 1; g.accumulate = 1;
-    g.M = N; g.N = K; g.K = M;
-    g.splitk = pick_splitk(g.M, g.N, g.K);
-    rc = launch_sgemm(g, st);
+    if (!dyf && !xf && ldx == K && tc_wgrad_supported(prec, M, N, K)) {
+      rc = tc_gemm_wgrad(dy, x, dw, N, K, M, st);
+    } else {
+      SgemmArgs g;
+      g.A = dy; g.sa_m = 1; g.sa_k = N; g.a_f32 = dyf;
+      g.B = x; g.sb_k = ldx; g.sb_n = 1; g.b_f32 = xf;
+      g.C = dw; g.ldc = K; g.c_f32 = 1; g.accumulate = 1;
+      g.M = N; g.N = K; g.K = M;
+      g.splitk = pick_splitk(g.M, g.N, g.K);
+      rc = launch_sgemm(g, st);
+    }
     if (rc != VIT3D_OK) return rc;
   }
   if (db) {
@@ -260,6 +269,10 @@ int vit3d_dropout_masked(const void* x, const unsigned char* mask, const void* r
 int vit3d_cast_f32_to_bf16(const float* x, void* y, long long n, vit3d_stream_t stream) {
   V3_REQUIRE(x && y && n >= 0, "cast: bad argument");
   return launch_cast(x, 1, y, 0, n, as_stream(stream));
+}
+int vit3d_transpose_f32_to_bf16(const float* x, void* y, int rows, int cols, vit3d_stream_t stream) {
+  V3_REQUIRE(x && y && rows >= 0 && cols >= 0, "transpose: bad argument");
+  return launch_transpose_cast(x, y, rows, cols, as_stream(stream));
 }
 int vit3d_round_tf32(const float* x, float* y, long long n, vit3d_stream_t stream) {
   V3_REQUIRE(x && y && n >= 0, "round_tf32: bad argument");

@@ -644,6 +644,27 @@ int launch_cast(const void* x, int x_f32, void* y, int y_f32, long long n, cudaS
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
+// y[cols, rows] (bf16) = x[rows, cols]^T (fp32): transposed bf16 shadow of a weight for the dgrad GEMM
+__global__ void transpose_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? x[(long long)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) y[(long long)c * rows + r] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+int launch_transpose_cast(const float* x, void* y, int rows, int cols, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return VIT3D_OK;
+  dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32));
+  transpose_cast_kernel<<<grid, dim3(32, 8), 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(y), rows, cols);
+  V3_LAUNCH_CHECK();
+  return VIT3D_OK;
+}
 int launch_round_tf32(const float* x, float* y, long long n, cudaStream_t st) {
   if (n <= 0) return VIT3D_OK;
   ew_kernel<<<ew_blocks(n), 256, 0, st>>>(n, [=] __device__(long long i) { y[i] = round_tf32(x[i]); });

@@ -250,7 +250,7 @@ template <bool TF32, int BN>
 __global__ void __launch_bounds__(tc_threads(BN), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmPre, TcEpilogue ep, int M,
-               int N, int K, int tiles_m, int tiles_n, int splits, int stationary, int patch_blocks) {
+               int N, int K, int tiles_m, int tiles_n, int splits, int stationary, int patch_blocks, int mn_major) {
   using Cfg = TcCfg<BN>;
   constexpr int BLOCK_K = TF32 ? 32 : 64;   // 128 bytes of K per stage row
   extern __shared__ uint8_t smem_raw[];
@@ -271,7 +271,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* ring = stat ? smem + TC_SLAB_BYTES : smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = patch_blocks > 0 ? K : (K + BLOCK_K - 1) / BLOCK_K;   // patch mode passes the k-block count as K
+  // patch mode passes the k-block count as K; MN-major stages hold 64 reduction rows
+  const int nkb = patch_blocks > 0 ? K : (mn_major ? (K + 63) / 64 : (K + BLOCK_K - 1) / BLOCK_K);
   const int kb_per = (nkb + splits - 1) / splits;
 
   if (warp == 0 && lane == 0) {
@@ -318,6 +319,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int i = kb / patch_blocks, c0 = (kb % patch_blocks) * 32;
             tma_load_5d(sa, &tmA, &full_bar[stage], c0, 0, i, 0, ti.tm * ep.vols_per_tile);
             tma_load_3d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], c0, i, ti.tn * BN);
+          } else if (mn_major) {
+            // both operands MN-major (weight gradients: dW = dY^T X reduces over the token rows): a stage
+            // holds 64 reduction rows; each 64-column block is one {64 cols x 64 rows} box = 8 KB
+#pragma unroll
+            for (int j = 0; j < TC_BLOCK_M / 64; ++j)
+              tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], ti.tm * TC_BLOCK_M + 64 * j, kb * 64);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sa + Cfg::A_BYTES + j * 8192, &tmB, &full_bar[stage], ti.tn * BN + 64 * j, kb * 64);
           } else {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, ti.tm * TC_BLOCK_M);
             if (!stat) tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, ti.tn * BN);
@@ -330,7 +340,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TF32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16, TC_BLOCK_M, BN, 0, 0);
+      const uint32_t idesc = make_idesc(TF32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16, TC_BLOCK_M, BN, mn_major ? 1 : 0,
+                                        mn_major ? 1 : 0);
+      // K-major SW128: 8-row groups 1024 B apart, K advances 32 B inside the 128 B swizzle row.
+      // MN-major SW128: 64-element MN blocks 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO),
+      //                 one MMA (K = 16) consumes two K groups -> advance 2048 B.
+      const uint32_t lbo = mn_major ? 8192u : 16u, kstep = mn_major ? 2048u : 32u;
       TileIter ti(stat, tiles_m, tiles_n, splits);
       int stage = 0;
       uint32_t phase = 0;
@@ -350,8 +365,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sb = stat ? smem_u32(smem + kb * Cfg::B_BYTES) : sa + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {   // 4 x 32 bytes of K per stage
-            const uint64_t ad = make_smem_desc(sa + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-            const uint64_t bd = make_smem_desc(sb + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t ad = make_smem_desc(sa + k * kstep, lbo, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t bd = make_smem_desc(sb + k * kstep, lbo, 1024, UMMA_LAYOUT_SW128);
             umma<TF32>(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
@@ -441,7 +456,7 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long ro
 template <bool TF32, int BN>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
                      const TcEpilogue& ep, int M, int N, int K, int splits, bool stationary, cudaStream_t st,
-                     int patch_blocks = 0) {
+                     int patch_blocks = 0, int mn_major = 0) {
   using Cfg = TcCfg<BN>;
   auto kern = tc_gemm_kernel<TF32, BN>;
   static thread_local int configured_dev = -1;
@@ -461,7 +476,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     grid = cpn * tiles_n;
   }
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tp, ep, M, N, K, tiles_m, tiles_n, splits, stationary ? 1 : 0,
-                                                      patch_blocks);
+                                                      patch_blocks, mn_major);
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
@@ -505,6 +520,42 @@ int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const 
   if (bn == 256) return launch_tc<false, 256>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
   if (bn == 128) return launch_tc<false, 128>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
   return launch_tc<false, 64>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
+}
+
+// D[Mo,No] += A^T B with A = [Kred, Mo] and B = [Kred, No] row-major bf16 (both operands MN-major):
+// the weight-gradient product dW[N,K] += dY[M,N]^T X[M,K].  Split over the reduction (token rows) so that
+// every SM has work; partial tiles are accumulated with fp32 atomics into `out`.
+int tc_gemm_wgrad(const void* A, const void* B, float* out, int Mo, int No, int Kred, cudaStream_t st) {
+  const int sms = sm_count();
+  int bn = 256;
+  if (No % 256) bn = 128;
+  if (No % 128) bn = 64;
+  const int tiles = ceil_div(Mo, TC_BLOCK_M) * ceil_div(No, bn);
+  const int nkb = ceil_div(Kred, 64);
+  int splits = ceil_div(2 * sms, tiles);
+  if (splits > nkb) splits = nkb;
+  if (splits < 1) splits = 1;
+  // no K-slice may be empty (an empty slice would publish an unwritten accumulator): iterate to the
+  // fixpoint splits == ceil(nkb / ceil(nkb / splits)), which is what the kernel derives from `splits`
+  for (;;) {
+    const int kp = ceil_div(nkb, splits), s2 = ceil_div(nkb, kp);
+    if (s2 == splits) break;
+    splits = s2;
+  }
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d(&ta, A, 2, Kred, Mo, Mo, 64, 64, 128);
+  if (rc != VIT3D_OK) return rc;
+  rc = make_tmap_2d(&tb, B, 2, Kred, No, No, 64, 64, 128);
+  if (rc != VIT3D_OK) return rc;
+  TcEpilogue ep;
+  ep.out = out; ep.out_f32 = 1; ep.atomic = 1;
+  if (bn == 256) return launch_tc<false, 256>(ta, tb, ta, ta, ep, Mo, No, Kred, splits, false, st, 0, 1);
+  if (bn == 128) return launch_tc<false, 128>(ta, tb, ta, ta, ep, Mo, No, Kred, splits, false, st, 0, 1);
+  return launch_tc<false, 64>(ta, tb, ta, ta, ep, Mo, No, Kred, splits, false, st, 0, 1);
+}
+
+bool tc_wgrad_supported(int prec, int M, int N, int K) {
+  return prec == VIT3D_PREC_BF16 && M >= 64 && N % 64 == 0 && K % 64 == 0;
 }
 
 bool tc_linear_supported(int prec, int M, int N, int K) {

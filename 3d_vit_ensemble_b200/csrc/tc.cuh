@@ -19,6 +19,10 @@ struct TcLinear {
 bool tc_linear_supported(int prec, int M, int N, int K);
 int tc_linear_fwd(const TcLinear& t, cudaStream_t st);
 
+// dW[N,K] += dY[M,N]^T X[M,K]  (bf16 operands, fp32 atomics)
+bool tc_wgrad_supported(int prec, int M, int N, int K);
+int tc_gemm_wgrad(const void* dy, const void* x, float* dw, int N, int K, int M, cudaStream_t st);
+
 bool tc_patch_embed_supported(int B, int X, int Y, int Z, int p0, int p1, int p2, int H);
 int tc_patch_embed_fwd(const float* x, const float* w, const float* bias, const float* pos, float* tokens, int B, int X,
                        int Y, int Z, int p0, int p1, int p2, int H, cudaStream_t st);

@@ -71,6 +71,9 @@ def lp_weight(w: torch.Tensor, prec: str = "bf16") -> torch.Tensor:
     if prec == "bf16":
         out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
         call("vit3d_cast_f32_to_bf16", ptr(w.detach()), ptr(out), w.numel(), stream())
+    elif prec == "bf16_t":          # transposed bf16 shadow [K,N] of a [N,K] weight: dgrad operand
+        out = torch.empty(w.shape[1], w.shape[0], dtype=torch.bfloat16, device=w.device)
+        call("vit3d_transpose_f32_to_bf16", ptr(w.detach()), ptr(out), w.shape[0], w.shape[1], stream())
     else:
         out = torch.empty(w.shape, dtype=torch.float32, device=w.device)
         call("vit3d_round_tf32", ptr(w.detach()), ptr(out), w.numel(), stream())
@@ -199,6 +202,7 @@ class LinearFn(torch.autograd.Function):
         y = torch.empty(M, N, device=x.device, dtype=yd)
         pre = torch.empty(M, N, device=x.device, dtype=yd) if act == ACT_GELU else None
         shadow = prec in ("bf16", "tf32")
+        w_obj = w
         w_lp = lp_weight(w, prec) if (shadow and w.is_contiguous()) else None
         w = _c(w)
         if shadow and w_lp is None:
@@ -208,6 +212,7 @@ class LinearFn(torch.autograd.Function):
              ptr(None if b is None else _c(b)), ptr(res), ptr(y), int(yd == torch.float32), ptr(pre), act, M, N, K,
              PREC[prec], stream())
         ctx.save_for_backward(x2, w, w_lp, pre)
+        ctx.w_obj = w_obj if (prec == "bf16" and w_obj.is_contiguous() and w_obj.dim() == 2) else None
         ctx.meta = (ldx, act, prec, b is not None, residual is not None, x.shape, x.dtype)
         return y.reshape(*lead, N)
 
@@ -231,8 +236,17 @@ class LinearFn(torch.autograd.Function):
         dx = torch.empty(M, K, device=dy.device, dtype=x2.dtype) if need_dx else None
         dw = torch.zeros_like(w) if ctx.needs_input_grad[1] else None
         db = torch.zeros(N, device=dy.device) if (has_b and ctx.needs_input_grad[2]) else None
+        w_t = None
+        if prec == "bf16":
+            # tensor-core backward wants bf16 operands: the residual-stream gradient arrives fp32
+            if dy2.dtype == torch.float32 and x2.dtype == torch.bfloat16:
+                dyb = torch.empty(M, N, device=dy.device, dtype=torch.bfloat16)
+                call("vit3d_cast_f32_to_bf16", ptr(dy2), ptr(dyb), dy2.numel(), stream())
+                dy2 = dyb
+            if need_dx and dy2.dtype == torch.bfloat16:
+                w_t = lp_weight(ctx.w_obj if ctx.w_obj is not None else w, "bf16_t")
         call("vit3d_linear_bwd", ptr(dy2), int(dy2.dtype == torch.float32), ptr(x2), ldx,
-             int(x2.dtype == torch.float32), ptr(w), ptr(w_lp), ptr(dx), K, int(x2.dtype == torch.float32), ptr(dw),
+             int(x2.dtype == torch.float32), ptr(w), ptr(w_t), ptr(dx), K, int(x2.dtype == torch.float32), ptr(dw),
              ptr(db), M, N, K, PREC[prec], stream())
         if dx is not None:
             dx = dx.reshape(xshape).to(xdtype)

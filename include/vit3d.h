@@ -97,8 +97,11 @@ int vit3d_linear_fwd(const void* x, int ldx, int x_f32, const float* w, const vo
                      const float* residual, void* y, int y_f32, void* pre, int act, int M, int N, int K, int prec,
                      vit3d_stream_t stream);
 /* dx[M,K] = dy[M,N] @ w[N,K]  (dx_f32: write fp32);  dw[N,K] += dy^T @ x ; db[N] += colsum(dy).
- * Any of dx / dw / db may be NULL.  dy is "act" typed unless dy_f32. */
-int vit3d_linear_bwd(const void* dy, int dy_f32, const void* x, int ldx, int x_f32, const float* w, const void* w_lp,
+ * Any of dx / dw / db may be NULL.  dy is "act" typed unless dy_f32.
+ *   w_t_lp  bf16 TRANSPOSED copy of w, [K,N] (vit3d_transpose_f32_to_bf16): with it, bf16 dy and BF16 mode
+ *           the data gradient runs on tcgen05; the weight gradient does when dy and x are bf16 (both
+ *           operands are read MN-major, nothing is transposed in memory). */
+int vit3d_linear_bwd(const void* dy, int dy_f32, const void* x, int ldx, int x_f32, const float* w, const void* w_t_lp,
                      void* dx, int lddx, int dx_f32, float* dw, float* db, int M, int N, int K, int prec,
                      vit3d_stream_t stream);
 
@@ -129,6 +132,8 @@ int vit3d_dropout_masked(const void* x, const unsigned char* mask, const void* r
                          int is_f32, float p, vit3d_stream_t stream);
 int vit3d_cast_f32_to_bf16(const float* x, void* y, long long n, vit3d_stream_t stream);
 int vit3d_cast_bf16_to_f32(const void* x, float* y, long long n, vit3d_stream_t stream);
+/* y[cols,rows] (bf16) = x[rows,cols]^T (fp32) */
+int vit3d_transpose_f32_to_bf16(const float* x, void* y, int rows, int cols, vit3d_stream_t stream);
 /* y = x rounded to nearest TF32 (fp32 container): shadow weights for the TF32 mode */
 int vit3d_round_tf32(const float* x, float* y, long long n, vit3d_stream_t stream);
 /* y += x (fp32) */

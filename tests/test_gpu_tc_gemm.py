@@ -82,3 +82,33 @@ def test_tc_patch_embedding_matches_oracle(B, H):
     # cls rows are exact fp32 adds
     cls_ref = (sd[pre + "cls_token"][0, 0] + sd[pre + "position_embeddings"][0, 0]).double()
     assert float((got[:, 0] - cls_ref).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(1300, 768, 256), (16640, 2048, 256), (16640, 256, 2048), (260, 256, 256),
+                                   (4161, 3072, 256), (130, 64, 64)])
+def test_tc_linear_backward_bf16(shape):
+    """tcgen05 data gradient (transposed bf16 weight shadow) and weight gradient (both operands MN-major,
+    split over the token rows, fp32 atomics) vs fp64 products of the same bf16 operands."""
+    M, N, K = shape
+    torch.manual_seed(M + N + K)
+    dy = torch.randn(M, N, device=DEV).to(torch.bfloat16)
+    x = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+    w = torch.randn(N, K, device=DEV) / K ** 0.5
+    wt = torch.empty(K, N, device=DEV, dtype=torch.bfloat16)
+    call("vit3d_transpose_f32_to_bf16", ptr(w), ptr(wt), N, K, stream())
+    assert torch.equal(wt, w.t().contiguous().to(torch.bfloat16))
+    for dx_f32 in (0, 1):
+        dx = torch.full((M, K), float("nan"), device=DEV, dtype=torch.float32 if dx_f32 else torch.bfloat16)
+        dw = torch.zeros(N, K, device=DEV)
+        db = torch.zeros(N, device=DEV)
+        call("vit3d_linear_bwd", ptr(dy), 0, ptr(x), K, 0, ptr(w), ptr(wt), ptr(dx), K, dx_f32, ptr(dw), ptr(db), M, N, K,
+             PREC["bf16"], stream())
+        torch.cuda.synchronize()
+        ref_dx = dy.double() @ wt.double().t()
+        ref_dw = dy.double().t() @ x.double()
+        ref_db = dy.double().sum(0)
+        e = float((dx.double() - ref_dx).abs().max())
+        assert np.isfinite(e) and e <= 1e-4 * N ** 0.5 + (0.0 if dx_f32 else 1.0 / 128) * float(ref_dx.abs().max()), e
+        e = float((dw.double() - ref_dw).abs().max())
+        assert np.isfinite(e) and e <= 2e-5 * M ** 0.5 * 4, (e, float(ref_dw.abs().max()))
+        assert float((db.double() - ref_db).abs().max()) <= 1e-3 * M ** 0.5
