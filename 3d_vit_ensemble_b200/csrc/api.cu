@@ -239,6 +239,7 @@ int vit3d_attn_bwd(const void* dctx, const void* qkv, void* dqkv, int B, int S, 
                    vit3d_stream_t stream) {
   V3_REQUIRE(dctx && qkv && dqkv, "attn_bwd: null pointer");
   V3_REQUIRE(B >= 0 && S > 0 && heads > 0 && D > 0, "attn_bwd: bad shape");
+  if (prec == VIT3D_PREC_BF16 && tc_attn_supported(S, heads, D)) return tc_attn_bwd(dctx, qkv, dqkv, B, S, heads, D, as_stream(stream));
   return launch_attn_bwd_generic(dctx, qkv, act_f32(prec), dqkv, B, S, heads, D, as_stream(stream));
 }
 

@@ -249,4 +249,287 @@ int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int head
   return launch_attn<64>(qkv, ctx, probs, B, st);
 }
 
+// ============================================================================ backward
+// dqkv from dctx, probabilities recomputed (nothing but qkv is saved by the forward).  One CTA per SM,
+// one volume at a time: qkv (65 x 768) and dctx (65 x 256) are staged in shared memory by bulk copies.
+//   pass 1, task = (head, 16-query tile):  S = Q K^T, P = softmax, dP = dO V^T, delta = rowsum(P dP),
+//           dS = P (dP - delta) / sqrt(D), dQ = dS K  -> dQ staging tile; row statistics (max, 1/sum,
+//           delta) go to shared memory.
+//   pass 2, task = (head, 16-key tile):    S^T = K Q^T, P^T from the saved statistics, dP^T = V dO^T,
+//           dS^T, dV = P^T dO, dK = dS^T Q -> written over the K / V tile they came from (dead by then).
+// All seven products run on mma.sync.m16n8k16 (bf16 in, fp32 accumulate); softmax math is fp32.
+constexpr int AB_DOP = AT_A * 2 + 16;                 // padded row pitch of the dctx / dQ images (528 B)
+constexpr int AB_QKV = AT_S * AT_PITCH;               // 100,880
+constexpr int AB_DO = AT_S * AB_DOP;                  // 34,320
+constexpr int AB_STATS = 16 * 80 * 3 * 4;             // (max, 1/sum, delta) x 80 rows x <=16 heads
+constexpr int AB_SMEM = AB_QKV + 2 * AB_DO + AB_STATS + 64 + 128;
+
+template <int D>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16* __restrict__ qkv,
+                   __nv_bfloat16* __restrict__ dqkv, int B, float scale, float scale_log2e) {
+  constexpr int HEADS = AT_A / D;
+  constexpr int KSTEPS = D / 16;
+  constexpr int NT = 10;
+  constexpr int DT = D / 8;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  uint8_t* s_qkv = smem;
+  uint8_t* s_do = smem + AB_QKV;
+  uint8_t* s_dq = s_do + AB_DO;
+  float* s_stat = reinterpret_cast<float*>(s_dq + AB_DO);        // [HEADS][3][80]
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_stat) + AB_STATS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  if (threadIdx.x == 0) {
+    mbar_init(full, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const uint32_t sb = smem_u32(s_qkv), dob = smem_u32(s_do);
+
+  int it = 0;
+  for (int b = blockIdx.x; b < B; b += gridDim.x, ++it) {
+    if (warp == 0) {
+      bulk_wait_read0();     // previous volume's stores have finished reading shared memory
+      if (lane == 0) mbar_arrive_expect_tx(full, AT_S * (AT_ROWB + AT_A * 2));
+      __syncwarp();
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(qkv) + (size_t)b * AT_S * AT_ROWB;
+      const uint8_t* dsrc = reinterpret_cast<const uint8_t*>(dctx) + (size_t)b * AT_S * AT_A * 2;
+      for (int r = lane; r < AT_S; r += 32) {
+        bulk_g2s(s_qkv + r * AT_PITCH, src + (size_t)r * AT_ROWB, AT_ROWB, full);
+        bulk_g2s(s_do + r * AB_DOP, dsrc + (size_t)r * AT_A * 2, AT_A * 2, full);
+      }
+    }
+    mbar_wait(full, it & 1);
+
+    // ------------------------------------------------------------------ pass 1: query tiles
+    for (int task = warp; task < HEADS * 5; task += AT_THREADS / 32) {
+      const int h = task / 5, rt = task % 5;
+      const int r0 = rt * 16;
+      uint32_t qa[KSTEPS][4], da[KSTEPS][4];
+      {
+        const int row = min(r0 + (lane & 7) + ((lane >> 3) & 1) * 8, AT_S - 1);
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          ldsm_x4(sb + row * AT_PITCH + (h * D + ks * 16 + (lane >> 4) * 8) * 2, qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+          ldsm_x4(dob + row * AB_DOP + (h * D + ks * 16 + (lane >> 4) * 8) * 2, da[ks][0], da[ks][1], da[ks][2], da[ks][3]);
+        }
+      }
+      float s[NT][4], dp[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+        if (nt < 9) {
+          const int key = min(nt * 8 + (lane & 7), AT_S - 1);
+#pragma unroll
+          for (int ks = 0; ks < KSTEPS; ++ks) {
+            uint32_t b0, b1;
+            ldsm_x2(sb + key * AT_PITCH + (AT_A + h * D + ks * 16 + ((lane >> 3) & 1) * 8) * 2, b0, b1);
+            mma_bf16(s[nt], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
+            ldsm_x2(sb + key * AT_PITCH + (2 * AT_A + h * D + ks * 16 + ((lane >> 3) & 1) * 8) * 2, b0, b1);
+            mma_bf16(dp[nt], da[ks][0], da[ks][1], da[ks][2], da[ks][3], b0, b1);
+          }
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 9; ++nt) {
+        const int c = nt * 8 + 2 * t;
+        if (c < AT_S) { mx0 = fmaxf(mx0, s[nt][0]); mx1 = fmaxf(mx1, s[nt][2]); }
+        if (c + 1 < AT_S) { mx0 = fmaxf(mx0, s[nt][1]); mx1 = fmaxf(mx1, s[nt][3]); }
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int c = nt * 8 + 2 * t;
+        const bool v0 = c < AT_S, v1 = c + 1 < AT_S;
+        s[nt][0] = v0 ? exp2f((s[nt][0] - mx0) * scale_log2e) : 0.f;
+        s[nt][1] = v1 ? exp2f((s[nt][1] - mx0) * scale_log2e) : 0.f;
+        s[nt][2] = v0 ? exp2f((s[nt][2] - mx1) * scale_log2e) : 0.f;
+        s[nt][3] = v1 ? exp2f((s[nt][3] - mx1) * scale_log2e) : 0.f;
+        sum0 += s[nt][0] + s[nt][1];
+        sum1 += s[nt][2] + s[nt][3];
+      }
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+      const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+      float dl0 = 0.f, dl1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] *= inv0; s[nt][1] *= inv0; s[nt][2] *= inv1; s[nt][3] *= inv1;       // P
+        dl0 += s[nt][0] * dp[nt][0] + s[nt][1] * dp[nt][1];
+        dl1 += s[nt][2] * dp[nt][2] + s[nt][3] * dp[nt][3];
+      }
+      dl0 += __shfl_xor_sync(0xffffffffu, dl0, 1);
+      dl0 += __shfl_xor_sync(0xffffffffu, dl0, 2);
+      dl1 += __shfl_xor_sync(0xffffffffu, dl1, 1);
+      dl1 += __shfl_xor_sync(0xffffffffu, dl1, 2);
+      const int row0 = r0 + g, row1 = r0 + g + 8;
+      if (t == 0) {
+        float* st = s_stat + h * 240;
+        st[row0] = mx0; st[80 + row0] = inv0; st[160 + row0] = dl0;
+        st[row1] = mx1; st[80 + row1] = inv1; st[160 + row1] = dl1;
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {                                              // dS (P is 0 on padding)
+        s[nt][0] *= (dp[nt][0] - dl0) * scale; s[nt][1] *= (dp[nt][1] - dl0) * scale;
+        s[nt][2] *= (dp[nt][2] - dl1) * scale; s[nt][3] *= (dp[nt][3] - dl1) * scale;
+      }
+      float o[DT][4];
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) {
+        const uint32_t a0 = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+        const uint32_t a1 = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+        const uint32_t a2 = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        const uint32_t a3 = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        const int key = min(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, AT_S - 1);
+#pragma unroll
+        for (int dt = 0; dt < DT; ++dt) {
+          uint32_t b0, b1;
+          ldsm_x2_t(sb + key * AT_PITCH + (AT_A + h * D + dt * 8) * 2, b0, b1);      // K rows, transposed
+          mma_bf16(o[dt], a0, a1, a2, a3, b0, b1);
+        }
+      }
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) {
+        const int col = h * D + dt * 8 + 2 * t;
+        if (row0 < AT_S) *reinterpret_cast<uint32_t*>(s_dq + row0 * AB_DOP + col * 2) = pack_bf16(o[dt][0], o[dt][1]);
+        if (row1 < AT_S) *reinterpret_cast<uint32_t*>(s_dq + row1 * AB_DOP + col * 2) = pack_bf16(o[dt][2], o[dt][3]);
+      }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ pass 2: key tiles
+    for (int task = warp; task < HEADS * 5; task += AT_THREADS / 32) {
+      const int h = task / 5, kt = task % 5;
+      const int k0 = kt * 16;
+      const float* st = s_stat + h * 240;
+      uint32_t ka[KSTEPS][4], va[KSTEPS][4];
+      {
+        const int row = min(k0 + (lane & 7) + ((lane >> 3) & 1) * 8, AT_S - 1);
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          ldsm_x4(sb + row * AT_PITCH + (AT_A + h * D + ks * 16 + (lane >> 4) * 8) * 2, ka[ks][0], ka[ks][1], ka[ks][2], ka[ks][3]);
+          ldsm_x4(sb + row * AT_PITCH + (2 * AT_A + h * D + ks * 16 + (lane >> 4) * 8) * 2, va[ks][0], va[ks][1], va[ks][2], va[ks][3]);
+        }
+      }
+      float s[NT][4], dp[NT][4];     // rows = keys (g, g+8), columns = queries
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+        if (nt < 9) {
+          const int qrow = min(nt * 8 + (lane & 7), AT_S - 1);
+#pragma unroll
+          for (int ks = 0; ks < KSTEPS; ++ks) {
+            uint32_t b0, b1;
+            ldsm_x2(sb + qrow * AT_PITCH + (h * D + ks * 16 + ((lane >> 3) & 1) * 8) * 2, b0, b1);      // Q rows
+            mma_bf16(s[nt], ka[ks][0], ka[ks][1], ka[ks][2], ka[ks][3], b0, b1);
+            ldsm_x2(dob + qrow * AB_DOP + (h * D + ks * 16 + ((lane >> 3) & 1) * 8) * 2, b0, b1);       // dO rows
+            mma_bf16(dp[nt], va[ks][0], va[ks][1], va[ks][2], va[ks][3], b0, b1);
+          }
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int c = nt * 8 + 2 * t;
+        const bool v0 = c < AT_S, v1 = c + 1 < AT_S;
+        const float m0 = v0 ? st[c] : 0.f, i0 = v0 ? st[80 + c] : 0.f, d0 = v0 ? st[160 + c] : 0.f;
+        const float m1 = v1 ? st[c + 1] : 0.f, i1 = v1 ? st[80 + c + 1] : 0.f, d1 = v1 ? st[160 + c + 1] : 0.f;
+        const float p00 = v0 ? exp2f((s[nt][0] - m0) * scale_log2e) * i0 : 0.f;       // P^T
+        const float p01 = v1 ? exp2f((s[nt][1] - m1) * scale_log2e) * i1 : 0.f;
+        const float p10 = v0 ? exp2f((s[nt][2] - m0) * scale_log2e) * i0 : 0.f;
+        const float p11 = v1 ? exp2f((s[nt][3] - m1) * scale_log2e) * i1 : 0.f;
+        s[nt][0] = p00; s[nt][1] = p01; s[nt][2] = p10; s[nt][3] = p11;
+        dp[nt][0] = p00 * (dp[nt][0] - d0) * scale; dp[nt][1] = p01 * (dp[nt][1] - d1) * scale;   // dS^T
+        dp[nt][2] = p10 * (dp[nt][2] - d0) * scale; dp[nt][3] = p11 * (dp[nt][3] - d1) * scale;
+      }
+      float ov[DT][4], ok[DT][4];
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) {
+        ov[dt][0] = ov[dt][1] = ov[dt][2] = ov[dt][3] = 0.f;
+        ok[dt][0] = ok[dt][1] = ok[dt][2] = ok[dt][3] = 0.f;
+      }
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) {
+        const uint32_t p0 = pack_bf16(s[2 * kk][0], s[2 * kk][1]), p1 = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+        const uint32_t p2 = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]), p3 = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        const uint32_t e0 = pack_bf16(dp[2 * kk][0], dp[2 * kk][1]), e1 = pack_bf16(dp[2 * kk][2], dp[2 * kk][3]);
+        const uint32_t e2 = pack_bf16(dp[2 * kk + 1][0], dp[2 * kk + 1][1]), e3 = pack_bf16(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
+        const int qrow = min(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, AT_S - 1);
+#pragma unroll
+        for (int dt = 0; dt < DT; ++dt) {
+          uint32_t b0, b1;
+          ldsm_x2_t(dob + qrow * AB_DOP + (h * D + dt * 8) * 2, b0, b1);              // dO rows, transposed
+          mma_bf16(ov[dt], p0, p1, p2, p3, b0, b1);
+          ldsm_x2_t(sb + qrow * AT_PITCH + (h * D + dt * 8) * 2, b0, b1);             // Q rows, transposed
+          mma_bf16(ok[dt], e0, e1, e2, e3, b0, b1);
+        }
+      }
+      __syncwarp();
+      const int row0 = k0 + g, row1 = k0 + g + 8;
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) {
+        const int col = h * D + dt * 8 + 2 * t;
+        if (row0 < AT_S) {
+          *reinterpret_cast<uint32_t*>(s_qkv + row0 * AT_PITCH + (AT_A + col) * 2) = pack_bf16(ok[dt][0], ok[dt][1]);
+          *reinterpret_cast<uint32_t*>(s_qkv + row0 * AT_PITCH + (2 * AT_A + col) * 2) = pack_bf16(ov[dt][0], ov[dt][1]);
+        }
+        if (row1 < AT_S) {
+          *reinterpret_cast<uint32_t*>(s_qkv + row1 * AT_PITCH + (AT_A + col) * 2) = pack_bf16(ok[dt][2], ok[dt][3]);
+          *reinterpret_cast<uint32_t*>(s_qkv + row1 * AT_PITCH + (2 * AT_A + col) * 2) = pack_bf16(ov[dt][2], ov[dt][3]);
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (warp == 0) {
+      uint8_t* dst = reinterpret_cast<uint8_t*>(dqkv) + (size_t)b * AT_S * AT_ROWB;
+      for (int r = lane; r < AT_S; r += 32) {
+        bulk_s2g(dst + (size_t)r * AT_ROWB, s_dq + r * AB_DOP, AT_A * 2);                            // dQ
+        bulk_s2g(dst + (size_t)r * AT_ROWB + AT_A * 2, s_qkv + r * AT_PITCH + AT_A * 2, 2 * AT_A * 2);  // dK | dV
+      }
+      bulk_commit();
+    }
+  }
+  if (warp == 0) bulk_wait0();
+}
+
+template <int D>
+static int launch_attn_bwd(const void* dctx, const void* qkv, void* dqkv, int B, cudaStream_t st) {
+  auto kern = attn_bwd_tc_kernel<D>;
+  V3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+  const int grid = B < sm_count() ? B : sm_count();
+  const float scale = 1.0f / sqrtf((float)D);
+  kern<<<grid, AT_THREADS, AB_SMEM, st>>>(reinterpret_cast<const __nv_bfloat16*>(dctx),
+                                           reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                           reinterpret_cast<__nv_bfloat16*>(dqkv), B, scale, 1.4426950408889634f * scale);
+  V3_LAUNCH_CHECK();
+  return VIT3D_OK;
+}
+
+int tc_attn_bwd(const void* dctx, const void* qkv, void* dqkv, int B, int S, int heads, int D, cudaStream_t st) {
+  if (!tc_attn_supported(S, heads, D)) V3_UNSUPPORTED("tc attention bwd: unsupported shape S=%d heads=%d D=%d", S, heads, D);
+  if (B <= 0) return VIT3D_OK;
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(dctx) & 15) ||
+      (reinterpret_cast<uintptr_t>(dqkv) & 15)) {
+    set_error("tc attention bwd: buffers must be 16-byte aligned");
+    return VIT3D_ERR_INVALID;
+  }
+  if (D == 16) return launch_attn_bwd<16>(dctx, qkv, dqkv, B, st);
+  if (D == 32) return launch_attn_bwd<32>(dctx, qkv, dqkv, B, st);
+  return launch_attn_bwd<64>(dctx, qkv, dqkv, B, st);
+}
+
 }  // namespace vit3d

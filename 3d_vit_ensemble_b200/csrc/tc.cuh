@@ -29,5 +29,6 @@ int tc_patch_embed_fwd(const float* x, const float* w, const float* bias, const 
 
 bool tc_attn_supported(int S, int heads, int D);
 int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int heads, int D, cudaStream_t st);
+int tc_attn_bwd(const void* dctx, const void* qkv, void* dqkv, int B, int S, int heads, int D, cudaStream_t st);
 
 }  // namespace vit3d

@@ -39,3 +39,25 @@ def test_attention_bf16(heads, B, vis):
         perr = float((probs.double() - rp).abs().max())
         assert np.isfinite(perr) and perr < 2e-5, perr         # softmax itself is fp32
         assert float((probs.sum(-1) - 1).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("heads", [4, 8, 16])
+@pytest.mark.parametrize("B", [1, 3, 149, 300])
+def test_attention_backward_bf16(heads, B):
+    """mma.sync attention backward (probabilities recomputed) vs fp64 autograd on the same bf16 inputs."""
+    torch.manual_seed(B * 17 + heads)
+    S, A = 65, 256
+    qkv = (torch.randn(B, S, 3 * A, device=DEV) * 1.2).to(torch.bfloat16)
+    dctx = torch.randn(B, S, A, device=DEV).to(torch.bfloat16)
+    dqkv = torch.full((B, S, 3 * A), float("nan"), device=DEV, dtype=torch.bfloat16)
+    call("vit3d_attn_bwd", ptr(dctx), ptr(qkv), ptr(dqkv), B, S, heads, A // heads, PREC["bf16"], stream())
+    torch.cuda.synchronize()
+    q64 = qkv.double().requires_grad_(True)
+    ctx, _ = ref_attention(q64, heads)
+    ctx.backward(dctx.double())
+    ref = q64.grad
+    err = float((dqkv.double() - ref).abs().max())
+    scale = float(ref.abs().max())
+    assert np.isfinite(err) and err <= 0.03 * scale, (err, scale)
+    rel = float((dqkv.double() - ref).norm() / ref.norm())
+    assert rel < 0.01, rel
