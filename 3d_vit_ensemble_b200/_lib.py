@@ -56,7 +56,7 @@ SIGNATURES = {
     "vit3d_attn_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "vit3d_gelu_fwd": (_i, [_p, _p, _ll, _i, _p]),
     "vit3d_gelu_bwd": (_i, [_p, _p, _p, _ll, _i, _p]),
-    "vit3d_dropout": (_i, [_p, _p, _p, _ll, _i, _f, _ull, _u, _u, _p]),
+    "vit3d_dropout": (_i, [_p, _p, _p, _ll, _i, _f, _ull, _u, _u, _p, _p]),
     "vit3d_dropout_mask": (_i, [_p, _ll, _f, _ull, _u, _u, _p]),
     "vit3d_dropout_masked": (_i, [_p, _p, _p, _p, _ll, _i, _f, _p]),
     "vit3d_cast_f32_to_bf16": (_i, [_p, _p, _ll, _p]),
@@ -64,12 +64,12 @@ SIGNATURES = {
     "vit3d_round_tf32": (_i, [_p, _p, _ll, _p]),
     "vit3d_transpose_f32_to_bf16": (_i, [_p, _p, _i, _i, _p]),
     "vit3d_add_inplace": (_i, [_p, _p, _ll, _p]),
-    "vit3d_bce_logits_fwd": (_i, [_p, _p, _f, _p, _i, _p]),
-    "vit3d_bce_logits_bwd": (_i, [_p, _p, _f, _p, _p, _i, _p]),
+    "vit3d_bce_logits_fwd": (_i, [_p, _p, _f, _p, _p, _i, _p]),
+    "vit3d_bce_logits_bwd": (_i, [_p, _p, _f, _p, _p, _p, _i, _p]),
     "vit3d_meta_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "vit3d_meta_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
-    "vit3d_sgd_step": (_i, [_p, _p, _p, _ll, _f, _f, _f, _i, _f, _p]),
-    "vit3d_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _i, _f, _p]),
+    "vit3d_sgd_step": (_i, [_p, _p, _p, _ll, _f, _f, _f, _i, _f, _p, _p]),
+    "vit3d_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _i, _f, _p, _p, _p]),
 }
 
 

@@ -253,9 +253,10 @@ int vit3d_gelu_bwd(const void* da, const void* h, void* dh, long long n, int pre
   return launch_gelu_bwd(da, h, dh, n, act_f32(prec), as_stream(stream));
 }
 int vit3d_dropout(const void* x, const void* residual, void* y, long long n, int is_f32, float p,
-                  unsigned long long seed, unsigned site, unsigned step, vit3d_stream_t stream) {
+                  unsigned long long seed, unsigned site, unsigned step, const unsigned* step_dev,
+                  vit3d_stream_t stream) {
   V3_REQUIRE(x && y && n >= 0 && p >= 0.f && p < 1.f, "dropout: bad argument");
-  return launch_dropout(x, residual, y, n, is_f32, p, seed, site, step, as_stream(stream));
+  return launch_dropout(x, residual, y, n, is_f32, p, seed, site, step, step_dev, as_stream(stream));
 }
 int vit3d_dropout_mask(unsigned char* mask, long long n, float p, unsigned long long seed, unsigned site, unsigned step,
                        vit3d_stream_t stream) {
@@ -289,15 +290,15 @@ int vit3d_add_inplace(float* y, const float* x, long long n, vit3d_stream_t stre
 }
 
 // ------------------------------------------------------------------------- loss / meta / optimizers
-int vit3d_bce_logits_fwd(const float* logits, const float* labels, float pos_weight, float* loss, int n,
-                         vit3d_stream_t stream) {
+int vit3d_bce_logits_fwd(const float* logits, const float* labels, float pos_weight, const float* pos_weight_dev,
+                         float* loss, int n, vit3d_stream_t stream) {
   V3_REQUIRE(logits && labels && loss && n > 0, "bce_fwd: bad argument");
-  return launch_bce_fwd(logits, labels, pos_weight, loss, n, as_stream(stream));
+  return launch_bce_fwd(logits, labels, pos_weight, pos_weight_dev, loss, n, as_stream(stream));
 }
-int vit3d_bce_logits_bwd(const float* logits, const float* labels, float pos_weight, const float* dloss, float* dlogits,
-                         int n, vit3d_stream_t stream) {
+int vit3d_bce_logits_bwd(const float* logits, const float* labels, float pos_weight, const float* pos_weight_dev,
+                         const float* dloss, float* dlogits, int n, vit3d_stream_t stream) {
   V3_REQUIRE(logits && labels && dlogits && n > 0, "bce_bwd: bad argument");
-  return launch_bce_bwd(logits, labels, pos_weight, dloss, dlogits, n, as_stream(stream));
+  return launch_bce_bwd(logits, labels, pos_weight, pos_weight_dev, dloss, dlogits, n, as_stream(stream));
 }
 int vit3d_meta_fwd(const float* feats, const float* w, const float* b, float* out, int B, int F, int C,
                    vit3d_stream_t stream) {
@@ -310,14 +311,16 @@ int vit3d_meta_bwd(const float* dout, const float* out, const float* feats, cons
   return launch_meta_bwd(dout, out, feats, w, dfeats, dw, db, B, F, C, as_stream(stream));
 }
 int vit3d_sgd_step(float* p, const float* g, float* mom, long long n, float lr, float momentum, float weight_decay,
-                   int first_step, float grad_scale, vit3d_stream_t stream) {
+                   int first_step, float grad_scale, const float* lr_dev, vit3d_stream_t stream) {
   V3_REQUIRE(p && g && n >= 0 && (momentum == 0.f || mom), "sgd_step: bad argument");
-  return launch_sgd(p, g, mom, n, lr, momentum, weight_decay, first_step, grad_scale, as_stream(stream));
+  return launch_sgd(p, g, mom, n, lr, momentum, weight_decay, first_step, grad_scale, lr_dev, as_stream(stream));
 }
 int vit3d_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                    float eps, float weight_decay, int step, float grad_scale, vit3d_stream_t stream) {
-  V3_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "adam_step: bad argument");
-  return launch_adam(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, as_stream(stream));
+                    float eps, float weight_decay, int step, float grad_scale, const float* lr_dev, const int* step_dev,
+                    vit3d_stream_t stream) {
+  V3_REQUIRE(p && g && m && v && n >= 0 && (step >= 1 || step_dev), "adam_step: bad argument");
+  return launch_adam(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, lr_dev, step_dev,
+                     as_stream(stream));
 }
 
 }  // extern "C"

@@ -603,17 +603,65 @@ int launch_gelu_bwd(const void* da, const void* h, void* dh, long long n, int f3
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
+// 4 elements per thread: one Philox block serves 4 consecutive elements; 8/16-byte vector accesses.
+template <bool F32>
+__global__ void __launch_bounds__(256) dropout4_kernel(const void* __restrict__ x, const void* __restrict__ residual,
+                                                       void* __restrict__ y, long long n4, long long n, uint32_t th,
+                                                       float sc, unsigned long long seed, unsigned site, unsigned step,
+                                                       const unsigned* __restrict__ step_dev) {
+  if (step_dev) step += *step_dev;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
+    const Philox4 r = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), site, step, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const long long i = q * 4;
+    float v[4], res[4] = {0.f, 0.f, 0.f, 0.f};
+    if (i + 3 < n) {
+      if (F32) {
+        const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + i);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        if (residual) {
+          const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(residual) + i);
+          res[0] = b.x; res[1] = b.y; res[2] = b.z; res[3] = b.w;
+        }
+      } else {
+        const uint2 a = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + i);
+        const __nv_bfloat162 a0 = *reinterpret_cast<const __nv_bfloat162*>(&a.x), a1 = *reinterpret_cast<const __nv_bfloat162*>(&a.y);
+        v[0] = __low2float(a0); v[1] = __high2float(a0); v[2] = __low2float(a1); v[3] = __high2float(a1);
+        if (residual) {
+          const uint2 b = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(residual) + i);
+          const __nv_bfloat162 b0 = *reinterpret_cast<const __nv_bfloat162*>(&b.x), b1 = *reinterpret_cast<const __nv_bfloat162*>(&b.y);
+          res[0] = __low2float(b0); res[1] = __high2float(b0); res[2] = __low2float(b1); res[3] = __high2float(b1);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (r.v[j] >= th ? v[j] * sc : 0.f) + res[j];
+      if (F32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + i) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+        __nv_bfloat162 o0 = __floats2bfloat162_rn(v[0], v[1]), o1 = __floats2bfloat162_rn(v[2], v[3]);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&o0); o.y = *reinterpret_cast<uint32_t*>(&o1);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + i) = o;
+      }
+    } else {
+      for (int j = 0; j < 4 && i + j < n; ++j) {
+        float o = r.v[j] >= th ? ld_any(x, i + j, F32) * sc : 0.f;
+        if (residual) o += ld_any(residual, i + j, F32);
+        st_any(y, i + j, F32, o);
+      }
+    }
+  }
+}
 int launch_dropout(const void* x, const void* residual, void* y, long long n, int f32, float p,
-                   unsigned long long seed, unsigned site, unsigned step, cudaStream_t st) {
+                   unsigned long long seed, unsigned site, unsigned step, const unsigned* step_dev, cudaStream_t st) {
   if (n <= 0) return VIT3D_OK;
   const uint32_t th = dropout_thresh(p);
   const float sc = 1.0f / (1.0f - p);
-  ew_kernel<<<ew_blocks(n), 256, 0, st>>>(n, [=] __device__(long long i) {
-    const float v = ld_any(x, i, f32);
-    float o = dropout_keep(seed, site, step, (unsigned long long)i, th) ? v * sc : 0.f;
-    if (residual) o += ld_any(residual, i, f32);
-    st_any(y, i, f32, o);
-  });
+  const long long n4 = (n + 3) / 4;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
+                         reinterpret_cast<uintptr_t>(residual)) & 15) == 0;
+  if (!aligned) { set_error("dropout: buffers must be 16-byte aligned"); return VIT3D_ERR_INVALID; }
+  if (f32) dropout4_kernel<true><<<ew_blocks(n4), 256, 0, st>>>(x, residual, y, n4, n, th, sc, seed, site, step, step_dev);
+  else dropout4_kernel<false><<<ew_blocks(n4), 256, 0, st>>>(x, residual, y, n4, n, th, sc, seed, site, step, step_dev);
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
@@ -683,7 +731,8 @@ int launch_add_inplace(float* y, const float* x, long long n, cudaStream_t st) {
 __device__ __forceinline__ float log_sigmoid(float z) { return fminf(z, 0.f) - log1pf(expf(-fabsf(z))); }
 
 __global__ void __launch_bounds__(256) bce_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y, float pw,
-                                                      float* __restrict__ loss, int n) {
+                                                      const float* __restrict__ pw_dev, float* __restrict__ loss, int n) {
+  if (pw_dev) pw = *pw_dev;
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float w = pw < 0.f ? 1.f : pw;
@@ -700,23 +749,26 @@ __global__ void __launch_bounds__(256) bce_fwd_kernel(const float* __restrict__ 
   }
 }
 __global__ void bce_bwd_kernel(const float* __restrict__ z, const float* __restrict__ y, float pw,
-                               const float* __restrict__ dloss, float* __restrict__ dz, int n) {
+                               const float* __restrict__ pw_dev, const float* __restrict__ dloss, float* __restrict__ dz,
+                               int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (pw_dev) pw = *pw_dev;
   const float w = pw < 0.f ? 1.f : pw;
   const float s = 1.f / (1.f + expf(-z[i]));
   // d/dz of -(w y log s + (1-y) log(1-s)) = -(w y (1-s)) + (1-y) s
   const float g = (1.f - y[i]) * s - w * y[i] * (1.f - s);
   dz[i] = g * (dloss ? *dloss : 1.f) / (float)n;
 }
-int launch_bce_fwd(const float* z, const float* y, float pw, float* loss, int n, cudaStream_t st) {
-  bce_fwd_kernel<<<1, 256, 0, st>>>(z, y, pw, loss, n);
+int launch_bce_fwd(const float* z, const float* y, float pw, const float* pw_dev, float* loss, int n, cudaStream_t st) {
+  bce_fwd_kernel<<<1, 256, 0, st>>>(z, y, pw, pw_dev, loss, n);
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
-int launch_bce_bwd(const float* z, const float* y, float pw, const float* dloss, float* dz, int n, cudaStream_t st) {
+int launch_bce_bwd(const float* z, const float* y, float pw, const float* pw_dev, const float* dloss, float* dz, int n,
+                   cudaStream_t st) {
   if (n <= 0) return VIT3D_OK;
-  bce_bwd_kernel<<<ceil_div(n, 256), 256, 0, st>>>(z, y, pw, dloss, dz, n);
+  bce_bwd_kernel<<<ceil_div(n, 256), 256, 0, st>>>(z, y, pw, pw_dev, dloss, dz, n);
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
@@ -778,28 +830,33 @@ int launch_meta_bwd(const float* dout, const float* out, const float* f, const f
 }
 
 // ============================================================================ optimizers (N1)
+// lr_dev / step_dev (device scalars, may be NULL) override the host values: a captured CUDA graph can
+// follow an LR schedule and Adam's bias correction without re-capture.
 int launch_sgd(float* p, const float* g, float* mom, long long n, float lr, float momentum, float wd, int first,
-               float gscale, cudaStream_t st) {
+               float gscale, const float* lr_dev, cudaStream_t st) {
   if (n <= 0) return VIT3D_OK;
   ew_kernel<<<ew_blocks(n), 256, 0, st>>>(n, [=] __device__(long long i) {
+    const float lr_ = lr_dev ? *lr_dev : lr;
     float d = g[i] * gscale + wd * p[i];
     if (momentum != 0.f) {
       const float b = first ? d : momentum * mom[i] + d;
       mom[i] = b;
       d = b;
     }
-    p[i] -= lr * d;
+    p[i] -= lr_ * d;
   });
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
-                float wd, int step, float gscale, cudaStream_t st) {
+                float wd, int step, float gscale, const float* lr_dev, const int* step_dev, cudaStream_t st) {
   if (n <= 0) return VIT3D_OK;
-  const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
-  const float step_size = lr / bc1;
-  const float inv_sqrt_bc2 = 1.f / sqrtf(bc2);
   ew_kernel<<<ew_blocks(n), 256, 0, st>>>(n, [=] __device__(long long i) {
+    const float lr_ = lr_dev ? *lr_dev : lr;
+    const float t = (float)(step_dev ? *step_dev : step);
+    const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+    const float step_size = lr_ / bc1;
+    const float inv_sqrt_bc2 = rsqrtf(bc2);
     const float gr = g[i] * gscale + wd * p[i];
     const float mi = b1 * m[i] + (1.f - b1) * gr;
     const float vi = b2 * v[i] + (1.f - b2) * gr * gr;

@@ -38,21 +38,22 @@ int launch_attn_bwd_generic(const void* dctx, const void* qkv, int f32, void* dq
 int launch_gelu_fwd(const void* h, void* a, long long n, int f32, cudaStream_t st);
 int launch_gelu_bwd(const void* da, const void* h, void* dh, long long n, int f32, cudaStream_t st);
 int launch_dropout(const void* x, const void* residual, void* y, long long n, int f32, float p,
-                   unsigned long long seed, unsigned site, unsigned step, cudaStream_t st);
+                   unsigned long long seed, unsigned site, unsigned step, const unsigned* step_dev, cudaStream_t st);
 int launch_dropout_mask(unsigned char* mask, long long n, float p, unsigned long long seed, unsigned site, unsigned step,
                         cudaStream_t st);
 int launch_dropout_masked(const void* x, const unsigned char* mask, const void* residual, void* y, long long n,
                           int f32, float p, cudaStream_t st);
 int launch_cast(const void* x, int x_f32, void* y, int y_f32, long long n, cudaStream_t st);
 int launch_add_inplace(float* y, const float* x, long long n, cudaStream_t st);
-int launch_bce_fwd(const float* z, const float* y, float pw, float* loss, int n, cudaStream_t st);
-int launch_bce_bwd(const float* z, const float* y, float pw, const float* dloss, float* dz, int n, cudaStream_t st);
+int launch_bce_fwd(const float* z, const float* y, float pw, const float* pw_dev, float* loss, int n, cudaStream_t st);
+int launch_bce_bwd(const float* z, const float* y, float pw, const float* pw_dev, const float* dloss, float* dz, int n,
+                   cudaStream_t st);
 int launch_meta_fwd(const float* f, const float* w, const float* b, float* out, int B, int F, int C, cudaStream_t st);
 int launch_meta_bwd(const float* dout, const float* out, const float* f, const float* w, float* df, float* dw, float* db,
                     int B, int F, int C, cudaStream_t st);
 int launch_sgd(float* p, const float* g, float* mom, long long n, float lr, float momentum, float wd, int first,
-               float gscale, cudaStream_t st);
+               float gscale, const float* lr_dev, cudaStream_t st);
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
-                float wd, int step, float gscale, cudaStream_t st);
+                float wd, int step, float gscale, const float* lr_dev, const int* step_dev, cudaStream_t st);
 
 }  // namespace vit3d

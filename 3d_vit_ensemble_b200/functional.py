@@ -309,7 +309,8 @@ class DropoutFn(torch.autograd.Function):
                 raise _lib.Vit3dError("dropout mask has the wrong number of elements")
             call("vit3d_dropout_masked", ptr(x), ptr(mask), ptr(residual), ptr(y), x.numel(), f32, float(p), stream())
         else:
-            call("vit3d_dropout", ptr(x), ptr(residual), ptr(y), x.numel(), f32, float(p), seed, site, step, stream())
+            call("vit3d_dropout", ptr(x), ptr(residual), ptr(y), x.numel(), f32, float(p), seed, site, step,
+                 ptr(_STATE.get("step_dev")), stream())
         ctx.meta = (p, seed, site, step, mask, residual is not None)
         return y
 
@@ -322,7 +323,8 @@ class DropoutFn(torch.autograd.Function):
         if mask is not None:
             call("vit3d_dropout_masked", ptr(dy), ptr(mask), None, ptr(dx), dy.numel(), f32, float(p), stream())
         else:
-            call("vit3d_dropout", ptr(dy), None, ptr(dx), dy.numel(), f32, float(p), seed, site, step, stream())
+            call("vit3d_dropout", ptr(dy), None, ptr(dx), dy.numel(), f32, float(p), seed, site, step,
+                 ptr(_STATE.get("step_dev")), stream())
         return dx, (dy if has_res else None), None, None, None, None, None
 
 
@@ -369,19 +371,25 @@ class BceLogitsFn(torch.autograd.Function):
         if y.numel() != z.numel():
             raise _lib.Vit3dError("BCE: logits and labels differ in size")
         loss = torch.empty((), device=z.device)
-        pw = -1.0 if pos_weight is None else float(pos_weight)
-        call("vit3d_bce_logits_fwd", ptr(z), ptr(y), pw, ptr(loss), z.numel(), stream())
-        ctx.save_for_backward(z, y)
+        pw_dev = None
+        if isinstance(pos_weight, torch.Tensor) and pos_weight.is_cuda:
+            # device-resident class weight (CUDA-graph replays): read by the kernel, no host sync
+            pw_dev = pos_weight.reshape(1).float()
+            pw = 1.0
+        else:
+            pw = -1.0 if pos_weight is None else float(pos_weight)
+        call("vit3d_bce_logits_fwd", ptr(z), ptr(y), pw, ptr(pw_dev), ptr(loss), z.numel(), stream())
+        ctx.save_for_backward(z, y, pw_dev)
         ctx.meta = (pw, logits.shape)
         return loss
 
     @staticmethod
     def backward(ctx, dloss):
-        z, y = ctx.saved_tensors
+        z, y, pw_dev = ctx.saved_tensors
         pw, shape = ctx.meta
         dz = torch.empty_like(z)
         dl = _c(dloss.float())
-        call("vit3d_bce_logits_bwd", ptr(z), ptr(y), pw, ptr(dl), ptr(dz), z.numel(), stream())
+        call("vit3d_bce_logits_bwd", ptr(z), ptr(y), pw, ptr(pw_dev), ptr(dl), ptr(dz), z.numel(), stream())
         return dz.reshape(shape), None, None
 
 

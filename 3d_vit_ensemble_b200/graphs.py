@@ -1,0 +1,117 @@
+"""CUDA-graph execution of the path (launch-bound regimes: the reference trains at batch 4 and validates
+at batch 1, train_baseline_cv.py:240, :64-101).  Every kernel of libvit3d_sm100.so is launched on the
+caller's stream without synchronising, so a whole forward - or a whole training step including the
+optimizer - is capturable; values that change from step to step (dropout step, per-batch class weight,
+learning rate, Adam step) are read from device scalars instead of being baked into the graph."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import functional as F
+
+
+class GraphedInference:
+    """`model(x)` (eval, no_grad) replayed from a CUDA graph, one graph per input shape.
+
+        g = GraphedInference(model)
+        logits, attn, enc = g(x)            # outputs are static buffers, overwritten by the next call
+    """
+
+    def __init__(self, model: torch.nn.Module, warmup: int = 2):
+        self.model = model
+        self.warmup = warmup
+        self._graphs = {}
+
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor):
+        key = (tuple(x.shape), x.dtype)
+        ent = self._graphs.get(key)
+        if ent is None:
+            self.model.eval()
+            static_x = x.clone()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(self.warmup):          # populates the weight-shadow cache: no casts in the graph
+                    self.model(static_x)
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.model(static_x)
+            ent = (g, static_x, out)
+            self._graphs[key] = ent
+        g, static_x, out = ent
+        static_x.copy_(x, non_blocking=True)
+        g.replay()
+        return out
+
+
+class GraphedTrainStep:
+    """One captured training step: loss = model(x, y, pos_weight); loss.backward(); optimizer.step().
+
+    `optimizer` must be a `optim.FusedSGD` / `FusedAdam` (flat arena: the gradient zeroing, the step and
+    the weight-shadow refresh are all inside the graph).  The warm-up iterations before capture ARE
+    training steps on the first batch passed in.
+
+        step = GraphedTrainStep(model, opt)
+        loss = step(x, y, pos_weight)       # pos_weight: float / 0-dim tensor / None; loss: static 0-dim tensor
+        step.set_lr(lr)                     # follow an LR schedule without re-capturing
+    """
+
+    def __init__(self, model: torch.nn.Module, optimizer, warmup: int = 3, grad_scale: float = 1.0):
+        self.model = model
+        self.opt = optimizer
+        self.warmup = max(1, warmup)
+        self.grad_scale = grad_scale
+        self._graph = None
+        dev = optimizer.arena.flat.device
+        self.lr_dev = torch.tensor([float(optimizer.param_groups[0]["lr"])], device=dev, dtype=torch.float32)
+        self.pw_dev = torch.ones(1, device=dev, dtype=torch.float32)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)      # dropout mask offset, Adam step
+        optimizer.lr_dev = self.lr_dev
+        if hasattr(optimizer, "exp_avg"):
+            optimizer.step_dev = self.step_dev
+
+    def set_lr(self, lr: float):
+        self.lr_dev.fill_(float(lr))
+        self.opt.param_groups[0]["lr"] = float(lr)
+
+    def _one(self):
+        self.step_dev.add_(1)
+        self.opt.zero_grad()
+        loss = self.model(self.x, self.y, self.pw_dev if self.use_pw else None)
+        loss.backward()
+        self.opt.step(grad_scale=self.grad_scale)
+        return loss
+
+    def __call__(self, x, y, pos_weight=None):
+        if self._graph is None:
+            self.model.train()
+            self.x, self.y = x.clone(), y.clone().float()
+            self.use_pw = pos_weight is not None
+            if self.use_pw:
+                self.pw_dev.fill_(float(pos_weight))
+            F._STATE["step_dev"] = self.step_dev
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(self.warmup):
+                    self._one()
+            torch.cuda.current_stream().wait_stream(s)
+            F.invalidate_weight_shadows()       # the captured step must re-derive the bf16 shadows itself
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self.loss = self._one()
+            F.invalidate_weight_shadows()       # shadows made during capture live in the graph's pool
+            self._graph.replay()                # capture records, it does not execute: run the step now
+            return self.loss
+        if (pos_weight is not None) != self.use_pw:
+            raise ValueError("GraphedTrainStep was captured %s pos_weight" % ("with" if self.use_pw else "without"))
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+        if self.use_pw:
+            self.pw_dev.fill_(float(pos_weight))
+        self._graph.replay()
+        return self.loss

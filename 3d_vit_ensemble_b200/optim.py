@@ -75,6 +75,9 @@ class _FlatOptimizer(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self.arena = FlatArena(self.param_groups[0]["params"])
         self._steps = 0
+        # device-resident lr / step for CUDA-graph replays (see graphs.GraphedTrainStep); None = host values
+        self.lr_dev = None
+        self.step_dev = None
 
     def zero_grad(self, set_to_none: bool = False):
         self.arena.zero_grad()
@@ -94,7 +97,7 @@ class FusedSGD(_FlatOptimizer):
         a = self.arena
         a.sync_grads()
         call("vit3d_sgd_step", ptr(a.flat), ptr(a.flat_grad), ptr(self.momentum_buffer), a.numel, float(g["lr"]),
-             float(g["momentum"]), float(g["weight_decay"]), int(self._steps == 0), float(grad_scale), stream())
+             float(g["momentum"]), float(g["weight_decay"]), 0, float(grad_scale), ptr(self.lr_dev), stream())
         self._steps += 1
         invalidate_weight_shadows()   # the kernel updated the weights behind torch's version counters
         return loss
@@ -117,6 +120,6 @@ class FusedAdam(_FlatOptimizer):
         self._steps += 1
         call("vit3d_adam_step", ptr(a.flat), ptr(a.flat_grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), a.numel,
              float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
-             self._steps, float(grad_scale), stream())
+             self._steps, float(grad_scale), ptr(self.lr_dev), ptr(self.step_dev), stream())
         invalidate_weight_shadows()
         return loss

@@ -122,8 +122,11 @@ int vit3d_gelu_bwd(const void* da, const void* h, void* dh, long long n, int pre
 /* Dropout(p) in training (modeling.py:121,123,174): y = x * keep / (1-p) (+ residual, same type, may be
  * NULL: the x + Mlp(..) add of modeling.py:196) with a counter-based Philox mask keyed by
  * (seed, site, step, element index); the same call on dy (residual NULL) gives dx. */
+/* step_dev (device, may be NULL) is added to `step` on the device: lets a captured CUDA graph draw new
+ * masks at every replay. */
 int vit3d_dropout(const void* x, const void* residual, void* y, long long n, int is_f32, float p,
-                  unsigned long long seed, unsigned site, unsigned step, vit3d_stream_t stream);
+                  unsigned long long seed, unsigned site, unsigned step, const unsigned* step_dev,
+                  vit3d_stream_t stream);
 /* export the keep mask (1 byte per element) for mask-injection parity tests */
 int vit3d_dropout_mask(unsigned char* mask, long long n, float p, unsigned long long seed, unsigned site,
                        unsigned step, vit3d_stream_t stream);
@@ -141,11 +144,13 @@ int vit3d_add_inplace(float* y, const float* x, long long n, vit3d_stream_t stre
 
 /* ---------------------------------------------------------------- a7: head loss
  * BCEWithLogitsLoss(pos_weight)(logits.view(-1,1), labels.view(-1,1)), mean (modeling.py:283-286).
- * pos_weight < 0 means None.  loss: 1 float.  dlogits = dloss * dL/dlogits (dloss: device scalar or NULL=1). */
-int vit3d_bce_logits_fwd(const float* logits, const float* labels, float pos_weight, float* loss, int n,
-                         vit3d_stream_t stream);
-int vit3d_bce_logits_bwd(const float* logits, const float* labels, float pos_weight, const float* dloss,
-                         float* dlogits, int n, vit3d_stream_t stream);
+ * pos_weight < 0 means None; pos_weight_dev (device scalar, may be NULL) overrides it (CUDA-graph replays
+ * with a per-batch class weight).  loss: 1 float.  dlogits = dloss * dL/dlogits (dloss: device scalar or
+ * NULL = 1). */
+int vit3d_bce_logits_fwd(const float* logits, const float* labels, float pos_weight, const float* pos_weight_dev,
+                         float* loss, int n, vit3d_stream_t stream);
+int vit3d_bce_logits_bwd(const float* logits, const float* labels, float pos_weight, const float* pos_weight_dev,
+                         const float* dloss, float* dlogits, int n, vit3d_stream_t stream);
 
 /* ---------------------------------------------------------------- a9: meta-classifier
  * out[B,C] = sigmoid(cat(member logits)[B,F] @ w[C,F]^T + b) (modeling.py:355-356) */
@@ -158,9 +163,12 @@ int vit3d_meta_bwd(const float* dout, const float* out, const float* feats, cons
  * torch.optim.SGD(momentum, weight_decay) (train_baseline_cv.py:111-114) and Adam (train_ensemble_whole_dataset.py:53)
  * semantics of torch 2.x (first momentum step copies the gradient). */
 int vit3d_sgd_step(float* p, const float* g, float* mom, long long n, float lr, float momentum, float weight_decay,
-                   int first_step, float grad_scale, vit3d_stream_t stream);
+                   int first_step, float grad_scale, const float* lr_dev, vit3d_stream_t stream);
 int vit3d_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                    float eps, float weight_decay, int step, float grad_scale, vit3d_stream_t stream);
+                    float eps, float weight_decay, int step, float grad_scale, const float* lr_dev, const int* step_dev,
+                    vit3d_stream_t stream);
+/* lr_dev / step_dev: optional DEVICE scalars that override lr / step (CUDA-graph replays under an LR
+ * schedule).  first_step may stay 0 when the momentum buffer starts zeroed (same arithmetic). */
 
 #ifdef __cplusplus
 }

@@ -293,7 +293,7 @@ def test_fused_sgd_and_adam_match_torch():
     for i, g in enumerate((g1, g2)):
         pr.grad = g.clone()
         opt.step()
-        call("vit3d_sgd_step", ptr(p), ptr(g.to(DEV)), ptr(mom), n, 1e-2, 0.9, 1e-2, int(i == 0), 1.0, stream())
+        call("vit3d_sgd_step", ptr(p), ptr(g.to(DEV)), ptr(mom), n, 1e-2, 0.9, 1e-2, int(i == 0), 1.0, None, stream())
     np.testing.assert_allclose(p.cpu().numpy(), pr.detach().numpy(), atol=1e-6)
     pr = torch.nn.Parameter(p0.clone())
     opt = torch.optim.Adam([pr], lr=1e-3)
@@ -303,7 +303,7 @@ def test_fused_sgd_and_adam_match_torch():
         pr.grad = g.clone()
         opt.step()
         call("vit3d_adam_step", ptr(p), ptr(g.to(DEV)), ptr(m_), ptr(v_), n, 1e-3, 0.9, 0.999, 1e-8, 0.0, i + 1, 1.0,
-             stream())
+             None, None, stream())
     np.testing.assert_allclose(p.cpu().numpy(), pr.detach().numpy(), atol=2e-6)
 
 
