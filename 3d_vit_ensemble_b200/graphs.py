@@ -9,6 +9,7 @@ from typing import Optional
 
 import torch
 
+from . import _lib
 from . import functional as F
 
 
@@ -23,6 +24,8 @@ class GraphedInference:
         self.model = model
         self.warmup = warmup
         self._graphs = {}
+        self.launches_per_replay = 0
+        self.replays = 0
 
     @torch.no_grad()
     def __call__(self, x: torch.Tensor):
@@ -38,13 +41,16 @@ class GraphedInference:
                     self.model(static_x)
             torch.cuda.current_stream().wait_stream(s)
             g = torch.cuda.CUDAGraph()
+            n0 = _lib.lib().vit3d_launch_count()
             with torch.cuda.graph(g):
                 out = self.model(static_x)
+            self.launches_per_replay = _lib.lib().vit3d_launch_count() - n0     # kernels recorded in the graph
             ent = (g, static_x, out)
             self._graphs[key] = ent
         g, static_x, out = ent
         static_x.copy_(x, non_blocking=True)
         g.replay()
+        self.replays += 1
         return out
 
 
@@ -66,6 +72,8 @@ class GraphedTrainStep:
         self.warmup = max(1, warmup)
         self.grad_scale = grad_scale
         self._graph = None
+        self.launches_per_replay = 0
+        self.replays = 0
         dev = optimizer.arena.flat.device
         self.lr_dev = torch.tensor([float(optimizer.param_groups[0]["lr"])], device=dev, dtype=torch.float32)
         self.pw_dev = torch.ones(1, device=dev, dtype=torch.float32)
@@ -102,10 +110,13 @@ class GraphedTrainStep:
             torch.cuda.current_stream().wait_stream(s)
             F.invalidate_weight_shadows()       # the captured step must re-derive the bf16 shadows itself
             self._graph = torch.cuda.CUDAGraph()
+            n0 = _lib.lib().vit3d_launch_count()
             with torch.cuda.graph(self._graph):
                 self.loss = self._one()
+            self.launches_per_replay = _lib.lib().vit3d_launch_count() - n0
             F.invalidate_weight_shadows()       # shadows made during capture live in the graph's pool
             self._graph.replay()                # capture records, it does not execute: run the step now
+            self.replays += 1
             return self.loss
         if (pos_weight is not None) != self.use_pw:
             raise ValueError("GraphedTrainStep was captured %s pos_weight" % ("with" if self.use_pw else "without"))
@@ -114,4 +125,5 @@ class GraphedTrainStep:
         if self.use_pw:
             self.pw_dev.fill_(float(pos_weight))
         self._graph.replay()
+        self.replays += 1
         return self.loss

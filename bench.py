@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--vis", type=int, default=1, help="materialise attention probabilities (reference default vis=True)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="volumes per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graphs", type=int, default=1, help="replay the step from a CUDA graph (vit3d_b200.graphs)")
     return ap.parse_args()
 
 
@@ -206,7 +207,20 @@ def main():
         from vit3d_b200.dist import ShardedEnsemble
         sharded = ShardedEnsemble(model, costs=[O.fwd_flops_per_volume(c) for c in cfgs])
 
+    graphed = None
+    if args.graphs and train and world == 1:
+        from vit3d_b200.graphs import GraphedTrainStep
+        graphed = GraphedTrainStep(model, opt, warmup=2)
+    elif args.graphs and not train and sharded is None:
+        from vit3d_b200.graphs import GraphedInference
+        graphed = GraphedInference(model)
+
     def step_dev(x, y):
+        if graphed is not None:
+            if train:
+                return graphed(x, y, O.balanced_pos_weight(y_host))
+            out = graphed(x)
+            return out[0] if isinstance(out, tuple) else out
         if train:
             pw = global_pos_weight(y) if world > 1 else O.balanced_pos_weight(y_host)
             if reducer is not None:
@@ -234,12 +248,15 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = L.vit3d_launch_count()
+        r0 = graphed.replays if graphed is not None else 0
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
         torch.cuda.synchronize()
         n1 = L.vit3d_launch_count()
+        if graphed is not None:     # kernels replayed from the captured graph (counted once, at capture)
+            n1 += (graphed.replays - r0) * graphed.launches_per_replay
         ms = e0.elapsed_time(e1)
         if dist is not None:
             t = torch.tensor([ms], device=dev)
@@ -288,7 +305,7 @@ def main():
             "scaling": "strong" if len(members) > 1 else "weak",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": wl["name"], "batch_per_gpu": B, "global_batch": units, "vis": bool(args.vis),
-                       "precision": args.precision, "l2": "inputs larger than L2 (batch of fp32 volumes = %.0f MB)" % (B * 327680 / 1e6),
+                       "precision": args.precision, "cuda_graph": graphed is not None, "l2": "inputs larger than L2 (batch of fp32 volumes = %.0f MB)" % (B * 327680 / 1e6),
                        "parallelism": (f"dp{world}: batch sharded, per-Block gradient all-reduce (NCCL) overlapped with backward, fused SGD step"
                                        if train else (f"{world} ranks: (member, batch-slice) work list balanced by FLOPs, all-gather of member logits, meta-head on every rank"
                                                       if len(members) > 1 else f"dp{world} (independent volumes, no data-path collective)"))},
