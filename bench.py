@@ -273,14 +273,59 @@ def main():
 
     res_host = torch.empty((B, 1) if not train else (), dtype=torch.float32).pin_memory()
 
-    def step_e2e():
-        xd = x_host.to(dev, non_blocking=True)
-        yd = y_host.to(dev, non_blocking=True) if train else None
-        out = step_dev(xd, yd)
-        res_host.copy_(out.detach().reshape(res_host.shape), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    # End-to-end: every step copies ITS batch from pinned host memory (H2D on a copy stream, double
+    # buffered so the copy of step s+1 overlaps the compute of step s), runs the public module call and
+    # reads the result back to the host (D2H) before the step counts as done.
+    copy_stream = torch.cuda.Stream()
+    xbuf = [torch.empty_like(x_dev) for _ in range(2)]
+    ybuf = [torch.empty_like(y_dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
 
-    ms_e2e, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+    def issue_copy(s):
+        b = s & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])          # the compute that read this buffer two steps ago is done
+            xbuf[b].copy_(x_host, non_blocking=True)
+            if train:
+                ybuf[b].copy_(y_host, non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def run_e2e(steps):
+        main = torch.cuda.current_stream()
+        for b in range(2):
+            consumed[b].record(main)
+        issue_copy(0)
+        for s in range(steps):
+            b = s & 1
+            main.wait_event(ready[b])
+            out = step_dev(xbuf[b], ybuf[b] if train else None)
+            consumed[b].record(main)
+            if s + 1 < steps:
+                issue_copy(s + 1)
+            res_host.copy_(out.detach().reshape(res_host.shape), non_blocking=True)
+            main.synchronize()
+
+    def timed_e2e(steps, warm):
+        run_e2e(warm)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_e2e(steps)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+            dist.barrier()
+        return ms
+
+    ms_e2e = timed_e2e(args.steps, max(3, args.warmup // 2))
 
     units = B if len(members) > 1 else world * B          # the sharded ensemble splits ONE batch over the ranks
     value = units * args.steps / (ms_dev * 1e-3)
@@ -367,7 +412,12 @@ def roofline_probe(args, cfg, B, dev):
     ach = flops / (ms * 1e-3) / 1e12
     return {"kernel": "fc1+GELU GEMM (vit3d_linear_fwd, M=%d N=%d K=%d, %s)" % (M, N, K, "tcgen05" if tc else "fp32 FMA fallback"),
             "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": ach / peaks["bf16_tflops"], "traffic": None, "ms_per_launch": ms,
+            "frac": ach / peaks["bf16_tflops"],
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one ncu --set full capture
+            # (profiles/r01_fc1_gelu_gemm_ncu_full_raw.csv); only valid for the captured shape
+            "traffic": 254.8e6 if (M == 66560 and N == 2048 and K == 256 and prec == "bf16" and tc) else None,
+            "traffic_unit": "bytes per launch", "algorithmic_bytes": float(M * K * 2 + N * K * 2 + M * N * 2) if prec == "bf16" else None,
+            "ms_per_launch": ms,
             "peak_source": peaks.get("source"), "how": "kernel timed alone, 10 launches, CUDA events (burst peak applies)"}
 
 
