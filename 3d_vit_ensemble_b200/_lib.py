@@ -62,6 +62,7 @@ SIGNATURES = {
     "vit3d_cast_f32_to_bf16": (_i, [_p, _p, _ll, _p]),
     "vit3d_cast_bf16_to_f32": (_i, [_p, _p, _ll, _p]),
     "vit3d_round_tf32": (_i, [_p, _p, _ll, _p]),
+    "vit3d_u8_to_f32": (_i, [_p, _p, _ll, _f, _p]),
     "vit3d_transpose_f32_to_bf16": (_i, [_p, _p, _i, _i, _p]),
     "vit3d_add_inplace": (_i, [_p, _p, _ll, _p]),
     "vit3d_bce_logits_fwd": (_i, [_p, _p, _f, _p, _p, _i, _p]),

@@ -276,6 +276,10 @@ int vit3d_transpose_f32_to_bf16(const float* x, void* y, int rows, int cols, vit
   V3_REQUIRE(x && y && rows >= 0 && cols >= 0, "transpose: bad argument");
   return launch_transpose_cast(x, y, rows, cols, as_stream(stream));
 }
+int vit3d_u8_to_f32(const unsigned char* x, float* y, long long n, float mean, vit3d_stream_t stream) {
+  V3_REQUIRE(x && y && n >= 0, "u8_to_f32: bad argument");
+  return launch_u8_to_f32(x, y, n, mean, as_stream(stream));
+}
 int vit3d_round_tf32(const float* x, float* y, long long n, vit3d_stream_t stream) {
   V3_REQUIRE(x && y && n >= 0, "round_tf32: bad argument");
   return launch_round_tf32(x, y, n, as_stream(stream));

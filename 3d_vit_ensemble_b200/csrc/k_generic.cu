@@ -713,6 +713,32 @@ int launch_transpose_cast(const float* x, void* y, int rows, int cols, cudaStrea
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
+// N2: y = float(x_u8) - mean, 16 elements per thread (one 16-byte load, four 16-byte stores)
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ x, float* __restrict__ y, long long n16,
+                                                        long long n, float mean) {
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n16; q += (long long)gridDim.x * blockDim.x) {
+    const long long i = q * 16;
+    if (i + 15 < n) {
+      const uint4 v = *reinterpret_cast<const uint4*>(x + i);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4*>(y + i + 4 * j) =
+            make_float4((float)(w[j] & 255u) - mean, (float)((w[j] >> 8) & 255u) - mean, (float)((w[j] >> 16) & 255u) - mean,
+                        (float)(w[j] >> 24) - mean);
+    } else {
+      for (long long k = i; k < n; ++k) y[k] = (float)x[k] - mean;
+    }
+  }
+}
+int launch_u8_to_f32(const uint8_t* x, float* y, long long n, float mean, cudaStream_t st) {
+  if (n <= 0) return VIT3D_OK;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) { set_error("u8_to_f32: buffers must be 16-byte aligned"); return VIT3D_ERR_INVALID; }
+  const long long n16 = (n + 15) / 16;
+  u8_to_f32_kernel<<<ew_blocks(n16), 256, 0, st>>>(x, y, n16, n, mean);
+  V3_LAUNCH_CHECK();
+  return VIT3D_OK;
+}
 int launch_round_tf32(const float* x, float* y, long long n, cudaStream_t st) {
   if (n <= 0) return VIT3D_OK;
   ew_kernel<<<ew_blocks(n), 256, 0, st>>>(n, [=] __device__(long long i) { y[i] = round_tf32(x[i]); });

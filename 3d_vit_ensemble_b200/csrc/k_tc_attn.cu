@@ -21,7 +21,7 @@ constexpr int AT_A = 256;          // all-head size (heads * D)
 constexpr int AT_ROWB = 3 * AT_A * 2;       // 1536 bytes of qkv per token
 constexpr int AT_PITCH = AT_ROWB + 16;      // padded smem row pitch: conflict-free ldmatrix
 constexpr int AT_BUF = AT_S * AT_PITCH;     // 100,880 bytes per volume buffer
-constexpr int AT_THREADS = 256;
+constexpr int AT_THREADS = 512;          // 16 warps: 4 per scheduler hide the ldmatrix / mma / MUFU latencies
 constexpr int AT_SMEM = 2 * AT_BUF + 64 + 128;
 
 __device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -56,6 +56,11 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
@@ -151,10 +156,10 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
       for (int nt = 0; nt < NT; ++nt) {
         const int c = nt * 8 + 2 * t;
         const bool v0 = c < AT_S, v1 = c + 1 < AT_S;
-        s[nt][0] = v0 ? exp2f((s[nt][0] - mx0) * scale_log2e) : 0.f;
-        s[nt][1] = v1 ? exp2f((s[nt][1] - mx0) * scale_log2e) : 0.f;
-        s[nt][2] = v0 ? exp2f((s[nt][2] - mx1) * scale_log2e) : 0.f;
-        s[nt][3] = v1 ? exp2f((s[nt][3] - mx1) * scale_log2e) : 0.f;
+        s[nt][0] = v0 ? ex2_approx((s[nt][0] - mx0) * scale_log2e) : 0.f;
+        s[nt][1] = v1 ? ex2_approx((s[nt][1] - mx0) * scale_log2e) : 0.f;
+        s[nt][2] = v0 ? ex2_approx((s[nt][2] - mx1) * scale_log2e) : 0.f;
+        s[nt][3] = v1 ? ex2_approx((s[nt][3] - mx1) * scale_log2e) : 0.f;
         sum0 += s[nt][0] + s[nt][1];
         sum1 += s[nt][2] + s[nt][3];
       }
@@ -165,6 +170,8 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
       const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
       const int row0 = r0 + g, row1 = r0 + g + 8;
       if (probs) {
+        // measured: staging these rows through shared memory for 128-byte-line stores is not faster (the
+        // kernel is latency-, not store-bound), so they go out straight from the accumulator registers
         float* p0 = probs + (((size_t)b * HEADS + h) * AT_S + row0) * AT_S;
         float* p1 = probs + (((size_t)b * HEADS + h) * AT_S + row1) * AT_S;
 #pragma unroll
@@ -350,10 +357,10 @@ attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16* 
       for (int nt = 0; nt < NT; ++nt) {
         const int c = nt * 8 + 2 * t;
         const bool v0 = c < AT_S, v1 = c + 1 < AT_S;
-        s[nt][0] = v0 ? exp2f((s[nt][0] - mx0) * scale_log2e) : 0.f;
-        s[nt][1] = v1 ? exp2f((s[nt][1] - mx0) * scale_log2e) : 0.f;
-        s[nt][2] = v0 ? exp2f((s[nt][2] - mx1) * scale_log2e) : 0.f;
-        s[nt][3] = v1 ? exp2f((s[nt][3] - mx1) * scale_log2e) : 0.f;
+        s[nt][0] = v0 ? ex2_approx((s[nt][0] - mx0) * scale_log2e) : 0.f;
+        s[nt][1] = v1 ? ex2_approx((s[nt][1] - mx0) * scale_log2e) : 0.f;
+        s[nt][2] = v0 ? ex2_approx((s[nt][2] - mx1) * scale_log2e) : 0.f;
+        s[nt][3] = v1 ? ex2_approx((s[nt][3] - mx1) * scale_log2e) : 0.f;
         sum0 += s[nt][0] + s[nt][1];
         sum1 += s[nt][2] + s[nt][3];
       }
@@ -447,10 +454,10 @@ attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16* 
         const bool v0 = c < AT_S, v1 = c + 1 < AT_S;
         const float m0 = v0 ? st[c] : 0.f, i0 = v0 ? st[80 + c] : 0.f, d0 = v0 ? st[160 + c] : 0.f;
         const float m1 = v1 ? st[c + 1] : 0.f, i1 = v1 ? st[80 + c + 1] : 0.f, d1 = v1 ? st[160 + c + 1] : 0.f;
-        const float p00 = v0 ? exp2f((s[nt][0] - m0) * scale_log2e) * i0 : 0.f;       // P^T
-        const float p01 = v1 ? exp2f((s[nt][1] - m1) * scale_log2e) * i1 : 0.f;
-        const float p10 = v0 ? exp2f((s[nt][2] - m0) * scale_log2e) * i0 : 0.f;
-        const float p11 = v1 ? exp2f((s[nt][3] - m1) * scale_log2e) * i1 : 0.f;
+        const float p00 = v0 ? ex2_approx((s[nt][0] - m0) * scale_log2e) * i0 : 0.f;       // P^T
+        const float p01 = v1 ? ex2_approx((s[nt][1] - m1) * scale_log2e) * i1 : 0.f;
+        const float p10 = v0 ? ex2_approx((s[nt][2] - m0) * scale_log2e) * i0 : 0.f;
+        const float p11 = v1 ? ex2_approx((s[nt][3] - m1) * scale_log2e) * i1 : 0.f;
         s[nt][0] = p00; s[nt][1] = p01; s[nt][2] = p10; s[nt][3] = p11;
         dp[nt][0] = p00 * (dp[nt][0] - d0) * scale; dp[nt][1] = p01 * (dp[nt][1] - d1) * scale;   // dS^T
         dp[nt][2] = p10 * (dp[nt][2] - d0) * scale; dp[nt][3] = p11 * (dp[nt][3] - d1) * scale;

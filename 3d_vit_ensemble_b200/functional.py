@@ -133,6 +133,16 @@ class PatchEmbedFn(torch.autograd.Function):
         return None, dw, db, dcls, dpos, None
 
 
+def u8_volumes_to_f32(x_u8: torch.Tensor, mean: float) -> torch.Tensor:
+    """N2: uint8 volumes (as stored on disk, create_dataset.py:46-59) -> fp32 minus the training mean
+    (tools.py:18-26), on the device; 4x less host->device traffic than shipping fp32 volumes."""
+    _need_cuda(x_u8)
+    x_u8 = _c(x_u8)
+    y = torch.empty(x_u8.shape, device=x_u8.device, dtype=torch.float32)
+    call("vit3d_u8_to_f32", ptr(x_u8), ptr(y), x_u8.numel(), float(mean), stream())
+    return y
+
+
 def patch_gather(x: torch.Tensor, patch) -> torch.Tensor:
     """Bit-exact im2col permutation used by the embedding (for tests / inspection)."""
     _need_cuda(x)

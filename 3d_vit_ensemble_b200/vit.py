@@ -215,6 +215,7 @@ class VisionTransformer(nn.Module):
         self.img_size = img_size
         self.transformer = Transformer(config, img_size, vis)
         self.head = Linear(config.hidden_size, num_classes)
+        self.input_mean = 0.0      # N2: subtracted from uint8 volumes on the device (tools.normalize's mean)
         self.set_precision(precision or F.get_precision())
 
     def set_precision(self, precision: str):
@@ -228,6 +229,8 @@ class VisionTransformer(nn.Module):
 
     def forward(self, x, labels=None, weights=None):
         F._need_cuda(x)
+        if x.dtype == torch.uint8:          # N2: raw 8-bit volumes; (u8 - mean) happens on the device
+            x = F.u8_volumes_to_f32(x, self.input_mean)
         x, attn_weights = self.transformer(x)
         logits = F.linear(x[:, 0], self.head.weight, self.head.bias, prec="fp32", out_f32=True)
         if labels is not None:
@@ -250,6 +253,8 @@ class TransformerEnsemble(nn.Module):
         self.classifier = nn.Linear(len(transformers) * in_features, n_classes)
 
     def forward(self, x):
+        if x.dtype == torch.uint8:          # N2: convert once for all members (they share input_mean of member 0)
+            x = F.u8_volumes_to_f32(x, self.transformers[0].input_mean)
         outputs = [transformer(x)[0] for transformer in self.transformers]
         concatenated_output = torch.cat(outputs, dim=1)
         return F.MetaFn.apply(concatenated_output, self.classifier.weight, self.classifier.bias)

@@ -135,6 +135,10 @@ int vit3d_dropout_masked(const void* x, const unsigned char* mask, const void* r
                          int is_f32, float p, vit3d_stream_t stream);
 int vit3d_cast_f32_to_bf16(const float* x, void* y, long long n, vit3d_stream_t stream);
 int vit3d_cast_bf16_to_f32(const void* x, float* y, long long n, vit3d_stream_t stream);
+/* N2 input pipeline (create_dataset.py:31-69 reads 8-bit slices; tools.py:18-26 subtracts the training
+ * mean): y = float(x_u8) - mean on the device, so volumes cross PCIe as uint8 (81,920 B instead of
+ * 327,680 B per volume). */
+int vit3d_u8_to_f32(const unsigned char* x, float* y, long long n, float mean, vit3d_stream_t stream);
 /* y[cols,rows] (bf16) = x[rows,cols]^T (fp32) */
 int vit3d_transpose_f32_to_bf16(const float* x, void* y, int rows, int cols, vit3d_stream_t stream);
 /* y = x rounded to nearest TF32 (fp32 container): shadow weights for the TF32 mode */

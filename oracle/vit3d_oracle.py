@@ -157,6 +157,15 @@ def synth_volumes(B: int, seed: int = 42, kind: str = "img", img_size: int = 128
     return (u8 - u8.mean()).float()
 
 
+def synth_volumes_u8(B: int, seed: int = 42, img_size: int = 128):
+    """The same 'img' volumes as synth_volumes, before the mean subtraction: (uint8 tensor, mean).
+    synth_volumes(B, seed) == u8.float() - mean exactly."""
+    g = torch.Generator().manual_seed(seed)
+    r = torch.randn(B, 1, img_size, img_size, Z_SIZE, generator=g)
+    u8 = torch.clamp(torch.round(66.0 + 45.0 * r), 0, 255)
+    return u8.to(torch.uint8), float(u8.mean())
+
+
 def synth_labels(B: int, seed: int = 42) -> torch.Tensor:
     g = torch.Generator().manual_seed(seed + 1)
     y = torch.randint(0, 2, (B,), generator=g).float()

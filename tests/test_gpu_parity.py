@@ -261,6 +261,30 @@ def test_real_volumes_predicted_classes():
         assert ((logits > 0) == (ref > 0)).all()
 
 
+def test_uint8_volume_input_equals_fp32_input():
+    """N2: shipping raw uint8 volumes + the mean gives bit-identical logits to shipping (u8 - mean) fp32."""
+    u8, mean = O.synth_volumes_u8(5, seed=42)
+    x = O.synth_volumes(5, seed=42)
+    assert torch.equal(u8.float() - mean, x)
+    g = load_golden("real_volumes")
+    for prec in ("fp32", "bf16"):
+        cfg = vit3d_b200.north_star_config(5)
+        m = VisionTransformer(cfg, 128, zero_head=True, num_classes=1, precision=prec, vis=False)
+        m.load_state_dict(O.init_state_dict(cfg, seed=42))
+        m.to(DEV).eval()
+        m.input_mean = mean
+        with torch.no_grad():
+            a = m(u8.to(DEV))[0]
+            b = m(x.to(DEV))[0]
+        assert torch.equal(a, b)
+        # the real fixture: 4 volumes read through the reference's ProstateDataset, stored as uint8
+        ru8 = torch.from_numpy(g["u8"]).permute(0, 4, 1, 2, 3).contiguous()
+        m.input_mean = float(ru8.float().mean())
+        with torch.no_grad():
+            lr = m(ru8.to(DEV))[0].cpu()
+        assert float((lr - torch.from_numpy(g["logits_conf5"])).abs().max()) <= LOGIT_TOL[prec]
+
+
 def test_batch_sizes_and_linearity_property():
     """Size-independent property at a larger batch: volumes are independent, so a batch's logits equal
     the per-volume logits (checks the flat token-matrix tiling at ragged row counts)."""
