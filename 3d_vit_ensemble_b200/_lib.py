@@ -52,6 +52,8 @@ SIGNATURES = {
     "vit3d_ln_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "vit3d_linear_fwd": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _p]),
     "vit3d_linear_bwd": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _p]),
+    "vit3d_mlp_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "vit3d_mlp_supported": (_i, [_i, _i, _i]),
     "vit3d_attn_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "vit3d_attn_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "vit3d_gelu_fwd": (_i, [_p, _p, _ll, _i, _p]),
@@ -62,6 +64,7 @@ SIGNATURES = {
     "vit3d_cast_f32_to_bf16": (_i, [_p, _p, _ll, _p]),
     "vit3d_cast_bf16_to_f32": (_i, [_p, _p, _ll, _p]),
     "vit3d_round_tf32": (_i, [_p, _p, _ll, _p]),
+    "vit3d_cast_f32_to_f16": (_i, [_p, _p, _ll, _p]),
     "vit3d_u8_to_f32": (_i, [_p, _p, _ll, _f, _p]),
     "vit3d_transpose_f32_to_bf16": (_i, [_p, _p, _i, _i, _p]),
     "vit3d_add_inplace": (_i, [_p, _p, _ll, _p]),

@@ -226,6 +226,16 @@ int vit3d_linear_bwd(const void* dy, int dy_f32, const void* x, int ldx, int x_f
   return VIT3D_OK;
 }
 
+// ------------------------------------------------------------------------- fused MLP
+int vit3d_mlp_supported(int M, int H, int d) { return tc_mlp_supported(M, H, d) ? 1 : 0; }
+int vit3d_mlp_fwd(const void* xn, const void* w1_lp, const float* b1, const void* w2_lp, const float* b2,
+                  const float* residual, float* out, int M, int H, int d, vit3d_stream_t stream) {
+  V3_REQUIRE(xn && w1_lp && b1 && w2_lp && b2 && residual && out, "mlp_fwd: null pointer");
+  V3_REQUIRE(M >= 0 && H > 0 && d > 0, "mlp_fwd: bad shape");
+  if (M == 0) return VIT3D_OK;
+  return tc_mlp_fwd(xn, w1_lp, b1, w2_lp, b2, residual, out, M, H, d, as_stream(stream));
+}
+
 // ------------------------------------------------------------------------- attention core
 int vit3d_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int heads, int D, int prec,
                    vit3d_stream_t stream) {
@@ -283,6 +293,10 @@ int vit3d_u8_to_f32(const unsigned char* x, float* y, long long n, float mean, v
 int vit3d_round_tf32(const float* x, float* y, long long n, vit3d_stream_t stream) {
   V3_REQUIRE(x && y && n >= 0, "round_tf32: bad argument");
   return launch_round_tf32(x, y, n, as_stream(stream));
+}
+int vit3d_cast_f32_to_f16(const float* x, void* y, long long n, vit3d_stream_t stream) {
+  V3_REQUIRE(x && y && n >= 0, "cast: bad argument");
+  return launch_cast_f16(x, y, n, as_stream(stream));
 }
 int vit3d_cast_bf16_to_f32(const void* x, float* y, long long n, vit3d_stream_t stream) {
   V3_REQUIRE(x && y && n >= 0, "cast: bad argument");

@@ -1,6 +1,8 @@
 // Shape-generic fp32 kernels: the exact path (VIT3D_PREC_FP32) and the fallback for shapes
 // the tcgen05 kernels do not serve (e.g. the as-shipped hidden-16 / head-dim-1 models).
 // All arithmetic is fp32 FMA; operands may be stored fp32 or bf16 (runtime flag).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -736,6 +738,13 @@ int launch_u8_to_f32(const uint8_t* x, float* y, long long n, float mean, cudaSt
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) { set_error("u8_to_f32: buffers must be 16-byte aligned"); return VIT3D_ERR_INVALID; }
   const long long n16 = (n + 15) / 16;
   u8_to_f32_kernel<<<ew_blocks(n16), 256, 0, st>>>(x, y, n16, n, mean);
+  V3_LAUNCH_CHECK();
+  return VIT3D_OK;
+}
+int launch_cast_f16(const float* x, void* y, long long n, cudaStream_t st) {
+  if (n <= 0) return VIT3D_OK;
+  __half* o = reinterpret_cast<__half*>(y);
+  ew_kernel<<<ew_blocks(n), 256, 0, st>>>(n, [=] __device__(long long i) { o[i] = __float2half_rn(x[i]); });
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }

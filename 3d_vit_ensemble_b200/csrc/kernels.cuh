@@ -32,6 +32,7 @@ int launch_colsum(const void* dy, int f32, float* db, int M, int N, cudaStream_t
 int launch_attn_fwd_generic(const void* qkv, int f32, void* ctx, float* probs, int B, int S, int heads, int D,
                             int round_out, cudaStream_t st);
 int launch_round_tf32(const float* x, float* y, long long n, cudaStream_t st);
+int launch_cast_f16(const float* x, void* y, long long n, cudaStream_t st);
 int launch_u8_to_f32(const uint8_t* x, float* y, long long n, float mean, cudaStream_t st);
 int launch_transpose_cast(const float* x, void* y, int rows, int cols, cudaStream_t st);
 int launch_attn_bwd_generic(const void* dctx, const void* qkv, int f32, void* dqkv, int B, int S, int heads, int D,

@@ -1,0 +1,229 @@
+// Shared epilogue machinery of the tcgen05 kernels (GEMM, fused MLP): TMEM -> registers -> swizzled
+// shared-memory transpose -> coalesced global / bulk tensor stores, with bias / GELU / residual / position
+// rows fused.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "ptx.cuh"
+#include "tc.cuh"
+
+namespace vit3d {
+
+using namespace ptx;
+
+struct TcEpilogue {
+  const float* bias = nullptr;      // [N]
+  const float* residual = nullptr;  // [M,N] fp32
+  const float* rowadd = nullptr;    // [(row_group+1), N] position table
+  void* out = nullptr;              // [rows, N] fp32 or bf16
+  void* pre = nullptr;              // pre-activation copy (type of out)
+  int out_f32 = 1;
+  int act = 0;
+  int row_group = 0;                // >0: out row = m + m / row_group + 1
+  int atomic = 0;                   // accumulate with fp32 atomics (split-K)
+  int vols_per_tile = 0;            // patch-embedding mode: volumes per 128-row tile
+  int round_tf32 = 0;               // fp32 output is the operand of a TF32 GEMM: round to nearest tf32
+};
+
+
+// 2-D row-major tensor map (defined in k_tc_gemm.cu, cached per thread)
+int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld_elems,
+                 int box_rows, int box_cols, int swizzle_bytes);
+
+// ----------------------------------------------------------------------------- epilogue
+// fast GELU for bf16 outputs: x * sigmoid(2u), u = x (c0 + c1 x^2 + c2 x^4) fitted to the exact erf
+// GELU (max abs error 3e-5, far below the bf16 rounding of the result): 7 FMA-pipe ops + 2 MUFU.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float x2 = fminf(x * x, 100.f);                // the fitted polynomial is monotone up to |x| = 10
+  // -2*log2(e) * {0.797458471, 0.0370503451, -3.58732362e-4}
+  float p = fmaf(x2, 1.03506367e-3f, -0.106903009f);
+  p = fmaf(x2, p, -2.30099750f);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * p));          // exp(-2u)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return x * r;
+}
+
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// GELU of two values at once in packed half precision, result packed bf16x2.  Same fitted form as
+// gelu_fast written with tanh: y = hx + hx * tanh(x (c0 + c1 x^2 + c2 x^4)), hx = x/2.  Seven HFMA2-pipe
+// ops and ONE MUFU (tanh.approx.f16x2) per PAIR - the scalar fp32 form costs 7 + 2 MUFU per ELEMENT and
+// made the fc1 epilogue MUFU/issue bound.  f16 carries 11 significant bits against the 8 of the bf16
+// result: measured mean |error| after the bf16 rounding is 1.38e-3 vs 1.30e-3 for a correctly rounded GELU
+// (|x| <= 4).  Pre-activations beyond +-65504 would overflow to inf (never the case for LayerNorm'd inputs).
+// same, result left as packed f16x2: the fused MLP feeds it to tcgen05 as an fp16 A operand (11 significant
+// bits instead of bf16's 8, and no f16 -> f32 -> bf16 repacking in the epilogue)
+__device__ __forceinline__ uint32_t gelu_pair_f16(float a, float b) {
+  const __half2 x = __floats2half2_rn(a, b);
+  const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(100.f));
+  __half2 p = __hfma2(x2, __float2half2_rn(-3.58732362e-4f), __float2half2_rn(0.0370503451f));
+  p = __hfma2(x2, p, __float2half2_rn(0.797458471f));
+  const __half2 u = __hmul2(x, p);
+  uint32_t ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
+  const __half2 th = *reinterpret_cast<const __half2*>(&ti);
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  const __half2 y = __hfma2(hx, th, hx);
+  return *reinterpret_cast<const uint32_t*>(&y);
+}
+__device__ __forceinline__ uint32_t gelu_pair_bf16(float a, float b) {
+  const __half2 x = __floats2half2_rn(a, b);
+  const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(100.f));
+  __half2 p = __hfma2(x2, __float2half2_rn(-3.58732362e-4f), __float2half2_rn(0.0370503451f));
+  p = __hfma2(x2, p, __float2half2_rn(0.797458471f));
+  const __half2 u = __hmul2(x, p);
+  uint32_t ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
+  const __half2 th = *reinterpret_cast<const __half2*>(&ti);
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  const float2 f = __half22float2(__hfma2(hx, th, hx));
+  return pack2_bf16(f.x, f.y);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// Each epilogue warp owns 32 accumulator rows (one TMEM lane quarter) x CW columns.  TMEM hands every
+// thread one ROW (tcgen05.ld 32x32b); rows are transposed through a 2 KB swizzled shared-memory tile
+// (32 rows x 64 bytes) so that global loads/stores are whole 32-byte sectors, 64 contiguous bytes per row.
+//   fp32 output : 16 columns per round; raw accumulators are staged, bias / position rows / GELU /
+//                 residual are applied in the coalesced phase (element-wise, layout does not matter).
+//   bf16 output : 32 columns per round; bias (+GELU) are applied in the row-owner phase, packed to bf16
+//                 and staged; the coalesced phase is a pure copy.
+// staging position of 16-byte chunk j of row r: r*64 + ((j ^ ((r >> 1) & 3)) << 4)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int CW, bool FAST_GELU>
+__device__ __forceinline__ void epilogue_rows(const TcEpilogue& ep, const CUtensorMap* tmC, const CUtensorMap* tmPre,
+                                              uint32_t taddr, uint32_t stage, int lane, int m_base, int n_base, int M,
+                                              int N) {
+  const uint32_t my_row = stage + lane * 64;
+  const int sw = (lane >> 1) & 3;
+  const int chunk = lane & 3, rsub = lane >> 2;       // coalesced phase: 4 lanes per row, 8 rows per instruction
+  if (ep.out_f32) {
+#pragma unroll 1
+    for (int c = 0; c < CW; c += 16) {
+      if (n_base + c >= N) break;
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(taddr + c, r);
+      const int col = n_base + c + chunk * 4;
+      const bool colok = col < N;
+      // issue every global read of this round before the TMEM wait / the stores (out may alias residual)
+      float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 res[4], radd[4];
+      if (colok) {
+        if (ep.bias) bias = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int m = m_base + i * 8 + rsub;
+          res[i] = radd[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m < M) {
+            if (ep.residual) res[i] = __ldg(reinterpret_cast<const float4*>(ep.residual + (long long)m * N + col));
+            if (ep.rowadd)
+              radd[i] = __ldg(reinterpret_cast<const float4*>(ep.rowadd + (long long)((m % ep.row_group) + 1) * N + col));
+          }
+        }
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st_shared_v4(my_row + ((j ^ sw) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      __syncwarp();
+      if (colok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = i * 8 + rsub;
+          const int m = m_base + row;
+          if (m < M) {
+            const uint4 u = ld_shared_v4(stage + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+            float4 v = make_float4(__uint_as_float(u.x) + bias.x + radd[i].x, __uint_as_float(u.y) + bias.y + radd[i].y,
+                                   __uint_as_float(u.z) + bias.z + radd[i].z, __uint_as_float(u.w) + bias.w + radd[i].w);
+            const long long orow = ep.row_group > 0 ? (long long)m + m / ep.row_group + 1 : (long long)m;
+            float* o = reinterpret_cast<float*>(ep.out) + orow * N + col;
+            if (ep.atomic) {
+              atomicAdd(o, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w);
+            } else {
+              if (ep.pre) *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.pre) + orow * N + col) = v;
+              if (ep.act == VIT3D_ACT_GELU) { v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w); }
+              v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w;
+              if (ep.round_tf32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+              *reinterpret_cast<float4*>(o) = v;
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // bf16 output: 32 columns (64 B per row) per round, staged in the TMA SWIZZLE_64B layout and written
+    // with one bulk tensor store per round (rows >= M / columns >= N are clipped by the TMA unit).
+#pragma unroll 1
+    for (int c = 0; c < CW; c += 32) {
+      if (n_base + c >= N) break;
+      float v[32];
+      {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      }
+      if (ep.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (n_base + c + j < N) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n_base + c + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+      }
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        // pass 0: pre-activation copy (training), pass 1: output
+        if (pass == 0 && ep.pre == nullptr) continue;
+        const bool gelu = pass == 1 && ep.act == VIT3D_ACT_GELU;
+        if (gelu && !FAST_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
+        }
+        if (lane == 0) bulk_store_wait_read();      // the previous round's store has finished reading the tile
+        __syncwarp();
+        if (gelu && FAST_GELU) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            st_shared_v4(my_row + ((j ^ sw) << 4), gelu_pair_bf16(v[8 * j], v[8 * j + 1]), gelu_pair_bf16(v[8 * j + 2], v[8 * j + 3]),
+                         gelu_pair_bf16(v[8 * j + 4], v[8 * j + 5]), gelu_pair_bf16(v[8 * j + 6], v[8 * j + 7]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            st_shared_v4(my_row + ((j ^ sw) << 4), pack2_bf16(v[8 * j], v[8 * j + 1]), pack2_bf16(v[8 * j + 2], v[8 * j + 3]),
+                         pack2_bf16(v[8 * j + 4], v[8 * j + 5]), pack2_bf16(v[8 * j + 6], v[8 * j + 7]));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(pass == 0 ? tmPre : tmC, stage, n_base + c, m_base);
+          bulk_store_commit();
+        }
+      }
+    }
+  }
+}
+
+}  // namespace vit3d

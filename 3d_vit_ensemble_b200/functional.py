@@ -71,6 +71,9 @@ def lp_weight(w: torch.Tensor, prec: str = "bf16") -> torch.Tensor:
     if prec == "bf16":
         out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
         call("vit3d_cast_f32_to_bf16", ptr(w.detach()), ptr(out), w.numel(), stream())
+    elif prec == "f16":             # fp16 shadow (fc2 weight of the fused MLP)
+        out = torch.empty(w.shape, dtype=torch.float16, device=w.device)
+        call("vit3d_cast_f32_to_f16", ptr(w.detach()), ptr(out), w.numel(), stream())
     elif prec == "bf16_t":          # transposed bf16 shadow [K,N] of a [N,K] weight: dgrad operand
         out = torch.empty(w.shape[1], w.shape[0], dtype=torch.bfloat16, device=w.device)
         call("vit3d_transpose_f32_to_bf16", ptr(w.detach()), ptr(out), w.shape[0], w.shape[1], stream())
@@ -261,6 +264,27 @@ class LinearFn(torch.autograd.Function):
         if dx is not None:
             dx = dx.reshape(xshape).to(xdtype)
         return dx, dw, db, d_res, None, None, None
+
+
+def mlp_fused_supported(M: int, H: int, d: int) -> bool:
+    return bool(_lib.lib().vit3d_mlp_supported(M, H, d))
+
+
+def mlp_fused(xn, w1, b1, w2, b2, residual):
+    """Inference-only fused fc1 -> GELU -> fc2 (+ residual): the [M, d] intermediate never reaches HBM.
+    xn: bf16 LayerNorm output (..., H); residual fp32 (..., H); returns fp32 (..., H).  No autograd."""
+    _need_cuda(xn, w1, b1, w2, b2, residual)
+    H = xn.shape[-1]
+    d = w1.shape[0]
+    x2 = _c(xn).reshape(-1, H)
+    if x2.dtype != torch.bfloat16:
+        x2 = x2.to(torch.bfloat16)
+    M = x2.shape[0]
+    res = _c(residual.float()).reshape(M, H)
+    out = torch.empty(M, H, device=xn.device, dtype=torch.float32)
+    call("vit3d_mlp_fwd", ptr(x2), ptr(lp_weight(w1, "bf16")), ptr(_c(b1)), ptr(lp_weight(w2, "f16")), ptr(_c(b2)),
+         ptr(res), ptr(out), M, H, d, stream())
+    return out.reshape(residual.shape)
 
 
 def linear(x, w, b=None, residual=None, act=ACT_NONE, prec=None, out_f32=False):

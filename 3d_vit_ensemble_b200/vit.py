@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import copy
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -80,6 +81,9 @@ class Mlp(nn.Module):
         self._init_weights()
         self.precision = F.get_precision()
         self._site = 1
+        # single-kernel fc1->GELU->fc2 inference path (bf16 mode, hidden 256).  Correct and tested, but measured
+        # slower than the two-GEMM path on B200 (the GELU epilogue, not HBM, bounds both), so opt-in.
+        self.fused = os.environ.get("VIT3D_FUSED_MLP", "0") == "1"
 
     def _init_weights(self):
         nn.init.xavier_uniform_(self.fc1.weight)
@@ -93,6 +97,11 @@ class Mlp(nn.Module):
         train = self.training and p > 0.0
         if train and step is None:
             step = F.next_dropout_step()
+        if (not train and prec == "bf16" and residual is not None and not torch.is_grad_enabled()
+                and self.fused and x.is_cuda and self.fc1.weight.is_contiguous() and self.fc2.weight.is_contiguous()
+                and F.mlp_fused_supported(x.numel() // x.shape[-1], x.shape[-1], self.fc1.weight.shape[0])):
+            # inference: one kernel, the (M, mlp_dim) intermediate stays in TMEM / shared memory
+            return F.mlp_fused(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, residual)
         h = F.linear(x, self.fc1.weight, self.fc1.bias, act=ACT_GELU, prec=prec)
         h = F.dropout(h, p, train, self._site, step)
         if train:

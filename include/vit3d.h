@@ -105,6 +105,17 @@ int vit3d_linear_bwd(const void* dy, int dy_f32, const void* x, int ldx, int x_f
                      void* dx, int lddx, int dx_f32, float* dw, float* db, int M, int N, int K, int prec,
                      vit3d_stream_t stream);
 
+/* ---------------------------------------------------------------- a3: Mlp.forward fused (inference)
+ * out[M,H] = residual + fc2(gelu(fc1(xn) + b1)) + b2  (modeling.py:118-124 with the x + Mlp(..) add of :196;
+ * dropout is the identity in eval mode).  BF16 mode, H = 256, d % 128 == 0: xn bf16 [M,H] (LayerNorm
+ * output), w1_lp bf16 [d,H], w2_h FP16 [H,d] (vit3d_cast_f32_to_f16: the GELU output is kept in fp16 -
+ * 11 significant bits - and tcgen05 kind::f16 needs both operands of fc2 in the same 16-bit format); the
+ * [M,d] intermediate stays on chip.  Returns VIT3D_ERR_UNSUPPORTED for other shapes (compose
+ * vit3d_linear_fwd instead). */
+int vit3d_mlp_fwd(const void* xn, const void* w1_lp, const float* b1, const void* w2_h, const float* b2,
+                  const float* residual, float* out, int M, int H, int d, vit3d_stream_t stream);
+int vit3d_mlp_supported(int M, int H, int d);
+
 /* ---------------------------------------------------------------- a2: scaled-dot-product attention core
  * scores = q k^T / sqrt(D); probs = softmax(scores); ctx = probs v  (modeling.py:83-96).
  * qkv is the packed [M, 3*k*D] matrix (q | k | v column blocks, head h at columns h*D..),
@@ -135,6 +146,7 @@ int vit3d_dropout_masked(const void* x, const unsigned char* mask, const void* r
                          int is_f32, float p, vit3d_stream_t stream);
 int vit3d_cast_f32_to_bf16(const float* x, void* y, long long n, vit3d_stream_t stream);
 int vit3d_cast_bf16_to_f32(const void* x, float* y, long long n, vit3d_stream_t stream);
+int vit3d_cast_f32_to_f16(const float* x, void* y, long long n, vit3d_stream_t stream);
 /* N2 input pipeline (create_dataset.py:31-69 reads 8-bit slices; tools.py:18-26 subtracts the training
  * mean): y = float(x_u8) - mean on the device, so volumes cross PCIe as uint8 (81,920 B instead of
  * 327,680 B per volume). */

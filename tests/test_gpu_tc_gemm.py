@@ -112,3 +112,31 @@ def test_tc_linear_backward_bf16(shape):
         e = float((dw.double() - ref_dw).abs().max())
         assert np.isfinite(e) and e <= 2e-5 * M ** 0.5 * 4, (e, float(ref_dw.abs().max()))
         assert float((db.double() - ref_db).abs().max()) <= 1e-3 * M ** 0.5
+
+
+@pytest.mark.parametrize("M", [65, 130, 260, 4160, 19000])
+@pytest.mark.parametrize("d", [2048, 3072, 128])
+def test_fused_mlp_matches_fp64(M, d):
+    """Single-kernel fc1 -> GELU -> fc2 (+bias, +residual) vs an fp64 evaluation on the same bf16 operands
+    (the bf16 rounding of the GELU output is reproduced in the reference)."""
+    torch.manual_seed(M + d)
+    H = 256
+    xn = torch.randn(M, H, device=DEV).to(torch.bfloat16)
+    w1 = (torch.randn(d, H, device=DEV) / H ** 0.5)
+    w2 = (torch.randn(H, d, device=DEV) / d ** 0.5)
+    b1 = torch.randn(d, device=DEV) * 0.1
+    b2 = torch.randn(H, device=DEV) * 0.1
+    res = torch.randn(M, H, device=DEV)
+    w1l, w2l = w1.to(torch.bfloat16), w2.to(torch.float16)
+    out = torch.full((M, H), float("nan"), device=DEV)
+    assert lib().vit3d_mlp_supported(M, H, d) == 1
+    call("vit3d_mlp_fwd", ptr(xn), ptr(w1l), ptr(b1), ptr(w2l), ptr(b2), ptr(res), ptr(out), M, H, d, stream())
+    torch.cuda.synchronize()
+    h = xn.double() @ w1l.double().t() + b1.double()
+    a = gelu(h).to(torch.float16).double()             # the kernel keeps GELU(h) in 16 bits before fc2
+    ref = a @ w2l.double().t() + b2.double() + res.double()
+    err = float((out.double() - ref).abs().max())
+    # a bf16 ulp flip of one GELU output (value ~ up to 4) moves one product by <= 2^-7 * |w2| ~ 1e-3; many flip
+    assert np.isfinite(err) and err <= 0.02, err
+    rel = float((out.double() - ref).norm() / ref.norm())
+    assert rel < 2e-3, rel
