@@ -65,7 +65,7 @@ int vit3d_patch_gather(const float* x, float* patches, int B, int X, int Y, int 
   V3_REQUIRE(B >= 0 && p0 > 0 && p1 > 0 && p2 > 0 && X >= p0 && Y >= p1 && Z >= p2, "patch_gather: bad shape");
   if (B == 0) return VIT3D_OK;
   V3_REQUIRE(x && patches, "patch_gather: null pointer");
-  return launch_patch_gather(x, patches, B, X, Y, Z, p0, p1, p2, as_stream(stream));
+  return launch_patch_gather(x, patches, 1, B, X, Y, Z, p0, p1, p2, as_stream(stream));
 }
 
 size_t vit3d_patch_embed_ws_bytes(int B, int X, int Y, int Z, int p0, int p1, int p2, int H, int prec) {
@@ -94,7 +94,7 @@ int vit3d_patch_embed_fwd(const float* x, const float* w, const float* bias, con
   }
   V3_REQUIRE(ws && ws_bytes >= vit3d_patch_embed_ws_bytes(B, X, Y, Z, p0, p1, p2, H, prec), "patch_embed_fwd: workspace too small");
   float* patches = reinterpret_cast<float*>(ws);
-  int rc = launch_patch_gather(x, patches, B, X, Y, Z, p0, p1, p2, st);
+  int rc = launch_patch_gather(x, patches, 1, B, X, Y, Z, p0, p1, p2, st);
   if (rc != VIT3D_OK) return rc;
   SgemmArgs g;
   g.A = patches; g.sa_m = Kp; g.sa_k = 1;
@@ -115,11 +115,27 @@ int vit3d_patch_embed_bwd(const float* x, const float* dtokens, float* dw, float
   cudaStream_t st = as_stream(stream);
   const int P = (X / p0) * (Y / p1) * (Z / p2), Kp = p0 * p1 * p2, S = P + 1;
   if (B == 0) return VIT3D_OK;
+  int rc;
+  if (prec == VIT3D_PREC_BF16 && tc_wgrad_supported(prec, B * P, H, Kp)) {
+    // BF16 mode: bf16 im2col + bf16 dY, weight gradient on tcgen05 (both operands MN-major, split over the
+    // B*P token rows, fp32 atomics into dw)
+    __nv_bfloat16* patches = reinterpret_cast<__nv_bfloat16*>(ws);
+    __nv_bfloat16* dYb = patches + (size_t)B * P * Kp;
+    rc = launch_patch_gather(x, patches, 0, B, X, Y, Z, p0, p1, p2, st);
+    if (rc != VIT3D_OK) return rc;
+    rc = launch_gather_patch_rows(dtokens, dYb, 0, B, P, H, st);
+    if (rc != VIT3D_OK) return rc;
+    rc = tc_gemm_wgrad(dYb, patches, dw, H, Kp, B * P, st);
+    if (rc != VIT3D_OK) return rc;
+    rc = launch_colsum(dYb, 0, dbias, B * P, H, st);
+    if (rc != VIT3D_OK) return rc;
+    return launch_embed_param_grads(dtokens, dpos, dcls, B, S, H, st);
+  }
   float* patches = reinterpret_cast<float*>(ws);
   float* dY = patches + (size_t)B * P * Kp;
-  int rc = launch_patch_gather(x, patches, B, X, Y, Z, p0, p1, p2, st);
+  rc = launch_patch_gather(x, patches, 1, B, X, Y, Z, p0, p1, p2, st);
   if (rc != VIT3D_OK) return rc;
-  rc = launch_gather_patch_rows(dtokens, dY, B, P, H, st);
+  rc = launch_gather_patch_rows(dtokens, dY, 1, B, P, H, st);
   if (rc != VIT3D_OK) return rc;
   // dw[H,Kp] += dY^T[H, BP] @ patches[BP, Kp]
   SgemmArgs g;

@@ -129,8 +129,8 @@ int pick_splitk(int M, int N, int K) {
 
 // ============================================================================ patch gather (a1)
 // Pure permutation (bit-exact): patches[(b*P+p)*Kp + (i*p1+j)*p2+z] = x[b,0,px*p0+i,py*p1+j,pz*p2+z]
-__global__ void patch_gather_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int X, int Y, int Z,
-                                    int p0, int p1, int p2, int nx, int ny, int nz) {
+__global__ void patch_gather_kernel(const float* __restrict__ x, void* __restrict__ out, int out_f32, int B, int X, int Y,
+                                    int Z, int p0, int p1, int p2, int nx, int ny, int nz) {
   const long long Kp = (long long)p0 * p1 * p2;
   const long long P = (long long)nx * ny * nz;
   const long long total = (long long)B * P * Kp;
@@ -141,17 +141,18 @@ __global__ void patch_gather_kernel(const float* __restrict__ x, float* __restri
     const int z = (int)(kk % p2), j = (int)((kk / p2) % p1), i = (int)(kk / ((long long)p2 * p1));
     const int pz = p % nz, py = (p / nz) % ny, px = p / (nz * ny);
     const long long src = (((long long)b * X + (px * p0 + i)) * Y + (py * p1 + j)) * Z + (pz * p2 + z);
-    out[t] = x[src];
+    st_any(out, t, out_f32, x[src]);
   }
 }
-int launch_patch_gather(const float* x, float* out, int B, int X, int Y, int Z, int p0, int p1, int p2, cudaStream_t st) {
+int launch_patch_gather(const float* x, void* out, int out_f32, int B, int X, int Y, int Z, int p0, int p1, int p2,
+                        cudaStream_t st) {
   const int nx = X / p0, ny = Y / p1, nz = Z / p2;
   const long long total = (long long)B * nx * ny * nz * p0 * p1 * p2;
   if (total == 0) return VIT3D_OK;
   int blocks = (int)((total + 255) / 256);
   const int cap = sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  patch_gather_kernel<<<blocks, 256, 0, st>>>(x, out, B, X, Y, Z, p0, p1, p2, nx, ny, nz);
+  patch_gather_kernel<<<blocks, 256, 0, st>>>(x, out, out_f32, B, X, Y, Z, p0, p1, p2, nx, ny, nz);
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
@@ -198,21 +199,21 @@ int launch_embed_param_grads(const float* dtok, float* dpos, float* dcls, int B,
 }
 
 // out[(b*P+p), :] = dtok[(b*(P+1)+1+p), :]   (drop the cls rows)
-__global__ void gather_patch_rows_kernel(const float* __restrict__ dtok, float* __restrict__ out, long long total, int P,
-                                         int H) {
+__global__ void gather_patch_rows_kernel(const float* __restrict__ dtok, void* __restrict__ out, int out_f32, long long total,
+                                         int P, int H) {
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const long long m = t / H;
     const int h = (int)(t % H);
-    out[t] = dtok[(m + m / P + 1) * H + h];
+    st_any(out, t, out_f32, dtok[(m + m / P + 1) * H + h]);
   }
 }
-int launch_gather_patch_rows(const float* dtok, float* out, int B, int P, int H, cudaStream_t st) {
+int launch_gather_patch_rows(const float* dtok, void* out, int out_f32, int B, int P, int H, cudaStream_t st) {
   const long long total = (long long)B * P * H;
   if (total == 0) return VIT3D_OK;
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  gather_patch_rows_kernel<<<(int)blocks, 256, 0, st>>>(dtok, out, total, P, H);
+  gather_patch_rows_kernel<<<(int)blocks, 256, 0, st>>>(dtok, out, out_f32, total, P, H);
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
@@ -598,8 +599,43 @@ int launch_gelu_fwd(const void* h, void* a, long long n, int f32, cudaStream_t s
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
+// bf16 fast path: 8 elements per thread (16-byte accesses); derivative of the same fitted tanh-form GELU the
+// BF16 forward evaluates, y = 0.5 x (1 + tanh(u)), u = x (c0 + c1 x^2 + c2 x^4):
+//   y' = 0.5 (1 + t) + 0.5 x (1 - t^2) (c0 + 3 c1 x^2 + 5 c2 x^4)
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  const float x2 = fminf(x * x, 100.f);
+  const float u = x * fmaf(x2, fmaf(x2, -3.58732362e-4f, 0.0370503451f), 0.797458471f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float du = fmaf(x2, fmaf(x2, 5.f * -3.58732362e-4f, 3.f * 0.0370503451f), 0.797458471f);
+  return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * du;
+}
+__global__ void __launch_bounds__(256) gelu_bwd_bf16_kernel(const uint4* __restrict__ da, const uint4* __restrict__ h,
+                                                            uint4* __restrict__ dh, long long n8) {
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n8; q += (long long)gridDim.x * blockDim.x) {
+    const uint4 a = da[q], b = h[q];
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 av = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
+      const __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(&bw[j]);
+      const __nv_bfloat162 o = __floats2bfloat162_rn(__low2float(av) * gelu_grad_fast(__low2float(hv)),
+                                                      __high2float(av) * gelu_grad_fast(__high2float(hv)));
+      ow[j] = *reinterpret_cast<const uint32_t*>(&o);
+    }
+    dh[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
 int launch_gelu_bwd(const void* da, const void* h, void* dh, long long n, int f32, cudaStream_t st) {
   if (n <= 0) return VIT3D_OK;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(dh)) & 15) == 0;
+  if (!f32 && aligned && n % 8 == 0) {
+    gelu_bwd_bf16_kernel<<<ew_blocks(n / 8), 256, 0, st>>>(reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(h),
+                                                           reinterpret_cast<uint4*>(dh), n / 8);
+    V3_LAUNCH_CHECK();
+    return VIT3D_OK;
+  }
   ew_kernel<<<ew_blocks(n), 256, 0, st>>>(
       n, [=] __device__(long long i) { st_any(dh, i, f32, ld_any(da, i, f32) * gelu_grad_f(ld_any(h, i, f32))); });
   V3_LAUNCH_CHECK();

@@ -20,10 +20,11 @@ struct SgemmArgs {
 
 int launch_sgemm(const SgemmArgs& a, cudaStream_t st);
 int pick_splitk(int M, int N, int K);
-int launch_patch_gather(const float* x, float* out, int B, int X, int Y, int Z, int p0, int p1, int p2, cudaStream_t st);
+int launch_patch_gather(const float* x, void* out, int out_f32, int B, int X, int Y, int Z, int p0, int p1, int p2,
+                        cudaStream_t st);
 int launch_cls_rows(const float* cls, const float* pos, float* tokens, int B, int S, int H, cudaStream_t st);
 int launch_embed_param_grads(const float* dtok, float* dpos, float* dcls, int B, int S, int H, cudaStream_t st);
-int launch_gather_patch_rows(const float* dtok, float* out, int B, int P, int H, cudaStream_t st);
+int launch_gather_patch_rows(const float* dtok, void* out, int out_f32, int B, int P, int H, cudaStream_t st);
 int launch_ln_fwd(const float* x, const float* g, const float* b, void* y, int y_bf16, float* mean, float* rstd, int M,
                   int H, float eps, cudaStream_t st);
 int launch_ln_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,

@@ -114,6 +114,10 @@ class GradReducer:
             p.grad = self.views[n]
         self._pending = {b: len(ps) for b, ps in self._bucket_params.items()}
         self._handles = []
+        # parameters whose gradient the kernels accumulate in place never reach autograd's hooks:
+        # functional._grad_done reports them here instead
+        from . import functional as F
+        F._STATE["grad_hook"] = self._on_grad
 
     def _on_grad(self, p):
         b = self._param_bucket[id(p)]
@@ -158,6 +162,9 @@ class GradReducer:
     def remove(self):
         for h in self._hooks:
             h.remove()
+        from . import functional as F
+        if F._STATE.get("grad_hook") == self._on_grad:
+            F._STATE["grad_hook"] = None
 
 
 # ----------------------------------------------------------------------------- ensemble sharding

@@ -49,6 +49,30 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def enable_direct_grads(on: bool = True) -> None:
+    """When on, backward kernels accumulate a parameter's gradient straight into its existing `.grad`
+    (e.g. a view of optim.FlatArena's flat buffer) and hand autograd `None` for it - no zero-filled
+    temporary and no extra add per parameter.  Turned on by the fused optimizers / GradReducer; leave it
+    off if you call torch.autograd.grad() for parameter gradients."""
+    _STATE["direct_grads"] = bool(on)
+
+
+def _grad_target(p):
+    """The tensor a parameter gradient can be accumulated into in place, or None."""
+    if not _STATE.get("direct_grads") or not isinstance(p, torch.nn.Parameter):
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or g.device != p.device or not g.is_contiguous() or g.shape != p.shape:
+        return None
+    return g
+
+
+def _grad_done(p):
+    hook = _STATE.get("grad_hook")
+    if hook is not None:
+        hook(p)
+
+
 # bf16 shadow copies of fp32 master weights (parameters only), refreshed when the parameter
 # changes (optimizer step / load_state_dict bump _version, .to() changes data_ptr).  Keyed by the
 # parameter object itself so that a freed-and-reallocated address can never alias a stale copy.
@@ -115,6 +139,7 @@ class PatchEmbedFn(torch.autograd.Function):
              B, X, Y, Z, p0, p1, p2, H, pid, ptr(ws), wsb, stream())
         ctx.save_for_backward(x)
         ctx.meta = (w.shape, cls.shape, pos.shape, prec)
+        ctx.params = (w, bias, cls, pos)
         return tokens
 
     @staticmethod
@@ -124,15 +149,24 @@ class PatchEmbedFn(torch.autograd.Function):
         B, _, X, Y, Z = x.shape
         H, _, p0, p1, p2 = wshape
         dev = x.device
-        dw = torch.zeros(wshape, device=dev)
-        db = torch.zeros(H, device=dev)
-        dcls = torch.zeros(cshape, device=dev)
-        dpos = torch.zeros(pshape, device=dev)
+        targets = [_grad_target(p) for p in ctx.params]
+        direct = all(t is not None for t in targets)
+        if direct:
+            dw, db, dcls, dpos = targets
+        else:
+            dw = torch.zeros(wshape, device=dev)
+            db = torch.zeros(H, device=dev)
+            dcls = torch.zeros(cshape, device=dev)
+            dpos = torch.zeros(pshape, device=dev)
         pid = PREC[prec]
         wsb = _lib.lib().vit3d_patch_embed_ws_bytes(B, X, Y, Z, p0, p1, p2, H, pid)
         ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
         call("vit3d_patch_embed_bwd", ptr(x), ptr(_c(dtok.float())), ptr(dw), ptr(db), ptr(dcls), ptr(dpos),
              B, X, Y, Z, p0, p1, p2, H, pid, ptr(ws), wsb, stream())
+        if direct:
+            for p in ctx.params:
+                _grad_done(p)
+            return None, None, None, None, None, None
         return None, dw, db, dcls, dpos, None
 
 
@@ -177,6 +211,7 @@ class LayerNormFn(torch.autograd.Function):
         call("vit3d_ln_fwd", ptr(x), ptr(_c(gamma)), ptr(_c(beta)), ptr(y), out_mode, ptr(mean),
              ptr(rstd), M, H, float(eps), stream())
         ctx.save_for_backward(x, gamma, mean, rstd)
+        ctx.params = (gamma, beta)
         return y
 
     @staticmethod
@@ -186,10 +221,16 @@ class LayerNormFn(torch.autograd.Function):
         M = x.numel() // H
         dy = _c(dy.float())
         dx = torch.empty_like(x)
-        dg = torch.zeros_like(gamma)
-        db = torch.zeros_like(gamma)
+        tg, tb = _grad_target(ctx.params[0]), _grad_target(ctx.params[1])
+        direct = tg is not None and tb is not None
+        dg = tg if direct else torch.zeros_like(gamma)
+        db = tb if direct else torch.zeros_like(gamma)
         call("vit3d_ln_bwd", ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(_c(gamma)), None, ptr(dx), ptr(dg), ptr(db),
              M, H, stream())
+        if direct:
+            _grad_done(ctx.params[0])
+            _grad_done(ctx.params[1])
+            return dx, None, None, None, None
         return dx, dg, db, None, None
 
 
@@ -226,6 +267,7 @@ class LinearFn(torch.autograd.Function):
              PREC[prec], stream())
         ctx.save_for_backward(x2, w, w_lp, pre)
         ctx.w_obj = w_obj if (prec == "bf16" and w_obj.is_contiguous() and w_obj.dim() == 2) else None
+        ctx.params = (w_obj, b)
         ctx.meta = (ldx, act, prec, b is not None, residual is not None, x.shape, x.dtype)
         return y.reshape(*lead, N)
 
@@ -247,8 +289,10 @@ class LinearFn(torch.autograd.Function):
             dy2 = dh
         need_dx = ctx.needs_input_grad[0]
         dx = torch.empty(M, K, device=dy.device, dtype=x2.dtype) if need_dx else None
-        dw = torch.zeros_like(w) if ctx.needs_input_grad[1] else None
-        db = torch.zeros(N, device=dy.device) if (has_b and ctx.needs_input_grad[2]) else None
+        tw = _grad_target(ctx.params[0]) if ctx.needs_input_grad[1] else None
+        tb = _grad_target(ctx.params[1]) if (has_b and ctx.needs_input_grad[2]) else None
+        dw = tw if tw is not None else (torch.zeros_like(w) if ctx.needs_input_grad[1] else None)
+        db = tb if tb is not None else (torch.zeros(N, device=dy.device) if (has_b and ctx.needs_input_grad[2]) else None)
         w_t = None
         if prec == "bf16":
             # tensor-core backward wants bf16 operands: the residual-stream gradient arrives fp32
@@ -263,6 +307,12 @@ class LinearFn(torch.autograd.Function):
              ptr(db), M, N, K, PREC[prec], stream())
         if dx is not None:
             dx = dx.reshape(xshape).to(xdtype)
+        if tw is not None:
+            _grad_done(ctx.params[0])
+            dw = None
+        if tb is not None:
+            _grad_done(ctx.params[1])
+            db = None
         return dx, dw, db, d_res, None, None, None
 
 

@@ -15,7 +15,7 @@ from typing import Iterable, List
 import torch
 
 from ._lib import call, ptr, stream
-from .functional import invalidate_weight_shadows
+from .functional import enable_direct_grads, invalidate_weight_shadows
 
 
 class FlatArena:
@@ -74,6 +74,7 @@ class _FlatOptimizer(torch.optim.Optimizer):
             raise ValueError("fused flat optimizers take one parameter group")
         super().__init__(params, defaults)
         self.arena = FlatArena(self.param_groups[0]["params"])
+        enable_direct_grads(True)      # backward kernels add straight into the arena views
         self._steps = 0
         # device-resident lr / step for CUDA-graph replays (see graphs.GraphedTrainStep); None = host values
         self.lr_dev = None

@@ -59,9 +59,12 @@ def test_graphed_train_step_equals_eager(opt_name):
         res.append((float(loss), {k: v.detach().clone() for k, v in m.state_dict().items()}))
     (le, se), (lg, sg) = res
     assert abs(le - lg) < 2e-3 * max(1.0, abs(le)), (le, lg)
+    # atomics order differs run to run; Adam turns a gradient that is noise around 0 into a +-lr step, so allow
+    # a fraction of the total possible movement (7 steps x lr) for it
+    slack = 0.35 * 7 * 1e-4 if opt_name == "adam" else 0.0
     for k in se:
         d = float((se[k] - sg[k]).abs().max())
-        assert d <= 2e-3 * float(se[k].abs().max()) + 1e-6, (k, d)     # atomics order differs run to run
+        assert d <= 2e-3 * float(se[k].abs().max()) + 1e-6 + slack, (k, d)
     assert np.isfinite(le)
 
 
