@@ -58,6 +58,7 @@ SIGNATURES = {
     "vit3d_attn_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "vit3d_gelu_fwd": (_i, [_p, _p, _ll, _i, _p]),
     "vit3d_gelu_bwd": (_i, [_p, _p, _p, _ll, _i, _p]),
+    "vit3d_gelu_dropout_bwd": (_i, [_p, _p, _p, _ll, _i, _f, _ull, _u, _u, _p, _p]),
     "vit3d_dropout": (_i, [_p, _p, _p, _ll, _i, _f, _ull, _u, _u, _p, _p]),
     "vit3d_dropout_mask": (_i, [_p, _ll, _f, _ull, _u, _u, _p]),
     "vit3d_dropout_masked": (_i, [_p, _p, _p, _p, _ll, _i, _f, _p]),

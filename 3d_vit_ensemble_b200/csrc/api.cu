@@ -278,6 +278,14 @@ int vit3d_gelu_bwd(const void* da, const void* h, void* dh, long long n, int pre
   V3_REQUIRE(da && h && dh && n >= 0, "gelu_bwd: bad argument");
   return launch_gelu_bwd(da, h, dh, n, act_f32(prec), as_stream(stream));
 }
+int vit3d_gelu_dropout_bwd(const void* da, const void* h, void* dh, long long n, int prec, float p,
+                           unsigned long long seed, unsigned site, unsigned step, const unsigned* step_dev,
+                           vit3d_stream_t stream) {
+  V3_REQUIRE(da && h && dh && n >= 0 && p >= 0.f && p < 1.f, "gelu_dropout_bwd: bad argument");
+  if (!gelu_dropout_bwd_supported(da, h, dh, n, act_f32(prec)))
+    V3_UNSUPPORTED("gelu_dropout_bwd: needs bf16 activations, 16-byte aligned buffers and n %% 8 == 0");
+  return launch_gelu_dropout_bwd(da, h, dh, n, p, seed, site, step, step_dev, as_stream(stream));
+}
 int vit3d_dropout(const void* x, const void* residual, void* y, long long n, int is_f32, float p,
                   unsigned long long seed, unsigned site, unsigned step, const unsigned* step_dev,
                   vit3d_stream_t stream) {

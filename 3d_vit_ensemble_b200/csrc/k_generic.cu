@@ -610,29 +610,63 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
   const float du = fmaf(x2, fmaf(x2, 5.f * -3.58732362e-4f, 3.f * 0.0370503451f), 0.797458471f);
   return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * du;
 }
+// DROP: the Dropout between GELU and fc2 (modeling.py:121) is undone here too - dh = keep * da / (1-p) * gelu'(h)
+// with the mask regenerated from (seed, site, step, element index), so training needs no separate dropout
+// backward pass over the [M, mlp_dim] gradient.
+template <bool DROP>
 __global__ void __launch_bounds__(256) gelu_bwd_bf16_kernel(const uint4* __restrict__ da, const uint4* __restrict__ h,
-                                                            uint4* __restrict__ dh, long long n8) {
+                                                            uint4* __restrict__ dh, long long n8, uint32_t th, float sc,
+                                                            unsigned long long seed, unsigned site, unsigned step,
+                                                            const unsigned* __restrict__ step_dev) {
+  if (DROP && step_dev) step += *step_dev;
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n8; q += (long long)gridDim.x * blockDim.x) {
     const uint4 a = da[q], b = h[q];
     const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    float keep[8];
+    if (DROP) {
+      // elements 8q .. 8q+7 = Philox blocks 2q and 2q+1 (4 elements per block, as in dropout4_kernel)
+      const unsigned long long b0 = 2ull * (unsigned long long)q;
+      const Philox4 r0 = philox4x32_10((uint32_t)b0, (uint32_t)(b0 >> 32), site, step, (uint32_t)seed, (uint32_t)(seed >> 32));
+      const Philox4 r1 = philox4x32_10((uint32_t)(b0 + 1), (uint32_t)((b0 + 1) >> 32), site, step, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        keep[j] = r0.v[j] >= th ? sc : 0.f;
+        keep[4 + j] = r1.v[j] >= th ? sc : 0.f;
+      }
+    }
     uint32_t ow[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const __nv_bfloat162 av = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
       const __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(&bw[j]);
-      const __nv_bfloat162 o = __floats2bfloat162_rn(__low2float(av) * gelu_grad_fast(__low2float(hv)),
-                                                      __high2float(av) * gelu_grad_fast(__high2float(hv)));
+      float g0 = __low2float(av) * gelu_grad_fast(__low2float(hv));
+      float g1 = __high2float(av) * gelu_grad_fast(__high2float(hv));
+      if (DROP) { g0 *= keep[2 * j]; g1 *= keep[2 * j + 1]; }
+      const __nv_bfloat162 o = __floats2bfloat162_rn(g0, g1);
       ow[j] = *reinterpret_cast<const uint32_t*>(&o);
     }
     dh[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
 }
+bool gelu_dropout_bwd_supported(const void* da, const void* h, void* dh, long long n, int f32) {
+  const bool aligned = ((reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(dh)) & 15) == 0;
+  return !f32 && aligned && n % 8 == 0;
+}
+int launch_gelu_dropout_bwd(const void* da, const void* h, void* dh, long long n, float p, unsigned long long seed,
+                            unsigned site, unsigned step, const unsigned* step_dev, cudaStream_t st) {
+  if (n <= 0) return VIT3D_OK;
+  gelu_bwd_bf16_kernel<true><<<ew_blocks(n / 8), 256, 0, st>>>(
+      reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(h), reinterpret_cast<uint4*>(dh), n / 8,
+      dropout_thresh(p), 1.0f / (1.0f - p), seed, site, step, step_dev);
+  V3_LAUNCH_CHECK();
+  return VIT3D_OK;
+}
 int launch_gelu_bwd(const void* da, const void* h, void* dh, long long n, int f32, cudaStream_t st) {
   if (n <= 0) return VIT3D_OK;
-  const bool aligned = ((reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(dh)) & 15) == 0;
-  if (!f32 && aligned && n % 8 == 0) {
-    gelu_bwd_bf16_kernel<<<ew_blocks(n / 8), 256, 0, st>>>(reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(h),
-                                                           reinterpret_cast<uint4*>(dh), n / 8);
+  if (gelu_dropout_bwd_supported(da, h, dh, n, f32)) {
+    gelu_bwd_bf16_kernel<false><<<ew_blocks(n / 8), 256, 0, st>>>(reinterpret_cast<const uint4*>(da),
+                                                                  reinterpret_cast<const uint4*>(h),
+                                                                  reinterpret_cast<uint4*>(dh), n / 8, 0u, 1.f, 0ull, 0u, 0u, nullptr);
     V3_LAUNCH_CHECK();
     return VIT3D_OK;
   }

@@ -40,6 +40,9 @@ int launch_attn_bwd_generic(const void* dctx, const void* qkv, int f32, void* dq
                             cudaStream_t st);
 int launch_gelu_fwd(const void* h, void* a, long long n, int f32, cudaStream_t st);
 int launch_gelu_bwd(const void* da, const void* h, void* dh, long long n, int f32, cudaStream_t st);
+bool gelu_dropout_bwd_supported(const void* da, const void* h, void* dh, long long n, int f32);
+int launch_gelu_dropout_bwd(const void* da, const void* h, void* dh, long long n, float p, unsigned long long seed,
+                            unsigned site, unsigned step, const unsigned* step_dev, cudaStream_t st);
 int launch_dropout(const void* x, const void* residual, void* y, long long n, int f32, float p,
                    unsigned long long seed, unsigned site, unsigned step, const unsigned* step_dev, cudaStream_t st);
 int launch_dropout_mask(unsigned char* mask, long long n, float p, unsigned long long seed, unsigned site, unsigned step,

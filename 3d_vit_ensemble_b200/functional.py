@@ -240,7 +240,9 @@ class LinearFn(torch.autograd.Function):
     (modeling.py:120) and the residual add (modeling.py:191,196) folded into the epilogue."""
 
     @staticmethod
-    def forward(ctx, x, w, b, residual, act, prec, out_f32):
+    def forward(ctx, x, w, b, residual, act, prec, out_f32, drop=None):
+        """drop = (p, seed, site, step): Dropout applied to the activation output (modeling.py:121); its
+        backward is folded into the GELU backward kernel."""
         _need_cuda(x, w, b, residual)
         N, K = w.shape
         lead = x.shape[:-1]
@@ -265,6 +267,12 @@ class LinearFn(torch.autograd.Function):
         call("vit3d_linear_fwd", ptr(x2), ldx, int(x2.dtype == torch.float32), ptr(w), ptr(w_lp),
              ptr(None if b is None else _c(b)), ptr(res), ptr(y), int(yd == torch.float32), ptr(pre), act, M, N, K,
              PREC[prec], stream())
+        ctx.drop = None
+        if drop is not None:
+            p_, seed_, site_, step_ = drop
+            call("vit3d_dropout", ptr(y), None, ptr(y), y.numel(), int(yd == torch.float32), float(p_), seed_, site_,
+                 step_, ptr(_STATE.get("step_dev")), stream())
+            ctx.drop = drop
         ctx.save_for_backward(x2, w, w_lp, pre)
         ctx.w_obj = w_obj if (prec == "bf16" and w_obj.is_contiguous() and w_obj.dim() == 2) else None
         ctx.params = (w_obj, b)
@@ -283,9 +291,22 @@ class LinearFn(torch.autograd.Function):
             if dy2.dtype != pre.dtype:
                 dy2 = dy2.to(pre.dtype)
             dh = torch.empty_like(pre)
-            # gelu'(pre) * dy, exact erf form
-            call("vit3d_gelu_bwd", ptr(dy2), ptr(pre), ptr(dh), dh.numel(),
-                 PREC["fp32"] if pre.dtype == torch.float32 else PREC["bf16"], stream())
+            pid = PREC["fp32"] if pre.dtype == torch.float32 else PREC["bf16"]
+            if ctx.drop is not None:
+                p_, seed_, site_, step_ = ctx.drop
+                fused = (pre.dtype == torch.bfloat16 and dh.numel() % 8 == 0 and dy2.data_ptr() % 16 == 0
+                         and pre.data_ptr() % 16 == 0 and dh.data_ptr() % 16 == 0)
+                if fused:       # dropout' and gelu' in one pass over the [M, mlp_dim] gradient
+                    call("vit3d_gelu_dropout_bwd", ptr(dy2), ptr(pre), ptr(dh), dh.numel(), pid, float(p_), seed_,
+                         site_, step_, ptr(_STATE.get("step_dev")), stream())
+                else:
+                    tmp = torch.empty_like(dy2)
+                    call("vit3d_dropout", ptr(dy2), None, ptr(tmp), dy2.numel(), int(dy2.dtype == torch.float32),
+                         float(p_), seed_, site_, step_, ptr(_STATE.get("step_dev")), stream())
+                    call("vit3d_gelu_bwd", ptr(tmp), ptr(pre), ptr(dh), dh.numel(), pid, stream())
+            else:
+                # gelu'(pre) * dy
+                call("vit3d_gelu_bwd", ptr(dy2), ptr(pre), ptr(dh), dh.numel(), pid, stream())
             dy2 = dh
         need_dx = ctx.needs_input_grad[0]
         dx = torch.empty(M, K, device=dy.device, dtype=x2.dtype) if need_dx else None
@@ -313,7 +334,7 @@ class LinearFn(torch.autograd.Function):
         if tb is not None:
             _grad_done(ctx.params[1])
             db = None
-        return dx, dw, db, d_res, None, None, None
+        return dx, dw, db, d_res, None, None, None, None
 
 
 def mlp_fused_supported(M: int, H: int, d: int) -> bool:
@@ -337,8 +358,8 @@ def mlp_fused(xn, w1, b1, w2, b2, residual):
     return out.reshape(residual.shape)
 
 
-def linear(x, w, b=None, residual=None, act=ACT_NONE, prec=None, out_f32=False):
-    return LinearFn.apply(x, w, b, residual, act, prec or get_precision(), out_f32)
+def linear(x, w, b=None, residual=None, act=ACT_NONE, prec=None, out_f32=False, drop=None):
+    return LinearFn.apply(x, w, b, residual, act, prec or get_precision(), out_f32, drop)
 
 
 # ----------------------------------------------------------------------------- attention core

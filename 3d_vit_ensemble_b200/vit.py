@@ -102,8 +102,14 @@ class Mlp(nn.Module):
                 and F.mlp_fused_supported(x.numel() // x.shape[-1], x.shape[-1], self.fc1.weight.shape[0])):
             # inference: one kernel, the (M, mlp_dim) intermediate stays in TMEM / shared memory
             return F.mlp_fused(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, residual)
-        h = F.linear(x, self.fc1.weight, self.fc1.bias, act=ACT_GELU, prec=prec)
-        h = F.dropout(h, p, train, self._site, step)
+        if train and F._STATE["mask_override"] is None:
+            # Dropout after the GELU rides along with fc1: applied in place on its output, undone inside the
+            # GELU backward kernel (no separate pass over the (M, mlp_dim) gradient)
+            seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+            h = F.linear(x, self.fc1.weight, self.fc1.bias, act=ACT_GELU, prec=prec, drop=(p, seed, self._site, step))
+        else:
+            h = F.linear(x, self.fc1.weight, self.fc1.bias, act=ACT_GELU, prec=prec)
+            h = F.dropout(h, p, train, self._site, step)
         if train:
             # Dropout follows fc2 and precedes the residual add (modeling.py:123, :196)
             y = F.linear(h, self.fc2.weight, self.fc2.bias, prec=prec, out_f32=True)

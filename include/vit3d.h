@@ -130,6 +130,11 @@ int vit3d_attn_bwd(const void* dctx, const void* qkv, void* dqkv, int B, int S, 
  * exact-erf GELU (modeling.py:52,107,120): a = gelu(h); da -> dh */
 int vit3d_gelu_fwd(const void* h, void* a, long long n, int prec, vit3d_stream_t stream);
 int vit3d_gelu_bwd(const void* da, const void* h, void* dh, long long n, int prec, vit3d_stream_t stream);
+/* dh = dropout'(da) * gelu'(h) in one pass (BF16 mode): the backward of Dropout(gelu(h)) at modeling.py:120-121,
+ * mask regenerated from (seed, site, step).  VIT3D_ERR_UNSUPPORTED unless bf16 / aligned / n % 8 == 0. */
+int vit3d_gelu_dropout_bwd(const void* da, const void* h, void* dh, long long n, int prec, float p,
+                           unsigned long long seed, unsigned site, unsigned step, const unsigned* step_dev,
+                           vit3d_stream_t stream);
 /* Dropout(p) in training (modeling.py:121,123,174): y = x * keep / (1-p) (+ residual, same type, may be
  * NULL: the x + Mlp(..) add of modeling.py:196) with a counter-based Philox mask keyed by
  * (seed, site, step, element index); the same call on dy (residual NULL) gives dx. */
