@@ -47,6 +47,31 @@ static inline cudaStream_t as_stream(vit3d_stream_t s) { return reinterpret_cast
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 int sm_count();
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Kernels launched with launch_pdl() may start while the previous kernel in the stream is still draining:
+// everything before pdl_wait() (barrier init, TMEM allocation, descriptor prefetch, smem carve-up) overlaps
+// the predecessor's tail; pdl_wait() returns once the predecessor has completed and its writes are visible.
+// No global memory may be read OR written before pdl_wait().  pdl_trigger() lets the NEXT kernel's CTAs be
+// scheduled as soon as this kernel's CTAs free their SMs.  Captured into CUDA graphs as programmatic edges.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ----------------------------------------------------------------------------- device math
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -229,6 +229,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
                                                      float eps) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  pdl_trigger();
+  pdl_wait();
   if (row >= M) return;
   const float* xr = x + (long long)row * H;
   float v[LN_MAXV];
@@ -284,9 +286,9 @@ int launch_ln_fwd(const float* x, const float* g, const float* b, void* y, int y
   if (M <= 0) return VIT3D_OK;
   const int rows_per_block = 8;
   const int blocks = ceil_div(M, rows_per_block);
-  if (y_bf16 == 1) ln_fwd_kernel<1><<<blocks, 256, 0, st>>>(x, g, b, y, mean, rstd, M, H, eps);
-  else if (y_bf16 == 2) ln_fwd_kernel<2><<<blocks, 256, 0, st>>>(x, g, b, y, mean, rstd, M, H, eps);
-  else ln_fwd_kernel<0><<<blocks, 256, 0, st>>>(x, g, b, y, mean, rstd, M, H, eps);
+  if (y_bf16 == 1) V3_CUDA(launch_pdl(ln_fwd_kernel<1>, dim3(blocks), dim3(256), (size_t)0, st, x, g, b, y, mean, rstd, M, H, eps));
+  else if (y_bf16 == 2) V3_CUDA(launch_pdl(ln_fwd_kernel<2>, dim3(blocks), dim3(256), (size_t)0, st, x, g, b, y, mean, rstd, M, H, eps));
+  else V3_CUDA(launch_pdl(ln_fwd_kernel<0>, dim3(blocks), dim3(256), (size_t)0, st, x, g, b, y, mean, rstd, M, H, eps));
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }

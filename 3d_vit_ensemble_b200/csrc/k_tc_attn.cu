@@ -88,6 +88,8 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_trigger();
+  pdl_wait();
 
   auto issue_load = [&](int b, int buf) {   // warp 0, all lanes
     if (lane == 0) mbar_arrive_expect_tx(&full[buf], AT_S * AT_ROWB);
@@ -238,8 +240,8 @@ static int launch_attn(const void* qkv, void* ctx, float* probs, int B, cudaStre
   V3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
   const int grid = B < sm_count() ? B : sm_count();
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)D);
-  kern<<<grid, AT_THREADS, AT_SMEM, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                           reinterpret_cast<__nv_bfloat16*>(ctx), probs, B, scale_log2e);
+  V3_CUDA(launch_pdl(kern, dim3(grid), dim3(AT_THREADS), (size_t)AT_SMEM, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
+                     reinterpret_cast<__nv_bfloat16*>(ctx), probs, B, scale_log2e));
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
@@ -294,6 +296,8 @@ attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16* 
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_trigger();
+  pdl_wait();
   const uint32_t sb = smem_u32(s_qkv), dob = smem_u32(s_do);
 
   int it = 0;
@@ -519,9 +523,9 @@ static int launch_attn_bwd(const void* dctx, const void* qkv, void* dqkv, int B,
   V3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
   const int grid = B < sm_count() ? B : sm_count();
   const float scale = 1.0f / sqrtf((float)D);
-  kern<<<grid, AT_THREADS, AB_SMEM, st>>>(reinterpret_cast<const __nv_bfloat16*>(dctx),
-                                           reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                           reinterpret_cast<__nv_bfloat16*>(dqkv), B, scale, 1.4426950408889634f * scale);
+  V3_CUDA(launch_pdl(kern, dim3(grid), dim3(AT_THREADS), (size_t)AB_SMEM, st, reinterpret_cast<const __nv_bfloat16*>(dctx),
+                     reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(dqkv), B, scale,
+                     1.4426950408889634f * scale));
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }

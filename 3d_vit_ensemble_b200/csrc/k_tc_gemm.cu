@@ -128,6 +128,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_trigger();     // the next kernel may begin its own prologue on SMs this grid frees
+  pdl_wait();        // everything above overlapped the previous kernel's tail; global memory from here on
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -310,8 +312,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     if (cpn > tiles_m) cpn = tiles_m;
     grid = cpn * tiles_n;
   }
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tp, ep, M, N, K, tiles_m, tiles_n, splits, stationary ? 1 : 0,
-                                                      patch_blocks, mn_major);
+  V3_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, ta, tb, tc, tp, ep, M, N, K, tiles_m,
+                     tiles_n, splits, stationary ? 1 : 0, patch_blocks, mn_major));
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }

@@ -61,8 +61,12 @@ def test_graphed_train_step_equals_eager(opt_name):
     assert abs(le - lg) < 2e-3 * max(1.0, abs(le)), (le, lg)
     # atomics order differs run to run; Adam turns a gradient that is noise around 0 into a +-lr step, so allow
     # a fraction of the total possible movement (7 steps x lr) for it
-    slack = 0.35 * 7 * 1e-4 if opt_name == "adam" else 0.0
     for k in se:
+        slack = 0.0
+        if opt_name == "adam":
+            # key.bias has an exactly-zero true gradient (softmax is shift invariant): its computed gradient is
+            # rounding noise and Adam moves it +-lr per step in a run-dependent direction
+            slack = (2.0 if k.endswith("attn.key.bias") else 0.35) * 7 * 1e-4
         d = float((se[k] - sg[k]).abs().max())
         assert d <= 2e-3 * float(se[k].abs().max()) + 1e-6 + slack, (k, d)
     assert np.isfinite(le)
