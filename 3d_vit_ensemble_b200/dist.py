@@ -93,6 +93,7 @@ class GradReducer:
             self._bucket_params[b].append(p)
             self._param_bucket[id(p)] = b
         self._pending = {}
+        self._seen = set()
         self._named = named
         self._handles: List = []
         self._stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
@@ -114,13 +115,21 @@ class GradReducer:
             p.grad = self.views[n]
         self._pending = {b: len(ps) for b, ps in self._bucket_params.items()}
         self._handles = []
+        self._seen = set()
         # parameters whose gradient the kernels accumulate in place never reach autograd's hooks:
         # functional._grad_done reports them here instead
         from . import functional as F
         F._STATE["grad_hook"] = self._on_grad
 
     def _on_grad(self, p):
-        b = self._param_bucket[id(p)]
+        # a parameter can be reported twice per step: by the kernels' in-place accumulation path
+        # (functional._grad_done) and by autograd's post-accumulate hook, which also fires for a None gradient
+        if id(p) in self._seen:
+            return
+        self._seen.add(id(p))
+        b = self._param_bucket.get(id(p))
+        if b is None:
+            return
         self._pending[b] -= 1
         if self._pending[b] == 0 and self.overlap:
             self._launch(b)

@@ -143,3 +143,16 @@ def test_pack_jobs():
     assert sorted(i for p in packs for i in p) == list(range(len(costs)))
     loads = [sum(costs[i] for i in p) for p in packs]
     assert max(loads) - min(loads) <= max(costs)
+
+
+def test_grad_reducer_counts_each_parameter_once():
+    """A parameter may be reported by the in-place accumulation path AND by autograd's hook (which also
+    fires for a None gradient): the bucket countdown must not go negative (it would all-reduce twice)."""
+    m = Toy()
+    red = D.GradReducer(m)
+    red.prepare()
+    for p in m.parameters():
+        red._on_grad(p)
+        red._on_grad(p)
+    assert all(v == 0 for v in red._pending.values()), red._pending
+    red.remove()
