@@ -215,11 +215,18 @@ class ShardedEnsemble:
     `ensemble` is a `TransformerEnsemble` whose members all live on this rank's device (weights are small:
     <= 60 MB per member); every rank receives the same input batch `x`."""
 
-    def __init__(self, ensemble, costs: Optional[Sequence[float]] = None, group=None):
+    def __init__(self, ensemble, costs: Optional[Sequence[float]] = None, group=None, graphs: bool = True):
+        """graphs=True replays each member's forward from a CUDA graph (one per member and slice shape): a rank's
+        share of a batch is small, so launch overhead would otherwise dominate."""
         self.ensemble = ensemble
         self.group = group
         m = len(ensemble.transformers)
         self.costs = list(costs) if costs is not None else [1.0] * m
+        self._graphed = None
+        params = list(ensemble.parameters()) if hasattr(ensemble, "parameters") else []
+        if graphs and params and params[0].is_cuda:
+            from .graphs import GraphedInference
+            self._graphed = [GraphedInference(t) for t in ensemble.transformers]
 
     @torch.no_grad()
     def member_logits(self, x: torch.Tensor) -> torch.Tensor:
@@ -232,7 +239,8 @@ class ShardedEnsemble:
         off = 0
         for j, b0, b1 in parts[rank]:
             if b1 > b0:
-                lg = self.ensemble.transformers[j](x[b0:b1])[0]
+                member = self._graphed[j] if self._graphed is not None else self.ensemble.transformers[j]
+                lg = member(x[b0:b1])[0]
                 mine[off:off + (b1 - b0)] = lg.reshape(-1).float()
                 off += b1 - b0
         if ws > 1:

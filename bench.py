@@ -202,15 +202,16 @@ def main():
         from vit3d_b200.dist import GradReducer, global_pos_weight
         from vit3d_b200.optim import FusedSGD
         opt = FusedSGD(model.parameters(), lr=1e-4, momentum=0.9, weight_decay=1e-2)
-        reducer = GradReducer(model, arena=opt.arena) if world > 1 else None
+        reducer = GradReducer(model, arena=opt.arena) if (world > 1 and not args.graphs) else None
     elif len(members) > 1:
         from vit3d_b200.dist import ShardedEnsemble
         sharded = ShardedEnsemble(model, costs=[O.fwd_flops_per_volume(c) for c in cfgs])
 
     graphed = None
-    if args.graphs and train and world == 1:
+    if args.graphs and train:
         from vit3d_b200.graphs import GraphedTrainStep
-        graphed = GraphedTrainStep(model, opt, warmup=2)
+        graphed = GraphedTrainStep(model, opt, warmup=2, data_parallel=world > 1)
+        reducer = None
     elif args.graphs and not train and sharded is None:
         from vit3d_b200.graphs import GraphedInference
         graphed = GraphedInference(model)
@@ -218,7 +219,7 @@ def main():
     def step_dev(x, y):
         if graphed is not None:
             if train:
-                return graphed(x, y, O.balanced_pos_weight(y_host))
+                return graphed(x, y, global_pos_weight(y) if world > 1 else O.balanced_pos_weight(y_host))
             out = graphed(x)
             return out[0] if isinstance(out, tuple) else out
         if train:
@@ -367,7 +368,7 @@ def main():
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": wl["name"], "batch_per_gpu": B, "global_batch": units, "vis": bool(args.vis),
                        "precision": args.precision, "cuda_graph": graphed is not None, "l2": "inputs larger than L2 (batch of fp32 volumes = %.0f MB)" % (B * 327680 / 1e6),
-                       "parallelism": (f"dp{world}: batch sharded, per-Block gradient all-reduce (NCCL) overlapped with backward, fused SGD step"
+                       "parallelism": (f"dp{world}: batch sharded, fwd+bwd replayed from a CUDA graph, one NCCL all-reduce of the flat gradient arena, fused SGD step"
                                        if train else (f"{world} ranks: (member, batch-slice) work list balanced by FLOPs, all-gather of member logits, meta-head on every rank"
                                                       if len(members) > 1 else f"dp{world} (independent volumes, no data-path collective)"))},
             "model_tflops": value * flops_per_vol / 1e12,
