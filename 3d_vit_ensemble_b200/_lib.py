@@ -42,6 +42,8 @@ SIGNATURES = {
     "vit3d_last_error": (C.c_char_p, []),
     "vit3d_device_info": (_i, [C.POINTER(_i), C.POINTER(_i)]),
     "vit3d_launch_count": (_ull, []),
+    "vit3d_set_tuning": (_i, [_i, _i]),
+    "vit3d_get_tuning": (_i, [_i]),
     "vit3d_act_bytes": (_i, [_i]),
     "vit3d_tc_supported": (_i, [_i, _i, _i, _i]),
     "vit3d_patch_gather": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
@@ -51,6 +53,8 @@ SIGNATURES = {
     "vit3d_ln_fwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _i, _i, _f, _p]),
     "vit3d_ln_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "vit3d_linear_fwd": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _p]),
+    "vit3d_linear_ln_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _i, _i, _i, _p]),
+    "vit3d_linear_ln_supported": (_i, [_i, _i, _i]),
     "vit3d_linear_bwd": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _p]),
     "vit3d_mlp_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "vit3d_mlp_supported": (_i, [_i, _i, _i]),

@@ -1,6 +1,7 @@
 // extern "C" surface of libvit3d_sm100.so (declared in include/vit3d.h): argument checks and
 // dispatch between the tcgen05 kernels and the shape-generic fp32 kernels.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -35,6 +36,21 @@ int sm_count() {
   return cached;
 }
 
+// tuning switches: A/B selection of kernel variants without rebuilding (defaults: environment, else built-in)
+static int g_tuning[VIT3D_TUNE_COUNT];
+static bool g_tuning_init = false;
+static void tuning_defaults() {
+  if (g_tuning_init) return;
+  auto env = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+  g_tuning[VIT3D_TUNE_EPI_DIRECT] = env("VIT3D_EPI_DIRECT", 1);
+  g_tuning[VIT3D_TUNE_ATTN_THREADS] = env("VIT3D_ATTN_THREADS", 640);
+  g_tuning_init = true;
+}
+int tuning(int key) {
+  tuning_defaults();
+  return (key >= 0 && key < VIT3D_TUNE_COUNT) ? g_tuning[key] : 0;
+}
+
 static inline int act_f32(int prec) { return prec != VIT3D_PREC_BF16; }
 
 }  // namespace vit3d
@@ -55,6 +71,13 @@ int vit3d_device_info(int* sms, int* cc) {
   if (cc) *cc = p.major * 10 + p.minor;
   return VIT3D_OK;
 }
+int vit3d_set_tuning(int key, int value) {
+  V3_REQUIRE(key >= 0 && key < VIT3D_TUNE_COUNT, "set_tuning: unknown key %d", key);
+  tuning_defaults();
+  g_tuning[key] = value;
+  return VIT3D_OK;
+}
+int vit3d_get_tuning(int key) { return tuning(key); }
 unsigned long long vit3d_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 int vit3d_act_bytes(int prec) { return prec == VIT3D_PREC_BF16 ? 2 : 4; }
 int vit3d_tc_supported(int prec, int M, int N, int K) { return tc_linear_supported(prec, M, N, K) ? 1 : 0; }
@@ -190,6 +213,23 @@ int vit3d_linear_fwd(const void* x, int ldx, int x_f32, const float* w, const vo
   g.bias = bias; g.residual = residual; g.ldr = N; g.pre = pre; g.act = act;
   g.M = M; g.N = N; g.K = K;
   return launch_sgemm(g, st);
+}
+
+int vit3d_linear_ln_supported(int M, int N, int K) { return tc_linear_ln_supported(VIT3D_PREC_BF16, M, N, K) ? 1 : 0; }
+
+int vit3d_linear_ln_fwd(const void* x, const void* w_lp, const float* bias, const float* residual, float* y,
+                        const float* gamma, const float* beta, float eps, void* ln_out, float* mean, float* rstd, int M,
+                        int N, int K, vit3d_stream_t stream) {
+  V3_REQUIRE(x && w_lp && y && gamma && beta && ln_out, "linear_ln_fwd: null pointer");
+  V3_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_ln_fwd: bad shape M=%d N=%d K=%d", M, N, K);
+  if (M == 0) return VIT3D_OK;
+  if (!tc_linear_ln_supported(VIT3D_PREC_BF16, M, N, K))
+    V3_UNSUPPORTED("linear_ln_fwd: needs BF16 mode shapes with N == 256 (got M=%d N=%d K=%d)", M, N, K);
+  TcLinear t;
+  t.x = x; t.w = w_lp; t.bias = bias; t.residual = residual; t.y = y; t.y_f32 = 1; t.M = M; t.N = N; t.K = K;
+  t.prec = VIT3D_PREC_BF16;
+  t.ln_gamma = gamma; t.ln_beta = beta; t.ln_out = ln_out; t.ln_mean = mean; t.ln_rstd = rstd; t.ln_eps = eps;
+  return tc_linear_fwd(t, as_stream(stream));
 }
 
 int vit3d_linear_bwd(const void* dy, int dy_f32, const void* x, int ldx, int x_f32, const float* w, const void* w_t_lp,

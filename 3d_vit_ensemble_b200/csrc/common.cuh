@@ -46,6 +46,8 @@ void count_launch();
 static inline cudaStream_t as_stream(vit3d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 int sm_count();
+// run-time tuning switches (vit3d_set_tuning; defaults from the environment, see include/vit3d.h)
+int tuning(int key);
 
 // ----------------------------------------------------------------------------- programmatic dependent launch
 // Kernels launched with launch_pdl() may start while the previous kernel in the stream is still draining:

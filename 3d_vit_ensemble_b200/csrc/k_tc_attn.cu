@@ -9,6 +9,8 @@
 // whole [65 x 256] context block leaves with bulk async stores.  With vis=True the fp32 probabilities
 // (B,k,65,65) are written from registers.  HBM traffic per volume: 99.8 KB in, 33.3 KB out
 // (+ k*65*65*4 B of probabilities) - the kernel is bandwidth bound.
+#include <stdlib.h>
+
 #include "ptx.cuh"
 #include "tc.cuh"
 
@@ -21,7 +23,7 @@ constexpr int AT_A = 256;          // all-head size (heads * D)
 constexpr int AT_ROWB = 3 * AT_A * 2;       // 1536 bytes of qkv per token
 constexpr int AT_PITCH = AT_ROWB + 16;      // padded smem row pitch: conflict-free ldmatrix
 constexpr int AT_BUF = AT_S * AT_PITCH;     // 100,880 bytes per volume buffer
-constexpr int AT_THREADS = 512;          // 16 warps: 4 per scheduler hide the ldmatrix / mma / MUFU latencies
+constexpr int AT_THREADS = 512;          // backward kernel: 16 warps
 constexpr int AT_SMEM = 2 * AT_BUF + 64 + 128;
 
 __device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -67,8 +69,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
-template <int D>
-__global__ void __launch_bounds__(AT_THREADS, 1)
+// THREADS: 512 (16 warps) or 640 (20 warps).  A volume is HEADS * 5 (head, 16-row tile) tasks: 40 tasks take
+// 3 rounds of 16 warps but 2 rounds of 20 (80 tasks: 5 vs 4, 20 tasks: 2 vs 1), and the fifth warp per
+// scheduler hides more of the ldmatrix / mma / MUFU / store latency.
+template <int D, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, float* __restrict__ probs,
                    int B, float scale_log2e) {
   constexpr int HEADS = AT_A / D;
@@ -112,7 +117,7 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
     mbar_wait(&full[buf], (it >> 1) & 1);
     const uint32_t sb = smem_u32(smem + buf * AT_BUF);
 
-    for (int task = warp; task < HEADS * 5; task += AT_THREADS / 32) {
+    for (int task = warp; task < HEADS * 5; task += THREADS / 32) {
       const int h = task / 5, rt = task % 5;
       const int r0 = rt * 16;
       // ---- Q fragments (A operand), rows clamped to the last token
@@ -234,17 +239,18 @@ bool tc_attn_supported(int S, int heads, int D) {
   return S == AT_S && heads * D == AT_A && (D == 16 || D == 32 || D == 64);
 }
 
-template <int D>
+template <int D, int THREADS>
 static int launch_attn(const void* qkv, void* ctx, float* probs, int B, cudaStream_t st) {
-  auto kern = attn_fwd_tc_kernel<D>;
+  auto kern = attn_fwd_tc_kernel<D, THREADS>;
   V3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
   const int grid = B < sm_count() ? B : sm_count();
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)D);
-  V3_CUDA(launch_pdl(kern, dim3(grid), dim3(AT_THREADS), (size_t)AT_SMEM, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
+  V3_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), (size_t)AT_SMEM, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
                      reinterpret_cast<__nv_bfloat16*>(ctx), probs, B, scale_log2e));
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
+static int attn_threads() { return tuning(VIT3D_TUNE_ATTN_THREADS) == 512 ? 512 : 640; }
 
 int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int heads, int D, cudaStream_t st) {
   if (!tc_attn_supported(S, heads, D)) V3_UNSUPPORTED("tc attention: unsupported shape S=%d heads=%d D=%d", S, heads, D);
@@ -253,9 +259,14 @@ int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int head
     set_error("tc attention: qkv/ctx must be 16-byte aligned");
     return VIT3D_ERR_INVALID;
   }
-  if (D == 16) return launch_attn<16>(qkv, ctx, probs, B, st);
-  if (D == 32) return launch_attn<32>(qkv, ctx, probs, B, st);
-  return launch_attn<64>(qkv, ctx, probs, B, st);
+  if (attn_threads() == 640) {
+    if (D == 16) return launch_attn<16, 640>(qkv, ctx, probs, B, st);
+    if (D == 32) return launch_attn<32, 640>(qkv, ctx, probs, B, st);
+    return launch_attn<64, 640>(qkv, ctx, probs, B, st);
+  }
+  if (D == 16) return launch_attn<16, 512>(qkv, ctx, probs, B, st);
+  if (D == 32) return launch_attn<32, 512>(qkv, ctx, probs, B, st);
+  return launch_attn<64, 512>(qkv, ctx, probs, B, st);
 }
 
 // ============================================================================ backward

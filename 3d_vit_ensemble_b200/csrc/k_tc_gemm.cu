@@ -9,6 +9,8 @@
 //     buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   * kind::f16 (bf16 operands) or kind::tf32 (fp32 operands read directly, no conversion pass).
 //   * optional split-K (work item = tile x K-slice, fp32 atomics) for deep-K / small-output products.
+#include <stdlib.h>
+
 #include <mutex>
 #include <unordered_map>
 
@@ -80,8 +82,10 @@ struct TileIter {
   }
 };
 
-template <bool TF32, int BN>
-__global__ void __launch_bounds__(tc_threads(BN), 1)
+// LNF: the fused-LayerNorm instantiation (bf16 operands, BN = N = 256, direct fp32 epilogue) is a separate
+// kernel so that its 64 live row values do not set the register budget of every other GEMM.
+template <bool TF32, int BN, bool LNF = false>
+__global__ void __launch_bounds__(tc_threads(BN)) __maxnreg__(BN >= 128 ? 112 : 168)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmPre, TcEpilogue ep, int M,
                int N, int K, int tiles_m, int tiles_n, int splits, int stationary, int patch_blocks, int mn_major) {
@@ -225,8 +229,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + part * CW;
-      epilogue_rows<CW, !TF32>(ep, &tmC, &tmPre, taddr, stage, lane, ti.tm * TC_BLOCK_M + q * 32, ti.tn * BN + part * CW,
-                               M, N);
+      const int m_base = ti.tm * TC_BLOCK_M + q * 32, n_base = ti.tn * BN + part * CW;
+      if constexpr (LNF) {
+        // the (unused) staging region holds the two 4 KB row-statistics scratch buffers
+        float2* scratch = reinterpret_cast<float2*>(epi_stage) + (it & 1) * (Cfg::EPI_WARPS * 32);
+        epilogue_direct_f32<CW, Cfg::EPI_WARPS / 4, true, false>(ep, taddr, lane, m_base, n_base, M, N, scratch, part, q);
+      } else if (ep.direct) {
+        if (ep.out_f32) epilogue_direct_f32<CW, Cfg::EPI_WARPS / 4, false, TF32>(ep, taddr, lane, m_base, n_base, M, N, nullptr, part, q);
+        else epilogue_direct_bf16<CW, !TF32>(ep, taddr, lane, m_base, n_base, M, N);
+      } else {
+        epilogue_rows<CW, !TF32>(ep, &tmC, &tmPre, taddr, stage, lane, m_base, n_base, M, N);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -290,12 +303,12 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long ro
   return VIT3D_OK;
 }
 
-template <bool TF32, int BN>
+template <bool TF32, int BN, bool LNF = false>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
                      const TcEpilogue& ep, int M, int N, int K, int splits, bool stationary, cudaStream_t st,
                      int patch_blocks = 0, int mn_major = 0) {
   using Cfg = TcCfg<BN>;
-  auto kern = tc_gemm_kernel<TF32, BN>;
+  auto kern = tc_gemm_kernel<TF32, BN, LNF>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   V3_CUDA(cudaGetDevice(&dev));
@@ -319,8 +332,26 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 }
 
 // D[M,N] = A[M,K] B[N,K]^T with both operands dense row-major K-major; elem = 2 (bf16) or 4 (tf32)
-int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const TcEpilogue& ep, int splits,
+static bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
+// VIT3D_EPI_DIRECT=0 selects the staged (shared-memory transpose / bulk tensor store) epilogue for A/B timing
+static bool direct_enabled() { return tuning(VIT3D_TUNE_EPI_DIRECT) != 0; }
+
+int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const TcEpilogue& ep_in, int splits,
             cudaStream_t st) {
+  TcEpilogue ep = ep_in;
+  // row-owner epilogue whenever the output rows can take aligned 32-byte stores
+  ep.direct = 0;
+  if (direct_enabled() && !ep.atomic && ep.row_group == 0 && !ep.rowadd && aligned32(ep.out) && aligned32(ep.pre) &&
+      aligned32(ep.residual) && (ep.out_f32 ? N % 8 == 0 : N % 16 == 0))
+    ep.direct = 1;
+  if (!tf32 && ep.out_f32 && ep.act == VIT3D_ACT_GELU) ep.direct = 0;   // fp32 GELU output from bf16 operands: staged path
+  const bool lnf = ep.ln_out != nullptr;
+  if (lnf) {
+    if (tf32 || N != 256 || !ep.out_f32 || !ep.direct || splits != 1 || !aligned32(ep.ln_out) || !ep.ln_gamma || !ep.ln_beta) {
+      set_error("tc_gemm: fused LayerNorm needs bf16 operands, N == 256, fp32 32-byte aligned output");
+      return VIT3D_ERR_UNSUPPORTED;
+    }
+  }
   const int eb = tf32 ? 4 : 2;
   const int sms = sm_count();
   const int tm = ceil_div(M, TC_BLOCK_M);
@@ -329,6 +360,7 @@ int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const 
   int bn = 256;
   if (N <= 64 || (long long)tm * ceil_div(N, 256) * splits < sms) bn = 128;
   if (N <= 64 || (bn == 128 && (long long)tm * ceil_div(N, 128) * splits < sms)) bn = 64;
+  if (lnf) bn = 256;                    // a CTA must own whole rows
   // stationary-B schedule when the [bn x K] weight slab fits (shrink the tile once if that makes it fit)
   auto fits = [&](int b) { return splits == 1 && (long long)nkb * b * 128 <= TC_SLAB_BYTES && ceil_div(N, b) <= sms; };
   bool stationary = fits(bn);
@@ -340,7 +372,7 @@ int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const 
   if (rc != VIT3D_OK) return rc;
   tc = ta;
   tp = ta;
-  if (!ep.out_f32) {   // bf16 outputs leave through bulk tensor stores
+  if (!ep.out_f32 && !ep.direct) {   // staged bf16 outputs leave through bulk tensor stores
     if (ep.row_group > 0 || ep.atomic) { set_error("tc_gemm: bf16 output with row remap / atomics is not supported"); return VIT3D_ERR_INVALID; }
     rc = make_tmap_2d(&tc, ep.out, 2, M, N, N, 32, 32, 64);
     if (rc != VIT3D_OK) return rc;
@@ -354,6 +386,7 @@ int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const 
     if (bn == 128) return launch_tc<true, 128>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
     return launch_tc<true, 64>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
   }
+  if (lnf) return launch_tc<false, 256, true>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
   if (bn == 256) return launch_tc<false, 256>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
   if (bn == 128) return launch_tc<false, 128>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
   return launch_tc<false, 64>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
@@ -402,10 +435,17 @@ bool tc_linear_supported(int prec, int M, int N, int K) {
   return false;
 }
 
+// fused Linear + residual + LayerNorm: a CTA's 128 x 256 tile must span whole rows
+bool tc_linear_ln_supported(int prec, int M, int N, int K) {
+  return prec == VIT3D_PREC_BF16 && N == 256 && tc_linear_supported(prec, M, N, K) && direct_enabled();
+}
+
 int tc_linear_fwd(const TcLinear& t, cudaStream_t st) {
   TcEpilogue ep;
   ep.bias = t.bias; ep.residual = t.residual; ep.out = t.y; ep.pre = t.pre; ep.out_f32 = t.y_f32; ep.act = t.act;
   ep.round_tf32 = (t.prec == VIT3D_PREC_TF32 && t.act == VIT3D_ACT_GELU && !t.residual) ? 1 : 0;
+  ep.ln_gamma = t.ln_gamma; ep.ln_beta = t.ln_beta; ep.ln_out = t.ln_out; ep.ln_mean = t.ln_mean; ep.ln_rstd = t.ln_rstd;
+  ep.ln_eps = t.ln_eps;
   return tc_gemm(t.prec == VIT3D_PREC_TF32, t.x, t.w, t.M, t.N, t.K, ep, 1, st);
 }
 

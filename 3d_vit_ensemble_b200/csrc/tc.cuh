@@ -14,7 +14,15 @@ struct TcLinear {
   void* pre = nullptr;           // optional pre-activation copy, same type as y
   int act = 0;
   int M = 0, N = 0, K = 0, prec = 0;
+  // optional LayerNorm of the finished rows fused into the epilogue (BF16 mode, N == 256, fp32 y):
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  void* ln_out = nullptr;        // [M,N] bf16
+  float* ln_mean = nullptr;      // [M] optional
+  float* ln_rstd = nullptr;      // [M] optional
+  float ln_eps = 1e-6f;
 };
+bool tc_linear_ln_supported(int prec, int M, int N, int K);
 
 bool tc_linear_supported(int prec, int M, int N, int K);
 int tc_linear_fwd(const TcLinear& t, cudaStream_t st);

@@ -256,7 +256,8 @@ class LinearFn(torch.autograd.Function):
         M = x2.shape[0]
         yd = torch.float32 if (residual is not None or out_f32) else ad
         y = torch.empty(M, N, device=x.device, dtype=yd)
-        pre = torch.empty(M, N, device=x.device, dtype=yd) if act == ACT_GELU else None
+        # the pre-activation is only needed by the GELU backward: inference (no_grad) does not write it
+        pre = torch.empty(M, N, device=x.device, dtype=yd) if (act == ACT_GELU and any(ctx.needs_input_grad)) else None
         shadow = prec in ("bf16", "tf32")
         w_obj = w
         w_lp = lp_weight(w, prec) if (shadow and w.is_contiguous()) else None
@@ -360,6 +361,67 @@ def mlp_fused(xn, w1, b1, w2, b2, residual):
 
 def linear(x, w, b=None, residual=None, act=ACT_NONE, prec=None, out_f32=False, drop=None):
     return LinearFn.apply(x, w, b, residual, act, prec or get_precision(), out_f32, drop)
+
+
+def linear_ln_supported(x, w, prec) -> bool:
+    """Can `linear_ln` run?  (inference only: BF16 mode, bf16 input, 256 output features)"""
+    if prec != "bf16" or torch.is_grad_enabled() or not x.is_cuda or x.dtype != torch.bfloat16:
+        return False
+    N, K = w.shape
+    return bool(_lib.lib().vit3d_linear_ln_supported(x.numel() // K, N, K))
+
+
+def linear_ln(x, w, b, residual, ln_weight, ln_bias, eps):
+    """Inference-only fused `y = x W^T + b + residual; yn = LayerNorm(y)` (modeling.py:190-194: the residual
+    add followed by the next LayerNorm): one tcgen05 GEMM whose epilogue owns whole rows.  x bf16 (..., K),
+    residual fp32 (..., N).  Returns (y fp32, yn bf16).  No autograd."""
+    _need_cuda(x, w, b, residual, ln_weight, ln_bias)
+    N, K = w.shape
+    x2 = _c(x).reshape(-1, K)
+    M = x2.shape[0]
+    res = _c(residual.float()).reshape(M, N)
+    y = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    yn = torch.empty(M, N, device=x.device, dtype=torch.bfloat16)
+    call("vit3d_linear_ln_fwd", ptr(x2), ptr(lp_weight(w, "bf16")), ptr(None if b is None else _c(b)), ptr(res), ptr(y),
+         ptr(_c(ln_weight)), ptr(_c(ln_bias)), float(eps), ptr(yn), None, None, M, N, K, stream())
+    return y.reshape(residual.shape), yn.reshape(residual.shape)
+
+
+# packed q|k|v weight of an Attention module for inference: built once per weight version instead of a
+# torch.cat + bf16 cast on every forward (training keeps the cat: autograd splits the gradient through it)
+_QKV_CACHE = {}   # id(query.weight) -> (weakref, versions, ptrs, epoch, packed fp32 weight, packed bias, lp shadow)
+
+
+def packed_qkv(attn, prec: str):
+    ws = (attn.query.weight, attn.key.weight, attn.value.weight)
+    bs = (attn.query.bias, attn.key.bias, attn.value.bias)
+    sig = (tuple(t._version for t in ws + bs), tuple(t.data_ptr() for t in ws + bs), _STATE.get("epoch", 0), prec)
+    key = id(ws[0])
+    ent = _QKV_CACHE.get(key)
+    if ent is not None and ent[0]() is ws[0] and ent[1] == sig:
+        return ent[2], ent[3], ent[4]
+    with torch.no_grad():
+        w = torch.cat([t.detach() for t in ws], dim=0).contiguous()
+        b = torch.cat([t.detach() for t in bs], dim=0).contiguous()
+    w_lp = lp_weight(w, prec) if prec in ("bf16", "tf32") else None
+    _QKV_CACHE[key] = (weakref.ref(ws[0], lambda _r, key=key: _QKV_CACHE.pop(key, None)), sig, w, b, w_lp)
+    return w, b, w_lp
+
+
+def linear_packed(x, w, b, w_lp, prec):
+    """Inference-only Linear with a caller-supplied low-precision weight shadow (no autograd)."""
+    _need_cuda(x, w, b)
+    N, K = w.shape
+    lead = x.shape[:-1]
+    ad = act_dtype(prec)
+    if x.dtype != ad:
+        x = x.to(ad)
+    x2 = _c(x).reshape(-1, K)
+    M = x2.shape[0]
+    y = torch.empty(M, N, device=x.device, dtype=ad)
+    call("vit3d_linear_fwd", ptr(x2), K, int(ad == torch.float32), ptr(w), ptr(w_lp), ptr(b), None, ptr(y),
+         int(ad == torch.float32), None, ACT_NONE, M, N, K, PREC[prec], stream())
+    return y.reshape(*lead, N)
 
 
 # ----------------------------------------------------------------------------- attention core

@@ -56,17 +56,28 @@ class Attention(nn.Module):
         self.precision = F.get_precision()
         self._site = 0
 
-    def forward(self, hidden_states, residual=None):
+    def forward(self, hidden_states, residual=None, next_ln=None):
+        """next_ln (inference): the LayerNorm that consumes `residual + out`; when the fused kernel applies it
+        the call returns (out, weights, LN(out)) - otherwise the third item is None."""
         prec = self.precision
-        w = torch.cat((self.query.weight, self.key.weight, self.value.weight), dim=0)
-        b = torch.cat((self.query.bias, self.key.bias, self.value.bias), dim=0)
-        qkv = F.linear(hidden_states, w, b, prec=prec)
+        if torch.is_grad_enabled() or not hidden_states.is_cuda:
+            w = torch.cat((self.query.weight, self.key.weight, self.value.weight), dim=0)
+            b = torch.cat((self.query.bias, self.key.bias, self.value.bias), dim=0)
+            qkv = F.linear(hidden_states, w, b, prec=prec)
+        else:
+            qkv = F.linear_packed(hidden_states, *F.packed_qkv(self, prec), prec)
         ctx, weights = F.AttnCoreFn.apply(qkv, self.num_attention_heads, bool(self.vis), prec)
         p = self.attn_dropout.p
         if p > 0.0 and self.training:
             raise Vit3dError("attention_dropout_rate > 0 is not implemented (the reference config fixes it at 0.0, "
                              "tools.py:93)")
+        if next_ln is not None and residual is not None and F.linear_ln_supported(ctx, self.out.weight, prec):
+            out, normed = F.linear_ln(ctx, self.out.weight, self.out.bias, residual, next_ln.weight, next_ln.bias,
+                                      next_ln.eps)
+            return out, weights, normed
         out = F.linear(ctx, self.out.weight, self.out.bias, residual=residual, prec=prec, out_f32=True)
+        if next_ln is not None:
+            return out, weights, None
         return out, weights
 
 
@@ -91,7 +102,19 @@ class Mlp(nn.Module):
         nn.init.normal_(self.fc1.bias, std=1e-6)
         nn.init.normal_(self.fc2.bias, std=1e-6)
 
-    def forward(self, x, residual=None, step=None):
+    def forward(self, x, residual=None, step=None, next_ln=None):
+        """next_ln (inference): LayerNorm applied to the block output inside the fc2 kernel; the call then
+        returns (out, LN(out) or None)."""
+        if next_ln is not None:
+            prec = self.precision
+            if (not (self.training and self.dropout.p > 0.0) and residual is not None and not self.fused
+                    and not torch.is_grad_enabled()):
+                h = F.linear(x, self.fc1.weight, self.fc1.bias, act=ACT_GELU, prec=prec)
+                if F.linear_ln_supported(h, self.fc2.weight, prec):
+                    return F.linear_ln(h, self.fc2.weight, self.fc2.bias, residual, next_ln.weight, next_ln.bias,
+                                       next_ln.eps)
+                return F.linear(h, self.fc2.weight, self.fc2.bias, residual=residual, prec=prec, out_f32=True), None
+            return self.forward(x, residual=residual, step=step), None
         prec = self.precision
         p = self.dropout.p
         train = self.training and p > 0.0
@@ -161,16 +184,33 @@ class Block(nn.Module):
         self.attn = Attention(config, vis)
         self.precision = F.get_precision()
 
-    def forward(self, x, step=None):
+    def forward(self, x, step=None, normed=None, next_ln=None):
+        """The reference signature is forward(x).  `normed` / `next_ln` are the inference fast path of
+        Encoder.forward: `normed` = attention_norm(x) already produced by the previous block's fc2 kernel,
+        `next_ln` = the LayerNorm that will consume this block's output (the next block's attention_norm);
+        with next_ln the call returns (x, weights, next_ln(x) or None)."""
         prec = self.precision
         x = x.float()
         h = x
         lp = {"bf16": 1, "tf32": 2}.get(prec, 0)     # LayerNorm output feeds a GEMM: bf16 / TF32-rounded / fp32
-        xn = F.LayerNormFn.apply(x, self.attention_norm.weight, self.attention_norm.bias, self.attention_norm.eps, lp)
-        x, weights = self.attn(xn, residual=h)
+        fuse = prec == "bf16" and not torch.is_grad_enabled() and x.is_cuda
+        xn = normed
+        if xn is None:
+            xn = F.LayerNormFn.apply(x, self.attention_norm.weight, self.attention_norm.bias, self.attention_norm.eps, lp)
+        if fuse:
+            x, weights, xn = self.attn(xn, residual=h, next_ln=self.ffn_norm)
+        else:
+            x, weights = self.attn(xn, residual=h)
+            xn = None
         h = x
-        xn = F.LayerNormFn.apply(x, self.ffn_norm.weight, self.ffn_norm.bias, self.ffn_norm.eps, lp)
+        if xn is None:
+            xn = F.LayerNormFn.apply(x, self.ffn_norm.weight, self.ffn_norm.bias, self.ffn_norm.eps, lp)
+        if next_ln is not None and fuse:
+            x, xn_next = self.ffn(xn, residual=h, step=step, next_ln=next_ln)
+            return x, weights, xn_next
         x = self.ffn(xn, residual=h, step=step)
+        if next_ln is not None:
+            return x, weights, None
         return x, weights
 
 
@@ -193,8 +233,17 @@ class Encoder(nn.Module):
         attn_weights = []
         if self.training and step is None:
             step = F.next_dropout_step()
-        for layer_block in self.layer:
-            hidden_states, weights = layer_block(hidden_states, step=step)
+        # inference in BF16 mode: each block's fc2 kernel also applies the NEXT block's attention_norm
+        chain = (self.precision == "bf16" and not torch.is_grad_enabled() and hidden_states.is_cuda)
+        normed = None
+        n_layers = len(self.layer)
+        for i, layer_block in enumerate(self.layer):
+            if chain and i + 1 < n_layers:
+                hidden_states, weights, normed = layer_block(hidden_states, step=step, normed=normed,
+                                                             next_ln=self.layer[i + 1].attention_norm)
+            else:
+                hidden_states, weights = layer_block(hidden_states, step=step, normed=normed)
+                normed = None
             if self.vis:
                 attn_weights.append(weights)
         encoded = F.LayerNormFn.apply(hidden_states, self.encoder_norm.weight, self.encoder_norm.bias,

@@ -52,6 +52,14 @@ const char* vit3d_last_error(void);
 int vit3d_device_info(int* sm_count, int* cc);
 /* number of kernels this library has launched in this process so far */
 unsigned long long vit3d_launch_count(void);
+/* Tuning switches: select between kernel variants at run time (for A/B timing; results are identical).
+ *   VIT3D_TUNE_EPI_DIRECT    1 (default): GEMM epilogue threads write their own accumulator rows with
+ *                            32-byte stores; 0: rows are transposed through shared memory / bulk tensor
+ *                            stores (also used whenever the output is not 32-byte aligned).  Env VIT3D_EPI_DIRECT.
+ *   VIT3D_TUNE_ATTN_THREADS  640 (default) or 512 threads per attention-forward CTA.  Env VIT3D_ATTN_THREADS. */
+enum { VIT3D_TUNE_EPI_DIRECT = 0, VIT3D_TUNE_ATTN_THREADS = 1, VIT3D_TUNE_COUNT = 2 };
+int vit3d_set_tuning(int key, int value);
+int vit3d_get_tuning(int key);
 /* bytes per "act" element for a precision mode */
 int vit3d_act_bytes(int prec);
 /* 1 if the tcgen05 path serves a [M,N,K] linear in this precision, else the fp32 FMA path is used */
@@ -96,6 +104,17 @@ int vit3d_ln_bwd(const float* dy, const float* x, const float* mean, const float
 int vit3d_linear_fwd(const void* x, int ldx, int x_f32, const float* w, const void* w_lp, const float* bias,
                      const float* residual, void* y, int y_f32, void* pre, int act, int M, int N, int K, int prec,
                      vit3d_stream_t stream);
+/* Linear + residual + the LayerNorm that follows it in the Block (modeling.py:189-196: `x = x + h` then
+ * `ffn_norm(x)` / the next Block's `attention_norm(x)` / `encoder_norm(x)`), one kernel, BF16 mode, N == 256:
+ *   y[M,N]      = x[M,K] @ w_lp[N,K]^T + bias + residual        (fp32 residual stream; y may alias residual)
+ *   ln_out[M,N] = (y - mean) * rstd * gamma + beta                (bf16: the A operand of the next GEMM)
+ * mean / rstd [M] optional (saved for vit3d_ln_bwd).  Each thread of the epilogue owns one accumulator row;
+ * the row statistics are combined across the four column slices in shared memory, so the fp32 rows are
+ * never re-read.  Returns VIT3D_ERR_UNSUPPORTED for other shapes (compose vit3d_linear_fwd + vit3d_ln_fwd). */
+int vit3d_linear_ln_fwd(const void* x, const void* w_lp, const float* bias, const float* residual, float* y,
+                        const float* gamma, const float* beta, float eps, void* ln_out, float* mean, float* rstd, int M,
+                        int N, int K, vit3d_stream_t stream);
+int vit3d_linear_ln_supported(int M, int N, int K);
 /* dx[M,K] = dy[M,N] @ w[N,K]  (dx_f32: write fp32);  dw[N,K] += dy^T @ x ; db[N] += colsum(dy).
  * Any of dx / dw / db may be NULL.  dy is "act" typed unless dy_f32.
  *   w_t_lp  bf16 TRANSPOSED copy of w, [K,N] (vit3d_transpose_f32_to_bf16): with it, bf16 dy and BF16 mode

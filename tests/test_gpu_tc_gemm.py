@@ -140,3 +140,62 @@ def test_fused_mlp_matches_fp64(M, d):
     assert np.isfinite(err) and err <= 0.02, err
     rel = float((out.double() - ref).norm() / ref.norm())
     assert rel < 2e-3, rel
+
+
+@pytest.mark.parametrize("shape", [(65, 256, 256), (130, 256, 256), (4161, 256, 256), (1300, 256, 2048), (16640, 256, 3072),
+                                   (19000, 256, 256)])
+@pytest.mark.parametrize("alias", [False, True])
+def test_linear_residual_layernorm_fused(shape, alias):
+    """vit3d_linear_ln_fwd: y = x W^T + b + residual (fp32) and LN(y) (bf16) from one GEMM epilogue, against
+    an fp64 evaluation on the same bf16 operands; mean / rstd outputs; y may alias the residual."""
+    M, N, K = shape
+    torch.manual_seed(M + K)
+    x = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+    w = torch.randn(N, K, device=DEV) / K ** 0.5
+    wl = w.to(torch.bfloat16)
+    b = torch.randn(N, device=DEV) * 0.1
+    res = torch.randn(M, N, device=DEV) * 2.0 + 0.5
+    gamma = 1.0 + 0.1 * torch.randn(N, device=DEV)
+    beta = 0.1 * torch.randn(N, device=DEV)
+    eps = 1e-6
+    res_in = res.clone()
+    y = res_in if alias else torch.full((M, N), float("nan"), device=DEV)
+    yn = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    mean = torch.full((M,), float("nan"), device=DEV)
+    rstd = torch.full((M,), float("nan"), device=DEV)
+    assert lib().vit3d_linear_ln_supported(M, N, K) == 1
+    call("vit3d_linear_ln_fwd", ptr(x), ptr(wl), ptr(b), ptr(res_in), ptr(y), ptr(gamma), ptr(beta), eps, ptr(yn),
+         ptr(mean), ptr(rstd), M, N, K, stream())
+    torch.cuda.synchronize()
+    ref = x.double() @ wl.double().t() + b.double() + res.double()
+    mu = ref.mean(1, keepdim=True)
+    var = ref.var(1, unbiased=False, keepdim=True)
+    ref_n = (ref - mu) / torch.sqrt(var + eps) * gamma.double() + beta.double()
+    e = float((y.double() - ref).abs().max())
+    assert np.isfinite(e) and e <= 2e-5 * K ** 0.5, e
+    assert float((mean.double() - mu[:, 0]).abs().max()) <= 1e-5
+    assert float((rstd.double() * torch.sqrt(var[:, 0] + eps) - 1).abs().max()) <= 1e-4
+    en = float((yn.double() - ref_n).abs().max())
+    assert np.isfinite(en) and en <= float(ref_n.abs().max()) / 128, en      # bf16 output rounding
+    # unsupported shapes are refused, not mis-computed
+    assert lib().vit3d_linear_ln_supported(M, 512, K) == 0
+
+
+@pytest.mark.parametrize("conf", [5, 18])
+def test_inference_ln_chain_matches_unfused(conf, monkeypatch):
+    """The inference fast path (LayerNorm fused into the out-proj / fc2 epilogues, cached packed q|k|v weight)
+    against the operator-by-operator composition the training path uses, same weights, same input."""
+    from oracle import vit3d_oracle as O
+    from vit3d_b200.models.modeling import VisionTransformer
+    cfg = vit3d_b200.north_star_config(conf)
+    m = VisionTransformer(cfg, 128, zero_head=True, num_classes=1, precision="bf16")
+    m.load_state_dict(O.init_state_dict(cfg, seed=7))
+    m.to(DEV).eval()
+    x = O.synth_volumes(6, seed=3).to(DEV)
+    with torch.no_grad():
+        lf, af, ef = m(x)
+    with torch.enable_grad():          # grad mode on -> the unfused composition (nothing requires grad on x)
+        lu, au, eu = m(x)
+    assert float((lf - lu).abs().max()) <= 5e-3
+    assert float((ef - eu).abs().max()) <= 0.05 * float(eu.abs().max())
+    assert len(af) == len(au) and float((af[-1] - au[-1]).abs().max()) <= 2e-2
