@@ -42,7 +42,8 @@ static bool g_tuning_init = false;
 static void tuning_defaults() {
   if (g_tuning_init) return;
   auto env = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
-  g_tuning[VIT3D_TUNE_EPI_DIRECT] = env("VIT3D_EPI_DIRECT", 1);
+  g_tuning[VIT3D_TUNE_EPI_PANEL] = env("VIT3D_EPI_PANEL", 1);
+  g_tuning[VIT3D_TUNE_EPI_LEAN] = env("VIT3D_EPI_LEAN", 1);
   g_tuning[VIT3D_TUNE_ATTN_THREADS] = env("VIT3D_ATTN_THREADS", 640);
   g_tuning_init = true;
 }

@@ -45,7 +45,8 @@ template <int BN> struct TcCfg {
   static constexpr int EPI_WARPS = tc_epi_warps(BN);
   static constexpr int THREADS = tc_threads(BN);
   static constexpr int EPI_BYTES = EPI_WARPS * 2048;   // one 32-row x 64-byte transpose tile per epilogue warp
-  static constexpr int SMEM_BYTES = OPER_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int BIAS_BYTES = BN * 6;            // the n-tile's bias: fp32 copy + packed-half copy
+  static constexpr int SMEM_BYTES = OPER_BYTES + EPI_BYTES + BIAS_BYTES + 256 /*barriers*/;
   static_assert(OPER_BYTES >= TC_SLAB_BYTES + TC_STAT_STAGES * A_BYTES, "operand region too small for the stationary schedule");
 };
 
@@ -82,19 +83,21 @@ struct TileIter {
   }
 };
 
-// LNF: the fused-LayerNorm instantiation (bf16 operands, BN = N = 256, direct fp32 epilogue) is a separate
-// kernel so that its 64 live row values do not set the register budget of every other GEMM.
-template <bool TF32, int BN, bool LNF = false>
-__global__ void __launch_bounds__(tc_threads(BN)) __maxnreg__(BN >= 128 ? 112 : 168)
+// EPI: EPI_GENERIC (run-time epilogue flags) or the compile-time mode of epilogue_bf16_lean.
+// 18 warps = 5 on one scheduler: 16384 / (5 * 32) -> at most 96 registers per thread (ptxas derives this).
+template <bool TF32, int BN, int EPI = EPI_GENERIC>
+__global__ void __launch_bounds__(tc_threads(BN), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmPre, TcEpilogue ep, int M,
                int N, int K, int tiles_m, int tiles_n, int splits, int stationary, int patch_blocks, int mn_major) {
   using Cfg = TcCfg<BN>;
   constexpr int BLOCK_K = TF32 ? 32 : 64;   // 128 bytes of K per stage row
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;                    // 128B-swizzled operand tiles need 1024-byte alignment
+  if (smem_u32(smem) & 1023u) __trap();
   uint8_t* epi_stage = smem + Cfg::OPER_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + Cfg::EPI_BYTES);
+  uint8_t* bias_stage = epi_stage + Cfg::EPI_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_stage + Cfg::BIAS_BYTES);
   constexpr int MAXST = 8;
   uint64_t* full_bar = bars;                 // [MAXST]
   uint64_t* empty_bar = bars + MAXST;        // [MAXST]
@@ -224,19 +227,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t stage = smem_u32(epi_stage + (warp - 2) * 2048);
     TileIter ti(stat, tiles_m, tiles_n, splits);
     int it = 0;
+    int cur_tn = -1;
     for (; ti.next(); ++it) {
       const int buf = it & 1;
+      if constexpr (EPI >= 0 && (EPI & 1) != 0) {
+        if (ti.tn != cur_tn) {
+          // stage this n-tile's bias (fp32 + packed half) for all epilogue warps; once per CTA under the
+          // stationary schedule.  First barrier: everyone is done reading the previous n-tile's copy.
+          constexpr int ETH = Cfg::EPI_WARPS * 32;
+          asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");
+          const int t = (int)threadIdx.x - 64;
+          if (t < BN / 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + ti.tn * BN + 4 * t));
+            *reinterpret_cast<float4*>(bias_stage + 16 * t) = b;
+            const __half2 h0 = __floats2half2_rn(b.x, b.y), h1 = __floats2half2_rn(b.z, b.w);
+            *reinterpret_cast<uint2*>(bias_stage + BN * 4 + 8 * t) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");
+          cur_tn = ti.tn;
+        }
+      }
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + part * CW;
       const int m_base = ti.tm * TC_BLOCK_M + q * 32, n_base = ti.tn * BN + part * CW;
-      if constexpr (LNF) {
-        // the (unused) staging region holds the two 4 KB row-statistics scratch buffers
-        float2* scratch = reinterpret_cast<float2*>(epi_stage) + (it & 1) * (Cfg::EPI_WARPS * 32);
-        epilogue_direct_f32<CW, Cfg::EPI_WARPS / 4, true, false>(ep, taddr, lane, m_base, n_base, M, N, scratch, part, q);
-      } else if (ep.direct) {
-        if (ep.out_f32) epilogue_direct_f32<CW, Cfg::EPI_WARPS / 4, false, TF32>(ep, taddr, lane, m_base, n_base, M, N, nullptr, part, q);
-        else epilogue_direct_bf16<CW, !TF32>(ep, taddr, lane, m_base, n_base, M, N);
+      if constexpr (EPI >= 0) {
+        epilogue_bf16_lean<CW, EPI>(&tmC, &tmPre, taddr, stage, smem_u32(bias_stage) + part * CW * 4,
+                                    smem_u32(bias_stage) + BN * 4 + part * CW * 2, lane, m_base, n_base);
       } else {
         epilogue_rows<CW, !TF32>(ep, &tmC, &tmPre, taddr, stage, lane, m_base, n_base, M, N);
       }
@@ -303,12 +321,12 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long ro
   return VIT3D_OK;
 }
 
-template <bool TF32, int BN, bool LNF = false>
+template <bool TF32, int BN, int EPI = EPI_GENERIC>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
                      const TcEpilogue& ep, int M, int N, int K, int splits, bool stationary, cudaStream_t st,
                      int patch_blocks = 0, int mn_major = 0) {
   using Cfg = TcCfg<BN>;
-  auto kern = tc_gemm_kernel<TF32, BN, LNF>;
+  auto kern = tc_gemm_kernel<TF32, BN, EPI>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   V3_CUDA(cudaGetDevice(&dev));
@@ -332,26 +350,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 }
 
 // D[M,N] = A[M,K] B[N,K]^T with both operands dense row-major K-major; elem = 2 (bf16) or 4 (tf32)
-static bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
-// VIT3D_EPI_DIRECT=0 selects the staged (shared-memory transpose / bulk tensor store) epilogue for A/B timing
-static bool direct_enabled() { return tuning(VIT3D_TUNE_EPI_DIRECT) != 0; }
-
-int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const TcEpilogue& ep_in, int splits,
+int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const TcEpilogue& ep, int splits,
             cudaStream_t st) {
-  TcEpilogue ep = ep_in;
-  // row-owner epilogue whenever the output rows can take aligned 32-byte stores
-  ep.direct = 0;
-  if (direct_enabled() && !ep.atomic && ep.row_group == 0 && !ep.rowadd && aligned32(ep.out) && aligned32(ep.pre) &&
-      aligned32(ep.residual) && (ep.out_f32 ? N % 8 == 0 : N % 16 == 0))
-    ep.direct = 1;
-  if (!tf32 && ep.out_f32 && ep.act == VIT3D_ACT_GELU) ep.direct = 0;   // fp32 GELU output from bf16 operands: staged path
-  const bool lnf = ep.ln_out != nullptr;
-  if (lnf) {
-    if (tf32 || N != 256 || !ep.out_f32 || !ep.direct || splits != 1 || !aligned32(ep.ln_out) || !ep.ln_gamma || !ep.ln_beta) {
-      set_error("tc_gemm: fused LayerNorm needs bf16 operands, N == 256, fp32 32-byte aligned output");
-      return VIT3D_ERR_UNSUPPORTED;
-    }
-  }
   const int eb = tf32 ? 4 : 2;
   const int sms = sm_count();
   const int tm = ceil_div(M, TC_BLOCK_M);
@@ -360,7 +360,6 @@ int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const 
   int bn = 256;
   if (N <= 64 || (long long)tm * ceil_div(N, 256) * splits < sms) bn = 128;
   if (N <= 64 || (bn == 128 && (long long)tm * ceil_div(N, 128) * splits < sms)) bn = 64;
-  if (lnf) bn = 256;                    // a CTA must own whole rows
   // stationary-B schedule when the [bn x K] weight slab fits (shrink the tile once if that makes it fit)
   auto fits = [&](int b) { return splits == 1 && (long long)nkb * b * 128 <= TC_SLAB_BYTES && ceil_div(N, b) <= sms; };
   bool stationary = fits(bn);
@@ -372,7 +371,7 @@ int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const 
   if (rc != VIT3D_OK) return rc;
   tc = ta;
   tp = ta;
-  if (!ep.out_f32 && !ep.direct) {   // staged bf16 outputs leave through bulk tensor stores
+  if (!ep.out_f32) {   // bf16 outputs leave through bulk tensor stores
     if (ep.row_group > 0 || ep.atomic) { set_error("tc_gemm: bf16 output with row remap / atomics is not supported"); return VIT3D_ERR_INVALID; }
     rc = make_tmap_2d(&tc, ep.out, 2, M, N, N, 32, 32, 64);
     if (rc != VIT3D_OK) return rc;
@@ -386,7 +385,16 @@ int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const 
     if (bn == 128) return launch_tc<true, 128>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
     return launch_tc<true, 64>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
   }
-  if (lnf) return launch_tc<false, 256, true>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
+  // compile-time specialised epilogue for the hot bf16-output products (full column tiles)
+  if (!ep.out_f32 && bn >= 128 && N % bn == 0 && tuning(VIT3D_TUNE_EPI_LEAN) != 0 &&
+      (!ep.pre || ep.act == VIT3D_ACT_GELU) && (ep.act == VIT3D_ACT_NONE || ep.bias)) {
+    const int mode = (ep.bias ? 1 : 0) | (ep.act == VIT3D_ACT_GELU ? 2 : 0) | (ep.pre ? 4 : 0);
+#define V3_LEAN(BN_, MODE_) \
+  if (bn == BN_ && mode == MODE_) return launch_tc<false, BN_, MODE_>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
+    V3_LEAN(256, 0) V3_LEAN(256, 1) V3_LEAN(256, 3) V3_LEAN(256, 7)
+    V3_LEAN(128, 0) V3_LEAN(128, 1) V3_LEAN(128, 3) V3_LEAN(128, 7)
+#undef V3_LEAN
+  }
   if (bn == 256) return launch_tc<false, 256>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
   if (bn == 128) return launch_tc<false, 128>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
   return launch_tc<false, 64>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
@@ -435,17 +443,22 @@ bool tc_linear_supported(int prec, int M, int N, int K) {
   return false;
 }
 
-// fused Linear + residual + LayerNorm: a CTA's 128 x 256 tile must span whole rows
+// fused Linear + residual + LayerNorm (k_tc_gemm_res.cu): a CTA's 128 x 256 tile must span whole rows
 bool tc_linear_ln_supported(int prec, int M, int N, int K) {
-  return prec == VIT3D_PREC_BF16 && N == 256 && tc_linear_supported(prec, M, N, K) && direct_enabled();
+  return prec == VIT3D_PREC_BF16 && tc_res_supported(M, N, K, true);
 }
 
 int tc_linear_fwd(const TcLinear& t, cudaStream_t st) {
+  // fp32 residual-stream outputs (out-projection, fc2, fp32 data gradients): TMA panel epilogue
+  const bool aligned = ((reinterpret_cast<uintptr_t>(t.y) | reinterpret_cast<uintptr_t>(t.residual) |
+                         reinterpret_cast<uintptr_t>(t.ln_out)) & 15) == 0;
+  if (t.prec == VIT3D_PREC_BF16 && t.y_f32 && t.act == VIT3D_ACT_NONE && !t.pre && aligned &&
+      tc_res_supported(t.M, t.N, t.K, t.ln_out != nullptr) && (t.ln_out || tuning(VIT3D_TUNE_EPI_PANEL) != 0))
+    return tc_gemm_res(t, st);
+  if (t.ln_out) V3_UNSUPPORTED("linear + LayerNorm: unsupported shape / alignment (M=%d N=%d K=%d)", t.M, t.N, t.K);
   TcEpilogue ep;
   ep.bias = t.bias; ep.residual = t.residual; ep.out = t.y; ep.pre = t.pre; ep.out_f32 = t.y_f32; ep.act = t.act;
   ep.round_tf32 = (t.prec == VIT3D_PREC_TF32 && t.act == VIT3D_ACT_GELU && !t.residual) ? 1 : 0;
-  ep.ln_gamma = t.ln_gamma; ep.ln_beta = t.ln_beta; ep.ln_out = t.ln_out; ep.ln_mean = t.ln_mean; ep.ln_rstd = t.ln_rstd;
-  ep.ln_eps = t.ln_eps;
   return tc_gemm(t.prec == VIT3D_PREC_TF32, t.x, t.w, t.M, t.N, t.K, ep, 1, st);
 }
 

@@ -23,6 +23,9 @@ struct TcLinear {
   float ln_eps = 1e-6f;
 };
 bool tc_linear_ln_supported(int prec, int M, int N, int K);
+// k_tc_gemm_res.cu: fp32 output (+ bias, + residual, + fused LayerNorm) through TMA panels; N % 256 == 0
+bool tc_res_supported(int M, int N, int K, bool ln);
+int tc_gemm_res(const TcLinear& t, cudaStream_t st);
 
 bool tc_linear_supported(int prec, int M, int N, int K);
 int tc_linear_fwd(const TcLinear& t, cudaStream_t st);

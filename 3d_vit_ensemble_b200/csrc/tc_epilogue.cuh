@@ -23,14 +23,6 @@ struct TcEpilogue {
   int atomic = 0;                   // accumulate with fp32 atomics (split-K)
   int vols_per_tile = 0;            // patch-embedding mode: volumes per 128-row tile
   int round_tf32 = 0;               // fp32 output is the operand of a TF32 GEMM: round to nearest tf32
-  int direct = 0;                   // row-owner epilogue: 32-byte global stores straight from the accumulator rows
-  // LayerNorm of the finished rows fused into the epilogue (direct fp32 output, N == tile width):
-  const float* ln_gamma = nullptr;  // [N]
-  const float* ln_beta = nullptr;   // [N]
-  void* ln_out = nullptr;           // [M,N] bf16: LN(out) - the A operand of the next GEMM
-  float* ln_mean = nullptr;         // [M] saved for backward (optional)
-  float* ln_rstd = nullptr;         // [M]
-  float ln_eps = 1e-6f;
 };
 
 
@@ -235,185 +227,94 @@ __device__ __forceinline__ void epilogue_rows(const TcEpilogue& ep, const CUtens
 }
 
 
-// ----------------------------------------------------------------------------- row-owner ("direct") epilogue
-// tcgen05.ld 32x32b hands every thread one accumulator ROW.  Instead of transposing through shared memory
-// the thread applies bias / GELU / residual to its own row and writes it with 32-byte global stores
-// (STG.256: one full sector per lane; a warp instruction covers 32 rows).  No staging tile, no proxy fence,
-// no wait on a previous bulk store: successive column groups of a row are independent instruction streams.
-__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&w)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
-               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
-               : "memory");
-}
-__device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&w)[8]) {
-  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
-               : "l"(p)
-               : "memory");
+// ----------------------------------------------------------------------------- lean bf16 epilogue
+// The hot bf16-output GEMMs (qkv, fc1 + GELU, the data-gradient products) are bound by the instruction
+// issue rate of their epilogue warps, not by the tensor pipe: at K = 256 a 128 x 256 tile is 2048 MMA
+// cycles, i.e. each scheduler has 2048 issue slots for 8192 output elements x (4 warps).  This variant is
+// specialised at compile time (no run-time flags, no column predicates: N % BN == 0; rows >= M are clipped
+// by the bulk tensor store), reads the bias from shared memory (staged once per n-tile by the CTA; fp32
+// and packed-half copies) instead of the global loads + scoreboard waits of the generic path, and with
+// GELU and no pre-activation output adds the bias in packed half precision after the conversion.
+//   MODE bit 0: bias, bit 1: GELU, bit 2: also store the pre-activation (training)
+constexpr int EPI_GENERIC = -1;
+__device__ __forceinline__ uint32_t gelu_pair_bf16_h2(__half2 x) {
+  const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(100.f));
+  __half2 p = __hfma2(x2, __float2half2_rn(-3.58732362e-4f), __float2half2_rn(0.0370503451f));
+  p = __hfma2(x2, p, __float2half2_rn(0.797458471f));
+  const __half2 u = __hmul2(x, p);
+  uint32_t ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
+  const __half2 th = *reinterpret_cast<const __half2*>(&ti);
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  const float2 f = __half22float2(__hfma2(hx, th, hx));
+  return pack2_bf16(f.x, f.y);
 }
 
-// bf16 output.  Requires N % 16 == 0 and 32-byte aligned out / pre (checked on the host).
-template <int CW, bool FAST_GELU>
-__device__ __forceinline__ void epilogue_direct_bf16(const TcEpilogue& ep, uint32_t taddr, int lane, int m_base, int n_base,
-                                                     int M, int N) {
-  const int m = m_base + lane;
-  const bool rowok = m < M;
-  __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)m * N + n_base;
-  __nv_bfloat16* prow = ep.pre ? reinterpret_cast<__nv_bfloat16*>(ep.pre) + (long long)m * N + n_base : nullptr;
-  const bool gelu = ep.act == VIT3D_ACT_GELU;
-#pragma unroll 1
+template <int CW, int MODE>
+__device__ __forceinline__ void epilogue_bf16_lean(const CUtensorMap* tmC, const CUtensorMap* tmPre, uint32_t taddr,
+                                                   uint32_t stage, uint32_t bias_f32, uint32_t bias_h2, int lane,
+                                                   int m_base, int n_base) {
+  constexpr bool BIAS = (MODE & 1) != 0, GELU = (MODE & 2) != 0, PRE = (MODE & 4) != 0;
+  const uint32_t my_row = stage + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
   for (int c = 0; c < CW; c += 32) {
-    if (n_base + c >= N) break;
     uint32_t r[32];
     tmem_ld_32x32b_x32(taddr + c, r);
     tmem_ld_wait();
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {                    // 16 columns = one 32-byte store
-      if (n_base + c + 16 * h < N) {
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[16 * h + j]);
-        if (ep.bias) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n_base + c + 16 * h + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
-        }
-        uint32_t w[8];
-        if (prow) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) w[j] = pack2_bf16(v[2 * j], v[2 * j + 1]);
-          if (rowok) st_global_v8(prow + c + 16 * h, w);
-        }
-        if (gelu) {
-          if (FAST_GELU) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) w[j] = gelu_pair_bf16(v[2 * j], v[2 * j + 1]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) w[j] = pack2_bf16(gelu_f(v[2 * j]), gelu_f(v[2 * j + 1]));
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) w[j] = pack2_bf16(v[2 * j], v[2 * j + 1]);
-        }
-        if (rowok) st_global_v8(orow + c + 16 * h, w);
-      }
-    }
-  }
-}
-
-// fp32 output (+ residual, + optional fused LayerNorm of the finished rows).  Requires N % 8 == 0, 32-byte
-// aligned out / residual / pre, no row remap, no atomics.  `out` may alias `residual` (each thread reads the
-// 32 bytes it is about to overwrite).
-//
-// Fused LayerNorm (ep.ln_out): the CTA's tile spans whole rows (N == BN), a row's columns are split over
-// NPART warps (same TMEM lane quarter, different column slices).  Every thread keeps its CW finished values
-// in registers, the NPART partial (sum, sum of squares) pairs of a row meet in shared memory (`ln_scratch`,
-// one float2 per (part, row)), and after a named barrier over those NPART warps each thread normalises its
-// own slice and writes it as bf16 - the separate LayerNorm kernel (one more read of the fp32 rows) is gone.
-template <int CW, int NPART, bool LN, bool GELU_OK>
-__device__ __forceinline__ void epilogue_direct_f32(const TcEpilogue& ep, uint32_t taddr, int lane, int m_base, int n_base,
-                                                    int M, int N, float2* ln_scratch, int part, int q) {
-  constexpr int CH = 16;                // columns per TMEM read (16 accumulators + 16 residual values in flight)
-  const int m = m_base + lane;
-  const bool rowok = m < M;
-  float* orow = reinterpret_cast<float*>(ep.out) + (long long)m * N + n_base;
-  float* prow = ep.pre ? reinterpret_cast<float*>(ep.pre) + (long long)m * N + n_base : nullptr;
-  const float* rrow = ep.residual ? ep.residual + (long long)m * N + n_base : nullptr;
-  const bool gelu = GELU_OK && ep.act == VIT3D_ACT_GELU;   // fp32 GELU outputs only exist in TF32 mode
-  float keep[LN ? CW : 1];              // finished values of this thread's slice
-  float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-  for (int c = 0; c < CW; c += CH) {
-    if (n_base + c < N) {
-      uint32_t r[CH];
-      tmem_ld_32x32b_x16(taddr + c, r);
-      uint32_t res[CH / 8][8];
-#pragma unroll
-      for (int g = 0; g < CH / 8; ++g) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) res[g][j] = 0u;
-        if (rrow && rowok && n_base + c + 8 * g < N) ld_global_v8(rrow + c + 8 * g, res[g]);
-      }
-      tmem_ld_wait();
-#pragma unroll
-      for (int g = 0; g < CH / 8; ++g) {             // 8 columns = one 32-byte store
-        if (n_base + c + 8 * g < N) {
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * g + j]);
-          if (ep.bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n_base + c + 8 * g));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n_base + c + 8 * g + 4));
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-          }
-          uint32_t w[8];
-          if (prow) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) w[j] = __float_as_uint(v[j]);
-            if (rowok) st_global_v8(prow + c + 8 * g, w);
-          }
-          if constexpr (GELU_OK) {
-            if (gelu) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = gelu_f(v[j]);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += __uint_as_float(res[g][j]);
-          if (ep.round_tf32) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = round_tf32(v[j]);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) w[j] = __float_as_uint(v[j]);
-          if (rowok) st_global_v8(orow + c + 8 * g, w);
-          if constexpr (LN) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { keep[c + 8 * g + j] = v[j]; s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
-          }
-        }
-      }
-    }
-  }
-  if constexpr (LN) {
-    // partial statistics of the NPART column slices of row (q*32 + lane) meet in shared memory; the caller
-    // alternates between two scratch buffers tile by tile, so one barrier per tile is enough
-    ln_scratch[(part * 4 + q) * 32 + lane] = make_float2(s1, s2);
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(NPART * 32) : "memory");
-    float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-    for (int p = 0; p < NPART; ++p) {
-      const float2 s = ln_scratch[(p * 4 + q) * 32 + lane];
-      t1 += s.x; t2 += s.y;
-    }
-    const float inv_n = 1.0f / (float)N;
-    const float mean = t1 * inv_n;
-    const float var = fmaxf(t2 * inv_n - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + ep.ln_eps);
-    if (part == 0 && rowok) {
-      if (ep.ln_mean) ep.ln_mean[m] = mean;
-      if (ep.ln_rstd) ep.ln_rstd[m] = rstd;
-    }
-    __nv_bfloat16* lrow = reinterpret_cast<__nv_bfloat16*>(ep.ln_out) + (long long)m * N + n_base;
-#pragma unroll
-    for (int c = 0; c < CW; c += 16) {
-      uint32_t w[8];
+    uint32_t w[16];
+    if constexpr (GELU && !PRE) {
+      // packed-half path: convert, add the half bias, GELU, repack as bf16
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
-        const float4 ga = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + n_base + c + j));
-        const float4 be = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + n_base + c + j));
-        const float y0 = fmaf((keep[c + j] - mean) * rstd, ga.x, be.x);
-        const float y1 = fmaf((keep[c + j + 1] - mean) * rstd, ga.y, be.y);
-        const float y2 = fmaf((keep[c + j + 2] - mean) * rstd, ga.z, be.z);
-        const float y3 = fmaf((keep[c + j + 3] - mean) * rstd, ga.w, be.w);
-        w[j / 2] = pack2_bf16(y0, y1);
-        w[j / 2 + 1] = pack2_bf16(y2, y3);
+        uint4 b = make_uint4(0u, 0u, 0u, 0u);
+        if constexpr (BIAS) b = ld_shared_v4(bias_h2 + (c + 2 * j) * 2);
+        const uint32_t bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __half2 x = __floats2half2_rn(__uint_as_float(r[2 * (j + i)]), __uint_as_float(r[2 * (j + i) + 1]));
+          if constexpr (BIAS) x = __hadd2(x, *reinterpret_cast<const __half2*>(&bb[i]));
+          w[j + i] = gelu_pair_bf16_h2(x);
+        }
       }
-      if (rowok) st_global_v8(lrow + c, w);
+    } else {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if constexpr (BIAS) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const uint4 b = ld_shared_v4(bias_f32 + (c + j) * 4);
+          v[j] += __uint_as_float(b.x); v[j + 1] += __uint_as_float(b.y);
+          v[j + 2] += __uint_as_float(b.z); v[j + 3] += __uint_as_float(b.w);
+        }
+      }
+      if constexpr (PRE) {
+        if (lane == 0) bulk_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_shared_v4(my_row + ((j ^ sw) << 4), pack2_bf16(v[8 * j], v[8 * j + 1]), pack2_bf16(v[8 * j + 2], v[8 * j + 3]),
+                       pack2_bf16(v[8 * j + 4], v[8 * j + 5]), pack2_bf16(v[8 * j + 6], v[8 * j + 7]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tmPre, stage, n_base + c, m_base);
+          bulk_store_commit();
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w[j] = GELU ? gelu_pair_bf16(v[2 * j], v[2 * j + 1]) : pack2_bf16(v[2 * j], v[2 * j + 1]);
+    }
+    if (lane == 0) bulk_store_wait_read();      // the previous store has finished reading the staging tile
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st_shared_v4(my_row + ((j ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmC, stage, n_base + c, m_base);
+      bulk_store_commit();
     }
   }
 }

@@ -52,12 +52,15 @@ const char* vit3d_last_error(void);
 int vit3d_device_info(int* sm_count, int* cc);
 /* number of kernels this library has launched in this process so far */
 unsigned long long vit3d_launch_count(void);
-/* Tuning switches: select between kernel variants at run time (for A/B timing; results are identical).
- *   VIT3D_TUNE_EPI_DIRECT    1 (default): GEMM epilogue threads write their own accumulator rows with
- *                            32-byte stores; 0: rows are transposed through shared memory / bulk tensor
- *                            stores (also used whenever the output is not 32-byte aligned).  Env VIT3D_EPI_DIRECT.
- *   VIT3D_TUNE_ATTN_THREADS  640 (default) or 512 threads per attention-forward CTA.  Env VIT3D_ATTN_THREADS. */
-enum { VIT3D_TUNE_EPI_DIRECT = 0, VIT3D_TUNE_ATTN_THREADS = 1, VIT3D_TUNE_COUNT = 2 };
+/* Tuning switches: select between kernel variants at run time (for A/B timing; results agree to rounding).
+ *   VIT3D_TUNE_EPI_PANEL     1 (default): fp32-output GEMMs with N % 256 == 0 (out-projection, fc2, fp32 data
+ *                            gradients) run the TMA-panel kernel (residual fetched and result stored by bulk
+ *                            tensor copies); 0: the generic epilogue.  Env VIT3D_EPI_PANEL.
+ *   VIT3D_TUNE_ATTN_THREADS  640 (default) or 512 threads per attention-forward CTA.  Env VIT3D_ATTN_THREADS.
+ *   VIT3D_TUNE_EPI_LEAN      1 (default): compile-time specialised epilogue (bias from shared memory, packed
+ *                            half GELU) for bf16-output GEMMs with full column tiles; 0: generic epilogue.
+ *                            Env VIT3D_EPI_LEAN. */
+enum { VIT3D_TUNE_EPI_PANEL = 0, VIT3D_TUNE_ATTN_THREADS = 1, VIT3D_TUNE_EPI_LEAN = 2, VIT3D_TUNE_COUNT = 3 };
 int vit3d_set_tuning(int key, int value);
 int vit3d_get_tuning(int key);
 /* bytes per "act" element for a precision mode */

@@ -83,19 +83,21 @@ yn = torch.empty(M, H, device=dev, dtype=bf)
 mean = torch.empty(M, device=dev)
 rstd = torch.empty(M, device=dev)
 
-for direct in (0, 1):
-    L.vit3d_set_tuning(0, direct)
-    tag = f"[direct={direct}]"
+for lean in (0, 1):
+    L.vit3d_set_tuning(2, lean)
+    tag = f"[lean={lean}]"
     report(f"qkv GEMM {tag}", timeit(lambda: linear(xn, w_qkv, wl_qkv, b_qkv, None, qkv, None, 0, 3 * H, H)),
            2.0 * M * 3 * H * H, M * H * 2 + M * 3 * H * 2)
-    report(f"out-proj GEMM + residual {tag}", timeit(lambda: linear(ctx, w_o, wl_o, b_o, x32, y32, None, 0, H, H)),
-           2.0 * M * H * H, M * H * 2 + 2 * M * H * 4)
     report(f"fc1 GEMM + GELU {tag}", timeit(lambda: linear(xn, w1, wl1, b1, None, h, None, 1, d, H)),
-           2.0 * M * d * H, M * H * 2 + M * d * 2)
-    report(f"fc1 GEMM no act {tag}", timeit(lambda: linear(xn, w1, wl1, b1, None, h, None, 0, d, H)),
            2.0 * M * d * H, M * H * 2 + M * d * 2)
     report(f"fc1 GEMM + GELU + pre (training) {tag}", timeit(lambda: linear(xn, w1, wl1, b1, None, h, pre, 1, d, H)),
            2.0 * M * d * H, M * H * 2 + 2 * M * d * 2)
+L.vit3d_set_tuning(2, 1)
+for panel in (0, 1):
+    L.vit3d_set_tuning(0, panel)
+    tag = f"[panel={panel}]"
+    report(f"out-proj GEMM + residual {tag}", timeit(lambda: linear(ctx, w_o, wl_o, b_o, x32, y32, None, 0, H, H)),
+           2.0 * M * H * H, M * H * 2 + 2 * M * H * 4)
     report(f"fc2 GEMM + residual {tag}", timeit(lambda: linear(h, w2, wl2, b2, x32, y32, None, 0, H, d)),
            2.0 * M * d * H, M * d * 2 + 2 * M * H * 4)
 L.vit3d_set_tuning(0, 1)
