@@ -58,6 +58,8 @@ SIGNATURES = {
     "vit3d_linear_bwd": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _p]),
     "vit3d_mlp_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "vit3d_mlp_supported": (_i, [_i, _i, _i]),
+    "vit3d_mlp_ln_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _i, _i, _i, _p]),
+    "vit3d_mlp_ln_supported": (_i, [_i, _i, _i]),
     "vit3d_attn_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "vit3d_attn_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "vit3d_gelu_fwd": (_i, [_p, _p, _ll, _i, _p]),

@@ -44,6 +44,10 @@ static void tuning_defaults() {
   auto env = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
   g_tuning[VIT3D_TUNE_EPI_PANEL] = env("VIT3D_EPI_PANEL", 1);
   g_tuning[VIT3D_TUNE_EPI_LEAN] = env("VIT3D_EPI_LEAN", 1);
+  g_tuning[VIT3D_TUNE_STORE_WIDE] = env("VIT3D_STORE_WIDE", 0);
+  g_tuning[VIT3D_TUNE_L2_AHEAD] = env("VIT3D_L2_AHEAD", 0);
+  g_tuning[VIT3D_TUNE_MLP_V2] = env("VIT3D_MLP_V2", 1);
+  g_tuning[VIT3D_TUNE_MLP_PAIR] = env("VIT3D_MLP_PAIR", 1);
   g_tuning[VIT3D_TUNE_ATTN_THREADS] = env("VIT3D_ATTN_THREADS", 640);
   g_tuning_init = true;
 }
@@ -284,13 +288,25 @@ int vit3d_linear_bwd(const void* dy, int dy_f32, const void* x, int ldx, int x_f
 }
 
 // ------------------------------------------------------------------------- fused MLP
-int vit3d_mlp_supported(int M, int H, int d) { return tc_mlp_supported(M, H, d) ? 1 : 0; }
 int vit3d_mlp_fwd(const void* xn, const void* w1_lp, const float* b1, const void* w2_lp, const float* b2,
                   const float* residual, float* out, int M, int H, int d, vit3d_stream_t stream) {
   V3_REQUIRE(xn && w1_lp && b1 && w2_lp && b2 && residual && out, "mlp_fwd: null pointer");
   V3_REQUIRE(M >= 0 && H > 0 && d > 0, "mlp_fwd: bad shape");
   if (M == 0) return VIT3D_OK;
+  if (tuning(VIT3D_TUNE_MLP_V2) != 0 && tc_mlp2_supported(M, H, d))
+    return tc_mlp2_fwd(xn, w1_lp, b1, w2_lp, b2, residual, out, nullptr, nullptr, 0.f, nullptr, M, H, d, as_stream(stream));
   return tc_mlp_fwd(xn, w1_lp, b1, w2_lp, b2, residual, out, M, H, d, as_stream(stream));
+}
+int vit3d_mlp_supported(int M, int H, int d) { return (tc_mlp_supported(M, H, d) || tc_mlp2_supported(M, H, d)) ? 1 : 0; }
+
+int vit3d_mlp_ln_supported(int M, int H, int d) { return tc_mlp2_supported(M, H, d) ? 1 : 0; }
+int vit3d_mlp_ln_fwd(const void* xn, const void* w1_lp, const float* b1, const void* w2_h, const float* b2,
+                     const float* residual, float* out, const float* gamma, const float* beta, float eps, void* ln_out,
+                     int M, int H, int d, vit3d_stream_t stream) {
+  V3_REQUIRE(xn && w1_lp && b1 && w2_h && b2 && residual && out && gamma && beta && ln_out, "mlp_ln_fwd: null pointer");
+  V3_REQUIRE(M >= 0 && H > 0 && d > 0, "mlp_ln_fwd: bad shape");
+  if (M == 0) return VIT3D_OK;
+  return tc_mlp2_fwd(xn, w1_lp, b1, w2_h, b2, residual, out, gamma, beta, eps, ln_out, M, H, d, as_stream(stream));
 }
 
 // ------------------------------------------------------------------------- attention core

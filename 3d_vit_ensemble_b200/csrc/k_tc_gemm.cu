@@ -85,18 +85,33 @@ struct TileIter {
 
 // EPI: EPI_GENERIC (run-time epilogue flags) or the compile-time mode of epilogue_bf16_lean.
 // 18 warps = 5 on one scheduler: 16384 / (5 * 32) -> at most 96 registers per thread (ptxas derives this).
-template <bool TF32, int BN, int EPI = EPI_GENERIC>
+// WIDE (lean bf16 epilogue, BN = 256): 4 KB staging panel per epilogue warp (128-byte output rows); the
+// operand region shrinks to slab + 2 A stages (stationary) or 3 stages (streaming) to make room.
+template <int BN, bool WIDE> struct TcLayout {
+  using Cfg = TcCfg<BN>;
+  static constexpr int STAT_STAGES = WIDE ? 2 : TC_STAT_STAGES;
+  static constexpr int STREAM_STAGES = WIDE ? 3 : Cfg::STAGES;
+  static constexpr int OPER_BYTES = WIDE ? TC_SLAB_BYTES + 2 * Cfg::A_BYTES : Cfg::OPER_BYTES;
+  static constexpr int EPI_WARP_BYTES = WIDE ? 4096 : 2048;
+  static constexpr int EPI_BYTES = Cfg::EPI_WARPS * EPI_WARP_BYTES;
+  static constexpr int SMEM_BYTES = OPER_BYTES + EPI_BYTES + Cfg::BIAS_BYTES + 256 /*barriers*/;
+  static_assert(!WIDE || STREAM_STAGES * Cfg::STAGE_BYTES <= OPER_BYTES, "streaming ring does not fit");
+  static_assert(SMEM_BYTES <= 232448, "over the 227 KB shared-memory limit");
+};
+
+template <bool TF32, int BN, int EPI = EPI_GENERIC, bool WIDE = false>
 __global__ void __launch_bounds__(tc_threads(BN), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmPre, TcEpilogue ep, int M,
                int N, int K, int tiles_m, int tiles_n, int splits, int stationary, int patch_blocks, int mn_major) {
   using Cfg = TcCfg<BN>;
+  using Lay = TcLayout<BN, WIDE>;
   constexpr int BLOCK_K = TF32 ? 32 : 64;   // 128 bytes of K per stage row
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;                    // 128B-swizzled operand tiles need 1024-byte alignment
   if (smem_u32(smem) & 1023u) __trap();
-  uint8_t* epi_stage = smem + Cfg::OPER_BYTES;
-  uint8_t* bias_stage = epi_stage + Cfg::EPI_BYTES;
+  uint8_t* epi_stage = smem + Lay::OPER_BYTES;
+  uint8_t* bias_stage = epi_stage + Lay::EPI_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_stage + Cfg::BIAS_BYTES);
   constexpr int MAXST = 8;
   uint64_t* full_bar = bars;                 // [MAXST]
@@ -107,7 +122,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAXST + 5);
 
   const bool stat = stationary != 0;
-  const int STAGES = stat ? TC_STAT_STAGES : Cfg::STAGES;
+  const int STAGES = stat ? Lay::STAT_STAGES : Lay::STREAM_STAGES;
   const int stage_bytes = stat ? Cfg::A_BYTES : Cfg::STAGE_BYTES;
   uint8_t* ring = stat ? smem + TC_SLAB_BYTES : smem;
 
@@ -148,6 +163,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       int stage = 0;
       uint32_t phase = 0;
+      // L2 look-ahead (tiles): deep-K tiles last long, one tile ahead is enough; K = 256 tiles need ~4
+      const int l2_ahead = (patch_blocks > 0 || mn_major || splits > 1) ? 0 : (nkb <= 8 ? ep.l2_ahead : min(ep.l2_ahead, 1));
       while (ti.next()) {
         const int kb0 = ti.split * kb_per, kb1 = min(nkb, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -174,6 +191,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, ti.tm * TC_BLOCK_M);
             if (!stat) tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, ti.tn * BN);
+            // pull the same k-block of the A tile this CTA will need `l2_ahead` tiles from now into L2
+            if (l2_ahead > 0) {
+              const int tm_ahead = stat ? ti.tm + l2_ahead * ti.cpn : (ti.w + l2_ahead * (int)gridDim.x) / (splits * tiles_n);
+              if (tm_ahead < tiles_m) tma_prefetch_2d(&tmA, kb * BLOCK_K, tm_ahead * TC_BLOCK_M);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -181,14 +203,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================== MMA issuer: all 32 lanes walk the schedule (uniform
+    // control flow, descriptors in uniform registers), one elected lane issues the tcgen05 instructions
+    {
       const uint32_t idesc = make_idesc(TF32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16, TC_BLOCK_M, BN, mn_major ? 1 : 0,
                                         mn_major ? 1 : 0);
       // K-major SW128: 8-row groups 1024 B apart, K advances 32 B inside the 128 B swizzle row.
       // MN-major SW128: 64-element MN blocks 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO),
       //                 one MMA (K = 16) consumes two K groups -> advance 2048 B.
-      const uint32_t lbo = mn_major ? 8192u : 16u, kstep = mn_major ? 2048u : 32u;
+      const uint32_t lbo = mn_major ? 8192u : 16u;
+      const uint64_t kstep = mn_major ? (2048u >> 4) : (32u >> 4);       // descriptor address units of 16 B
+      const uint64_t ring_desc = make_smem_desc(smem_u32(ring), lbo, 1024, UMMA_LAYOUT_SW128);
+      const uint64_t slab_desc = make_smem_desc(smem_u32(smem), lbo, 1024, UMMA_LAYOUT_SW128);
       TileIter ti(stat, tiles_m, tiles_n, splits);
       int stage = 0;
       uint32_t phase = 0;
@@ -204,18 +230,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(ring + stage * stage_bytes);
-          const uint32_t sb = stat ? smem_u32(smem + kb * Cfg::B_BYTES) : sa + Cfg::A_BYTES;
+          const uint64_t ad = ring_desc + (uint64_t)((stage * stage_bytes) >> 4);
+          const uint64_t bd = stat ? slab_desc + (uint64_t)((kb * Cfg::B_BYTES) >> 4) : ad + (uint64_t)(Cfg::A_BYTES >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {   // 4 x 32 bytes of K per stage
-            const uint64_t ad = make_smem_desc(sa + k * kstep, lbo, 1024, UMMA_LAYOUT_SW128);
-            const uint64_t bd = make_smem_desc(sb + k * kstep, lbo, 1024, UMMA_LAYOUT_SW128);
-            umma<TF32>(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)     // 4 x 32 bytes of K per stage
+              umma<TF32>(d_tmem, ad + k * kstep, bd + k * kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[buf]);       // accumulator ready for the epilogue
+        if (elect_one()) umma_commit(&tmem_full[buf]);       // accumulator ready for the epilogue
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -224,7 +251,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int part = (warp - 2) >> 2;       // which slice of the tile's columns
     constexpr int CW = BN / (Cfg::EPI_WARPS / 4);
-    const uint32_t stage = smem_u32(epi_stage + (warp - 2) * 2048);
+    const uint32_t stage = smem_u32(epi_stage + (warp - 2) * Lay::EPI_WARP_BYTES);
     TileIter ti(stat, tiles_m, tiles_n, splits);
     int it = 0;
     int cur_tn = -1;
@@ -253,7 +280,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + part * CW;
       const int m_base = ti.tm * TC_BLOCK_M + q * 32, n_base = ti.tn * BN + part * CW;
       if constexpr (EPI >= 0) {
-        epilogue_bf16_lean<CW, EPI>(&tmC, &tmPre, taddr, stage, smem_u32(bias_stage) + part * CW * 4,
+        epilogue_bf16_lean<CW, EPI, WIDE>(&tmC, &tmPre, taddr, stage, smem_u32(bias_stage) + part * CW * 4,
                                     smem_u32(bias_stage) + BN * 4 + part * CW * 2, lane, m_base, n_base);
       } else {
         epilogue_rows<CW, !TF32>(ep, &tmC, &tmPre, taddr, stage, lane, m_base, n_base, M, N);
@@ -321,17 +348,18 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long ro
   return VIT3D_OK;
 }
 
-template <bool TF32, int BN, int EPI = EPI_GENERIC>
+template <bool TF32, int BN, int EPI = EPI_GENERIC, bool WIDE = false>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
                      const TcEpilogue& ep, int M, int N, int K, int splits, bool stationary, cudaStream_t st,
                      int patch_blocks = 0, int mn_major = 0) {
   using Cfg = TcCfg<BN>;
-  auto kern = tc_gemm_kernel<TF32, BN, EPI>;
+  using Lay = TcLayout<BN, WIDE>;
+  auto kern = tc_gemm_kernel<TF32, BN, EPI, WIDE>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   V3_CUDA(cudaGetDevice(&dev));
   if (configured_dev != dev) {
-    V3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    V3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay::SMEM_BYTES));
     configured_dev = dev;
   }
   const int tiles_m = ceil_div(M, TC_BLOCK_M), tiles_n = ceil_div(N, BN);
@@ -343,15 +371,17 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     if (cpn > tiles_m) cpn = tiles_m;
     grid = cpn * tiles_n;
   }
-  V3_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, ta, tb, tc, tp, ep, M, N, K, tiles_m,
+  V3_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), (size_t)Lay::SMEM_BYTES, st, ta, tb, tc, tp, ep, M, N, K, tiles_m,
                      tiles_n, splits, stationary ? 1 : 0, patch_blocks, mn_major));
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
 
 // D[M,N] = A[M,K] B[N,K]^T with both operands dense row-major K-major; elem = 2 (bf16) or 4 (tf32)
-int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const TcEpilogue& ep, int splits,
+int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const TcEpilogue& ep_in, int splits,
             cudaStream_t st) {
+  TcEpilogue ep = ep_in;
+  ep.l2_ahead = tuning(VIT3D_TUNE_L2_AHEAD);
   const int eb = tf32 ? 4 : 2;
   const int sms = sm_count();
   const int tm = ceil_div(M, TC_BLOCK_M);
@@ -389,6 +419,15 @@ int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const 
   if (!ep.out_f32 && bn >= 128 && N % bn == 0 && tuning(VIT3D_TUNE_EPI_LEAN) != 0 &&
       (!ep.pre || ep.act == VIT3D_ACT_GELU) && (ep.act == VIT3D_ACT_NONE || ep.bias)) {
     const int mode = (ep.bias ? 1 : 0) | (ep.act == VIT3D_ACT_GELU ? 2 : 0) | (ep.pre ? 4 : 0);
+    if (bn == 256 && !ep.pre && tuning(VIT3D_TUNE_STORE_WIDE) != 0) {
+      // one [32 x 64] panel (128-byte rows) per epilogue warp and tile
+      CUtensorMap tw;
+      rc = make_tmap_2d(&tw, ep.out, 2, M, N, N, 32, 64, 128);
+      if (rc != VIT3D_OK) return rc;
+      if (mode == 0) return launch_tc<false, 256, 0, true>(ta, tb, tw, tw, ep, M, N, K, splits, stationary, st);
+      if (mode == 1) return launch_tc<false, 256, 1, true>(ta, tb, tw, tw, ep, M, N, K, splits, stationary, st);
+      if (mode == 3) return launch_tc<false, 256, 3, true>(ta, tb, tw, tw, ep, M, N, K, splits, stationary, st);
+    }
 #define V3_LEAN(BN_, MODE_) \
   if (bn == BN_ && mode == MODE_) return launch_tc<false, BN_, MODE_>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
     V3_LEAN(256, 0) V3_LEAN(256, 1) V3_LEAN(256, 3) V3_LEAN(256, 7)

@@ -44,6 +44,7 @@ struct ResEpilogue {
   float* mean = nullptr;           // [M] optional (LN)
   float* rstd = nullptr;           // [M] optional (LN)
   float eps = 1e-6f;
+  int l2_ahead = 0;                // tiles of A prefetched into L2 ahead of the operand ring
 };
 
 // MODE bit 0: bias, bit 1: residual, bit 2: fused LayerNorm output
@@ -106,15 +107,22 @@ tc_gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           mbar_arrive_expect_tx(&full_bar[stage], RS_STAGE_BYTES);
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * 64, tm * RS_BM);
           tma_load_2d(sa + RS_A_BYTES, &tmB, &full_bar[stage], kb * 64, tn * RS_BN);
+          // the same k-block of the A tile this CTA handles `l2_ahead` tiles from now -> L2
+          if (ep.l2_ahead > 0) {
+            const int wa = w + (nkb <= 8 ? ep.l2_ahead : 1) * (int)gridDim.x;
+            if (wa < total) tma_prefetch_2d(&tmA, kb * 64, (wa / tiles_n) * RS_BM);
+          }
           if (++stage == RS_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================== MMA issuer: all lanes walk the schedule, one elected
+    // lane issues (operands stay in uniform registers: see ptx.cuh elect_one)
+    {
       const uint32_t idesc = make_idesc(UMMA_FMT_BF16, RS_BM, RS_BN, 0, 0);
+      const uint64_t ring_desc = make_smem_desc(smem_u32(smem), 16, 1024, UMMA_LAYOUT_SW128);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -126,18 +134,18 @@ tc_gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * RS_STAGE_BYTES);
-          const uint32_t sb = sa + RS_A_BYTES;
+          const uint64_t ad = ring_desc + (uint64_t)((stage * RS_STAGE_BYTES) >> 4);
+          const uint64_t bd = ad + (uint64_t)(RS_A_BYTES >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = make_smem_desc(sa + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-            const uint64_t bd = make_smem_desc(sb + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-            umma<false>(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma<false>(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == RS_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[buf]);
+        if (elect_one()) umma_commit(&tmem_full[buf]);
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -361,6 +369,7 @@ int tc_gemm_res(const TcLinear& t, cudaStream_t st) {
     if (rc != VIT3D_OK) return rc;
   }
   ResEpilogue ep;
+  ep.l2_ahead = tuning(VIT3D_TUNE_L2_AHEAD);
   ep.bias = t.bias; ep.gamma = t.ln_gamma; ep.beta = t.ln_beta; ep.mean = t.ln_mean; ep.rstd = t.ln_rstd; ep.eps = t.ln_eps;
   const int mode = (t.bias ? 1 : 0) | (t.residual ? 2 : 0) | (ln ? 4 : 0);
   switch (mode) {

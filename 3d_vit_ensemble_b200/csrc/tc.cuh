@@ -43,6 +43,12 @@ bool tc_mlp_supported(int M, int H, int d);
 int tc_mlp_fwd(const void* xn, const void* w1, const float* b1, const void* w2, const float* b2, const float* residual,
                float* out, int M, int H, int d, cudaStream_t st);
 
+// k_tc_mlp2.cu: chunked fused MLP (256 fc1 columns per chunk, optional CTA pairs), + residual, + fused LayerNorm
+bool tc_mlp2_supported(int M, int H, int d);
+int tc_mlp2_fwd(const void* xn, const void* w1, const float* b1, const void* w2_h, const float* b2, const float* residual,
+                float* y, const float* gamma, const float* beta, float eps, void* ln_out, int M, int H, int d,
+                cudaStream_t st);
+
 bool tc_attn_supported(int S, int heads, int D);
 int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int heads, int D, cudaStream_t st);
 int tc_attn_bwd(const void* dctx, const void* qkv, void* dqkv, int B, int S, int heads, int D, cudaStream_t st);

@@ -23,6 +23,7 @@ struct TcEpilogue {
   int atomic = 0;                   // accumulate with fp32 atomics (split-K)
   int vols_per_tile = 0;            // patch-embedding mode: volumes per 128-row tile
   int round_tf32 = 0;               // fp32 output is the operand of a TF32 GEMM: round to nearest tf32
+  int l2_ahead = 0;                 // producer: tiles of A to prefetch into L2 ahead of the shared-memory ring
 };
 
 
@@ -250,13 +251,17 @@ __device__ __forceinline__ uint32_t gelu_pair_bf16_h2(__half2 x) {
   return pack2_bf16(f.x, f.y);
 }
 
-template <int CW, int MODE>
+// WIDE (CW == 64, no pre-activation output): the warp's whole 32 x 64 slice is staged as ONE panel with
+// 128-byte rows (128B swizzle, 4 KB) and leaves by one bulk tensor store per tile instead of two stores of
+// 64-byte rows - half the TMA row transactions, and the wait for the previous store moves a whole tile away.
+template <int CW, int MODE, bool WIDE = false>
 __device__ __forceinline__ void epilogue_bf16_lean(const CUtensorMap* tmC, const CUtensorMap* tmPre, uint32_t taddr,
                                                    uint32_t stage, uint32_t bias_f32, uint32_t bias_h2, int lane,
                                                    int m_base, int n_base) {
   constexpr bool BIAS = (MODE & 1) != 0, GELU = (MODE & 2) != 0, PRE = (MODE & 4) != 0;
-  const uint32_t my_row = stage + lane * 64;
-  const int sw = (lane >> 1) & 3;
+  static_assert(!WIDE || (CW == 64 && !PRE), "wide staging: 64 columns per warp, no pre-activation copy");
+  const uint32_t my_row = stage + lane * (WIDE ? 128 : 64);
+  const int sw = WIDE ? (lane & 7) : ((lane >> 1) & 3);
 #pragma unroll
   for (int c = 0; c < CW; c += 32) {
     uint32_t r[32];
@@ -306,15 +311,21 @@ __device__ __forceinline__ void epilogue_bf16_lean(const CUtensorMap* tmC, const
 #pragma unroll
       for (int j = 0; j < 16; ++j) w[j] = GELU ? gelu_pair_bf16(v[2 * j], v[2 * j + 1]) : pack2_bf16(v[2 * j], v[2 * j + 1]);
     }
-    if (lane == 0) bulk_store_wait_read();      // the previous store has finished reading the staging tile
-    __syncwarp();
+    if (!WIDE || c == 0) {
+      if (lane == 0) bulk_store_wait_read();    // the previous store has finished reading the staging tile
+      __syncwarp();
+    }
+    const int j0 = WIDE ? c / 8 : 0;            // 16-byte chunk index of column c within the staged row
 #pragma unroll
-    for (int j = 0; j < 4; ++j) st_shared_v4(my_row + ((j ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      tma_store_2d(tmC, stage, n_base + c, m_base);
-      bulk_store_commit();
+    for (int j = 0; j < 4; ++j)
+      st_shared_v4(my_row + (((j0 + j) ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+    if (!WIDE || c + 32 == CW) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmC, stage, WIDE ? n_base : n_base + c, m_base);
+        bulk_store_commit();
+      }
     }
   }
 }

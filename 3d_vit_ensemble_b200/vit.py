@@ -92,9 +92,10 @@ class Mlp(nn.Module):
         self._init_weights()
         self.precision = F.get_precision()
         self._site = 1
-        # single-kernel fc1->GELU->fc2 inference path (bf16 mode, hidden 256).  Correct and tested, but measured
-        # slower than the two-GEMM path on B200 (the GELU epilogue, not HBM, bounds both), so opt-in.
-        self.fused = os.environ.get("VIT3D_FUSED_MLP", "0") == "1"
+        # single-kernel fc1 -> GELU -> fc2 (+ residual, + next LayerNorm) inference path (BF16 mode, hidden 256,
+        # mlp_dim % 256 == 0): the (M, mlp_dim) intermediate never reaches HBM.  VIT3D_FUSED_MLP=0 composes the
+        # two GEMMs instead.
+        self.fused = os.environ.get("VIT3D_FUSED_MLP", "1") == "1"
 
     def _init_weights(self):
         nn.init.xavier_uniform_(self.fc1.weight)
@@ -107,8 +108,15 @@ class Mlp(nn.Module):
         returns (out, LN(out) or None)."""
         if next_ln is not None:
             prec = self.precision
-            if (not (self.training and self.dropout.p > 0.0) and residual is not None and not self.fused
-                    and not torch.is_grad_enabled()):
+            infer = (not (self.training and self.dropout.p > 0.0) and residual is not None
+                     and not torch.is_grad_enabled())
+            if (infer and self.fused and prec == "bf16" and self.fc1.weight.is_contiguous()
+                    and self.fc2.weight.is_contiguous()
+                    and F.mlp_fused_ln_supported(x.numel() // x.shape[-1], x.shape[-1], self.fc1.weight.shape[0])):
+                # one kernel: fc1 -> GELU -> fc2 -> + residual -> next LayerNorm
+                return F.mlp_fused_ln(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, residual,
+                                      next_ln.weight, next_ln.bias, next_ln.eps)
+            if infer:
                 h = F.linear(x, self.fc1.weight, self.fc1.bias, act=ACT_GELU, prec=prec)
                 if F.linear_ln_supported(h, self.fc2.weight, prec):
                     return F.linear_ln(h, self.fc2.weight, self.fc2.bias, residual, next_ln.weight, next_ln.bias,

@@ -59,8 +59,19 @@ unsigned long long vit3d_launch_count(void);
  *   VIT3D_TUNE_ATTN_THREADS  640 (default) or 512 threads per attention-forward CTA.  Env VIT3D_ATTN_THREADS.
  *   VIT3D_TUNE_EPI_LEAN      1 (default): compile-time specialised epilogue (bias from shared memory, packed
  *                            half GELU) for bf16-output GEMMs with full column tiles; 0: generic epilogue.
- *                            Env VIT3D_EPI_LEAN. */
-enum { VIT3D_TUNE_EPI_PANEL = 0, VIT3D_TUNE_ATTN_THREADS = 1, VIT3D_TUNE_EPI_LEAN = 2, VIT3D_TUNE_COUNT = 3 };
+ *                            Env VIT3D_EPI_LEAN.
+ *   VIT3D_TUNE_STORE_WIDE    0 (default): 32 x 32 bf16 staging panels, 4-stage A ring; 1: 32 x 64 panels (128-byte
+ *                            rows, one bulk tensor store per warp and tile) with a 2-stage ring - measured
+ *                            slower (the ring is too shallow).  Env VIT3D_STORE_WIDE.
+ *   VIT3D_TUNE_L2_AHEAD      tiles of the A operand the TMA producer prefetches into L2 ahead of its shared-
+ *                            memory ring (default 0 = off: measured no gain, the long operand latency under
+ *                            write-saturated HBM is not an L2 miss).  Env VIT3D_L2_AHEAD.
+ *   VIT3D_TUNE_MLP_V2        1 (default): vit3d_mlp_fwd runs the 256-column-chunk kernel (k_tc_mlp2.cu); 0: the
+ *                            first-generation 64 / 128-column kernels.  Env VIT3D_MLP_V2.
+ *   VIT3D_TUNE_MLP_PAIR      1 (default): the fused MLP runs on CTA pairs (cta_group::2, weights shared by two
+ *                            SMs); 0: one CTA per 128-row tile.  Env VIT3D_MLP_PAIR. */
+enum { VIT3D_TUNE_EPI_PANEL = 0, VIT3D_TUNE_ATTN_THREADS = 1, VIT3D_TUNE_EPI_LEAN = 2, VIT3D_TUNE_STORE_WIDE = 3,
+       VIT3D_TUNE_L2_AHEAD = 4, VIT3D_TUNE_MLP_V2 = 5, VIT3D_TUNE_MLP_PAIR = 6, VIT3D_TUNE_COUNT = 7 };
 int vit3d_set_tuning(int key, int value);
 int vit3d_get_tuning(int key);
 /* bytes per "act" element for a precision mode */
@@ -137,6 +148,13 @@ int vit3d_linear_bwd(const void* dy, int dy_f32, const void* x, int ldx, int x_f
 int vit3d_mlp_fwd(const void* xn, const void* w1_lp, const float* b1, const void* w2_h, const float* b2,
                   const float* residual, float* out, int M, int H, int d, vit3d_stream_t stream);
 int vit3d_mlp_supported(int M, int H, int d);
+/* Same block with the LayerNorm that consumes its output (the next Block's attention_norm, modeling.py:189)
+ * applied in the final epilogue: ln_out[M,H] = LayerNorm(out) * gamma + beta as bf16.  H = 256, d % 256 == 0.
+ * `out` may alias `residual`. */
+int vit3d_mlp_ln_fwd(const void* xn, const void* w1_lp, const float* b1, const void* w2_h, const float* b2,
+                     const float* residual, float* out, const float* gamma, const float* beta, float eps, void* ln_out,
+                     int M, int H, int d, vit3d_stream_t stream);
+int vit3d_mlp_ln_supported(int M, int H, int d);
 
 /* ---------------------------------------------------------------- a2: scaled-dot-product attention core
  * scores = q k^T / sqrt(D); probs = softmax(scores); ctx = probs v  (modeling.py:83-96).

@@ -199,3 +199,43 @@ def test_inference_ln_chain_matches_unfused(conf, monkeypatch):
     assert float((lf - lu).abs().max()) <= 5e-3
     assert float((ef - eu).abs().max()) <= 0.05 * float(eu.abs().max())
     assert len(af) == len(au) and float((af[-1] - au[-1]).abs().max()) <= 2e-2
+
+
+@pytest.mark.parametrize("M", [65, 130, 260, 4160, 19000])
+@pytest.mark.parametrize("d", [2048, 3072, 256])
+@pytest.mark.parametrize("pair", [0, 1])
+def test_fused_mlp_layernorm_matches_fp64(M, d, pair):
+    """vit3d_mlp_ln_fwd (chunked fused MLP, single CTA and CTA pair): y = x + fc2(GELU(fc1(xn))) in fp32 and
+    LayerNorm(y) in bf16 vs an fp64 evaluation on the same operands; y written in place over the residual."""
+    torch.manual_seed(M + d + pair)
+    H = 256
+    xn = torch.randn(M, H, device=DEV).to(torch.bfloat16)
+    w1 = (torch.randn(d, H, device=DEV) / H ** 0.5)
+    w2 = (torch.randn(H, d, device=DEV) / d ** 0.5)
+    b1 = torch.randn(d, device=DEV) * 0.1
+    b2 = torch.randn(H, device=DEV) * 0.1
+    res = torch.randn(M, H, device=DEV)
+    gamma = 1.0 + 0.1 * torch.randn(H, device=DEV)
+    beta = 0.1 * torch.randn(H, device=DEV)
+    w1l, w2l = w1.to(torch.bfloat16), w2.to(torch.float16)
+    out = res.clone()                      # in place
+    yn = torch.full((M, H), float("nan"), device=DEV, dtype=torch.bfloat16)
+    assert lib().vit3d_mlp_ln_supported(M, H, d) == 1
+    lib().vit3d_set_tuning(6, pair)
+    try:
+        call("vit3d_mlp_ln_fwd", ptr(xn), ptr(w1l), ptr(b1), ptr(w2l), ptr(b2), ptr(out), ptr(out), ptr(gamma), ptr(beta),
+             1e-6, ptr(yn), M, H, d, stream())
+        torch.cuda.synchronize()
+    finally:
+        lib().vit3d_set_tuning(6, 1)
+    h = xn.double() @ w1l.double().t() + b1.double()
+    a = gelu(h).to(torch.float16).double()
+    ref = a @ w2l.double().t() + b2.double() + res.double()
+    err = float((out.double() - ref).abs().max())
+    assert np.isfinite(err) and err <= 0.02, err
+    assert float((out.double() - ref).norm() / ref.norm()) < 2e-3
+    mu = ref.mean(1, keepdim=True)
+    var = ref.var(1, unbiased=False, keepdim=True)
+    ref_n = (ref - mu) / torch.sqrt(var + 1e-6) * gamma.double() + beta.double()
+    en = float((yn.double() - ref_n).abs().max())
+    assert np.isfinite(en) and en <= 0.02 + float(ref_n.abs().max()) / 128, en
