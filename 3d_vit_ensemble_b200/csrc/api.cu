@@ -47,8 +47,8 @@ static void tuning_defaults() {
   g_tuning[VIT3D_TUNE_STORE_WIDE] = env("VIT3D_STORE_WIDE", 0);
   g_tuning[VIT3D_TUNE_L2_AHEAD] = env("VIT3D_L2_AHEAD", 0);
   g_tuning[VIT3D_TUNE_MLP_V2] = env("VIT3D_MLP_V2", 1);
-  g_tuning[VIT3D_TUNE_MLP_PAIR] = env("VIT3D_MLP_PAIR", 1);
-  g_tuning[VIT3D_TUNE_ATTN_THREADS] = env("VIT3D_ATTN_THREADS", 640);
+  g_tuning[VIT3D_TUNE_MLP_PAIR] = env("VIT3D_MLP_PAIR", 0);
+  g_tuning[VIT3D_TUNE_ATTN_THREADS] = env("VIT3D_ATTN_THREADS", 0);
   g_tuning_init = true;
 }
 int tuning(int key) {

@@ -177,20 +177,41 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
       const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
       const int row0 = r0 + g, row1 = r0 + g + 8;
       if (probs) {
-        // measured: staging these rows through shared memory for 128-byte-line stores is not faster (the
-        // kernel is latency-, not store-bound), so they go out straight from the accumulator registers
-        float* p0 = probs + (((size_t)b * HEADS + h) * AT_S + row0) * AT_S;
-        float* p1 = probs + (((size_t)b * HEADS + h) * AT_S + row1) * AT_S;
+        // The probabilities leave from the accumulator registers.  What bounds this kernel with vis=True is the
+        // L1 store path (one wavefront per row and instruction), so every store carries a PAIR of columns as
+        // one 8-byte word.  Rows of 65 floats start at alternating 8-byte phases: where (head block + row) is
+        // even the pair is this thread's own (c, c+1); where it is odd the aligned pair is (c+1, c+2) and
+        // column c+2 comes from the neighbour lane of the quad by one shuffle.
+        const int bh = b * HEADS + h;
+        float* p0 = probs + ((size_t)bh * AT_S + row0) * AT_S;
+        float* p1 = probs + ((size_t)bh * AT_S + row1) * AT_S;
+        const bool odd = ((bh + row0) & 1) != 0;          // row1 = row0 + 8 has the same parity
+        const int src = (lane & ~3) | ((t + 1) & 3);
 #pragma unroll
         for (int nt = 0; nt < 9; ++nt) {
           const int c = nt * 8 + 2 * t;
-          if (row0 < AT_S) {
-            if (c < AT_S) p0[c] = s[nt][0] * inv0;
-            if (c + 1 < AT_S) p0[c + 1] = s[nt][1] * inv0;
-          }
-          if (row1 < AT_S) {
-            if (c < AT_S) p1[c] = s[nt][2] * inv1;
-            if (c + 1 < AT_S) p1[c + 1] = s[nt][3] * inv1;
+          // what this lane hands to its left neighbour: its column c, or (t == 0) the first column of the next tile
+          const float n0 = __shfl_sync(0xffffffffu, t == 0 ? s[nt + 1][0] : s[nt][0], src) * inv0;
+          const float n1 = __shfl_sync(0xffffffffu, t == 0 ? s[nt + 1][2] : s[nt][2], src) * inv1;
+          const float a0 = s[nt][0] * inv0, a1 = s[nt][1] * inv0, b0 = s[nt][2] * inv1, b1 = s[nt][3] * inv1;
+          if (!odd) {
+            if (row0 < AT_S) {
+              if (c + 1 < AT_S) *reinterpret_cast<float2*>(p0 + c) = make_float2(a0, a1);
+              else if (c < AT_S) p0[c] = a0;
+            }
+            if (row1 < AT_S) {
+              if (c + 1 < AT_S) *reinterpret_cast<float2*>(p1 + c) = make_float2(b0, b1);
+              else if (c < AT_S) p1[c] = b0;
+            }
+          } else {
+            if (row0 < AT_S) {
+              if (c + 2 < AT_S) *reinterpret_cast<float2*>(p0 + c + 1) = make_float2(a1, n0);
+              if (c == 0) p0[0] = a0;
+            }
+            if (row1 < AT_S) {
+              if (c + 2 < AT_S) *reinterpret_cast<float2*>(p1 + c + 1) = make_float2(b1, n1);
+              if (c == 0) p1[0] = b0;
+            }
           }
         }
       }
@@ -250,16 +271,23 @@ static int launch_attn(const void* qkv, void* ctx, float* probs, int B, cudaStre
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
-static int attn_threads() { return tuning(VIT3D_TUNE_ATTN_THREADS) == 512 ? 512 : 640; }
+// 0 = automatic: 20 warps (a volume of 8 heads is exactly two rounds of (head, row-tile) tasks), except for
+// 16 heads with the probabilities written, where 16 warps measured faster (120 vs 135 us at batch 1024)
+static int attn_threads(int D, bool vis) {
+  const int v = tuning(VIT3D_TUNE_ATTN_THREADS);
+  if (v == 512 || v == 640) return v;
+  return (D == 16 && vis) ? 512 : 640;
+}
 
 int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int heads, int D, cudaStream_t st) {
   if (!tc_attn_supported(S, heads, D)) V3_UNSUPPORTED("tc attention: unsupported shape S=%d heads=%d D=%d", S, heads, D);
   if (B <= 0) return VIT3D_OK;
-  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(ctx) & 15)) {
-    set_error("tc attention: qkv/ctx must be 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(ctx) & 15) ||
+      (reinterpret_cast<uintptr_t>(probs) & 7)) {
+    set_error("tc attention: qkv/ctx must be 16-byte aligned, probs 8-byte aligned");
     return VIT3D_ERR_INVALID;
   }
-  if (attn_threads() == 640) {
+  if (attn_threads(D, probs != nullptr) == 640) {
     if (D == 16) return launch_attn<16, 640>(qkv, ctx, probs, B, st);
     if (D == 32) return launch_attn<32, 640>(qkv, ctx, probs, B, st);
     return launch_attn<64, 640>(qkv, ctx, probs, B, st);

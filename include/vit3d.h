@@ -56,7 +56,8 @@ unsigned long long vit3d_launch_count(void);
  *   VIT3D_TUNE_EPI_PANEL     1 (default): fp32-output GEMMs with N % 256 == 0 (out-projection, fc2, fp32 data
  *                            gradients) run the TMA-panel kernel (residual fetched and result stored by bulk
  *                            tensor copies); 0: the generic epilogue.  Env VIT3D_EPI_PANEL.
- *   VIT3D_TUNE_ATTN_THREADS  640 (default) or 512 threads per attention-forward CTA.  Env VIT3D_ATTN_THREADS.
+ *   VIT3D_TUNE_ATTN_THREADS  0 (default: chosen per shape), 640 or 512 threads per attention-forward CTA.
+ *                            Env VIT3D_ATTN_THREADS.
  *   VIT3D_TUNE_EPI_LEAN      1 (default): compile-time specialised epilogue (bias from shared memory, packed
  *                            half GELU) for bf16-output GEMMs with full column tiles; 0: generic epilogue.
  *                            Env VIT3D_EPI_LEAN.
@@ -68,8 +69,9 @@ unsigned long long vit3d_launch_count(void);
  *                            write-saturated HBM is not an L2 miss).  Env VIT3D_L2_AHEAD.
  *   VIT3D_TUNE_MLP_V2        1 (default): vit3d_mlp_fwd runs the 256-column-chunk kernel (k_tc_mlp2.cu); 0: the
  *                            first-generation 64 / 128-column kernels.  Env VIT3D_MLP_V2.
- *   VIT3D_TUNE_MLP_PAIR      1 (default): the fused MLP runs on CTA pairs (cta_group::2, weights shared by two
- *                            SMs); 0: one CTA per 128-row tile.  Env VIT3D_MLP_PAIR. */
+ *   VIT3D_TUNE_MLP_PAIR      0 (default): one CTA per 128-row tile of the fused MLP; 1: clusters of two CTAs that
+ *                            share every weight k-block by TMA multicast (half the L2 reads; measured equal -
+ *                            the kernel is bound by its GELU / final epilogue, not by L2).  Env VIT3D_MLP_PAIR. */
 enum { VIT3D_TUNE_EPI_PANEL = 0, VIT3D_TUNE_ATTN_THREADS = 1, VIT3D_TUNE_EPI_LEAN = 2, VIT3D_TUNE_STORE_WIDE = 3,
        VIT3D_TUNE_L2_AHEAD = 4, VIT3D_TUNE_MLP_V2 = 5, VIT3D_TUNE_MLP_PAIR = 6, VIT3D_TUNE_COUNT = 7 };
 int vit3d_set_tuning(int key, int value);

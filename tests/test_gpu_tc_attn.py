@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from vit3d_b200._lib import PREC, call, ptr, stream
+from vit3d_b200._lib import PREC, call, lib, ptr, stream
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -24,14 +24,19 @@ def ref_attention(qkv, heads):
 @pytest.mark.parametrize("heads", [4, 8, 16])
 @pytest.mark.parametrize("B", [1, 3, 149, 700])
 @pytest.mark.parametrize("vis", [True, False])
-def test_attention_bf16(heads, B, vis):
+@pytest.mark.parametrize("threads", [0, 640, 512])
+def test_attention_bf16(heads, B, vis, threads):
     torch.manual_seed(B * 31 + heads)
     S, A = 65, 256
     qkv = (torch.randn(B, S, 3 * A, device=DEV) * 1.5).to(torch.bfloat16)
     ctx = torch.full((B, S, A), float("nan"), device=DEV, dtype=torch.bfloat16)
     probs = torch.full((B, heads, S, S), float("nan"), device=DEV) if vis else None
-    call("vit3d_attn_fwd", ptr(qkv), ptr(ctx), ptr(probs), B, S, heads, A // heads, PREC["bf16"], stream())
-    torch.cuda.synchronize()
+    lib().vit3d_set_tuning(1, threads)
+    try:
+        call("vit3d_attn_fwd", ptr(qkv), ptr(ctx), ptr(probs), B, S, heads, A // heads, PREC["bf16"], stream())
+        torch.cuda.synchronize()
+    finally:
+        lib().vit3d_set_tuning(1, 0)
     rc, rp = ref_attention(qkv, heads)
     err = float((ctx.double() - rc).abs().max())
     assert np.isfinite(err) and err < 0.03, err                 # bf16 P and bf16 output rounding

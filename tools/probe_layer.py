@@ -144,6 +144,6 @@ for thr in (512, 640):
                timeit(lambda: call("vit3d_attn_fwd", ptr(qkv), ptr(ctx), ptr(probs) if vis else None, B, S, a.heads, D,
                                    PREC["bf16"], stream())),
                4.0 * B * S * S * H, M * 4 * H * 2 + (B * a.heads * S * S * 4 if vis else 0))
-L.vit3d_set_tuning(1, 640)
+L.vit3d_set_tuning(1, 0)
 if a.json:
     json.dump(results, open(a.json, "w"), indent=1)
