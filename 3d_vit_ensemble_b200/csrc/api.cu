@@ -211,6 +211,8 @@ int vit3d_linear_fwd(const void* x, int ldx, int x_f32, const float* w, const vo
     t.y = y; t.y_f32 = yf; t.pre = pre; t.act = act; t.M = M; t.N = N; t.K = K; t.prec = prec;
     return tc_linear_fwd(t, st);
   }
+  if (N <= 8 && xf && yf && !residual && !pre && act == VIT3D_ACT_NONE)      // the classification head
+    return launch_rowdot(reinterpret_cast<const float*>(x), ldx, w, bias, reinterpret_cast<float*>(y), M, N, K, st);
   SgemmArgs g;
   g.A = x; g.sa_m = ldx; g.sa_k = 1; g.a_f32 = xf;
   g.B = w; g.sb_k = 1; g.sb_n = K; g.b_f32 = 1;

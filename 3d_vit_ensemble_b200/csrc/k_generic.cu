@@ -115,6 +115,33 @@ int launch_sgemm(const SgemmArgs& a, cudaStream_t st) {
   return VIT3D_OK;
 }
 
+// ---------------------------------------------------------------------------- skinny-N Linear (the head)
+// y[m, n] = x[m, :] . w[n, :] + bias[n] for N <= 8 (num_classes = 1 in the reference scripts): one warp per
+// output row, fp32 FMA, strided x rows (the head reads token 0 of every volume).  The tiled GEMM spends
+// 28 us on this [1024 x 1 x 256] product (one CTA column); this takes a few microseconds.
+__global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ w,
+                                                     const float* __restrict__ bias, float* __restrict__ y, int M, int N,
+                                                     int K) {
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const float* xr = x + (long long)m * ldx;
+  for (int n = 0; n < N; ++n) {
+    const float* wr = w + (long long)n * K;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(__ldg(xr + k), __ldg(wr + k), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) y[(long long)m * N + n] = acc + (bias ? bias[n] : 0.f);
+  }
+}
+int launch_rowdot(const float* x, long long ldx, const float* w, const float* bias, float* y, int M, int N, int K,
+                  cudaStream_t st) {
+  if (M <= 0) return VIT3D_OK;
+  rowdot_kernel<<<ceil_div(M, 8), 256, 0, st>>>(x, ldx, w, bias, y, M, N, K);
+  V3_LAUNCH_CHECK();
+  return VIT3D_OK;
+}
+
 // pick a split so that a skinny-output / deep-K product (weight gradients) fills the GPU
 int pick_splitk(int M, int N, int K) {
   const int tiles = ceil_div(M, GBM) * ceil_div(N, GBN);
@@ -368,8 +395,72 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ dy
     atomicAdd(db + n, s);
   }
 }
+// vectorised version: a thread owns V consecutive columns (one 16-byte load per row: 8 bf16 / 4 fp32), a warp
+// reads 512 contiguous bytes of a row, the 8 warps of a block stride over the rows (4 loads in flight each)
+template <bool F32>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const void* __restrict__ dy, float* __restrict__ db, int M, int N,
+                                                         int rows_per_block) {
+  constexpr int V = F32 ? 4 : 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + lane) * V;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float acc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = 0.f;
+  if (col < N) {
+    const uint4* base = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(dy) + (size_t)col * (F32 ? 4 : 2));
+    const size_t pitch = (size_t)N * (F32 ? 4 : 2) / 16;      // row pitch in uint4
+    auto add = [&](const uint4& v) {
+      if (F32) {
+        acc[0] += __uint_as_float(v.x); acc[1] += __uint_as_float(v.y); acc[2] += __uint_as_float(v.z); acc[3] += __uint_as_float(v.w);
+      } else {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[2 * j] += __uint_as_float(w[j] << 16);
+          acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+        }
+      }
+    };
+    int m = r0 + warp;
+    for (; m + 24 < r1; m += 32) {
+      const uint4 a = __ldg(base + (size_t)m * pitch), b = __ldg(base + (size_t)(m + 8) * pitch);
+      const uint4 c = __ldg(base + (size_t)(m + 16) * pitch), d = __ldg(base + (size_t)(m + 24) * pitch);
+      add(a); add(b); add(c); add(d);
+    }
+    for (; m < r1; m += 8) add(__ldg(base + (size_t)m * pitch));
+  }
+  __shared__ float red[8][32][V + 1];
+#pragma unroll
+  for (int j = 0; j < V; ++j) red[warp][lane][j] = acc[j];
+  __syncthreads();
+  if (warp == 0 && col < N) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += red[w][lane][j];
+      atomicAdd(db + col + j, sum);
+    }
+  }
+}
+
 int launch_colsum(const void* dy, int f32, float* db, int M, int N, cudaStream_t st) {
   if (M <= 0 || N <= 0) return VIT3D_OK;
+  const int V = f32 ? 4 : 8;
+  if (N % V == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+    const int gx = ceil_div(N, 32 * V);
+    int gy = (8 * sm_count()) / gx;
+    if (gy < 1) gy = 1;
+    int rpb = ceil_div(M, gy);
+    if (rpb < 32) rpb = 32;
+    gy = ceil_div(M, rpb);
+    if (f32) colsum_vec_kernel<true><<<dim3(gx, gy), 256, 0, st>>>(dy, db, M, N, rpb);
+    else colsum_vec_kernel<false><<<dim3(gx, gy), 256, 0, st>>>(dy, db, M, N, rpb);
+    V3_LAUNCH_CHECK();
+    return VIT3D_OK;
+  }
   const int gx = ceil_div(N, 32);
   int gy = (4 * sm_count()) / gx;
   if (gy < 1) gy = 1;

@@ -96,8 +96,10 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   uint64_t* a2_empty = bars + 17;      // (commit)
   uint64_t* acc2_full = bars + 18;     // (commit)
   uint64_t* acc2_empty = bars + 19;    // EPI_ARRIVALS
-  uint64_t* res_bar = bars + 20;       // [16] per warp: residual panel landed
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 36);
+  uint64_t* res_bar = bars + 20;       // [16] per warp: residual panel 0 landed (buffer = the warp's GELU-tile slice)
+  uint64_t* res_bar1 = bars + 36;      // [16] per warp: residual panel 1 landed (buffer = a 4 KB slice of the xn tile)
+  uint64_t* xpanel_free = bars + 52;   // 16: the final epilogue no longer uses the xn region
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 53);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = MC ? cluster_ctarank() : 0u;
@@ -120,7 +122,8 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     mbar_init(a2_empty, 1);
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, EPI_ARRIVALS);
-    for (int w = 0; w < 16; ++w) mbar_init(&res_bar[w], 1);
+    for (int w = 0; w < 16; ++w) { mbar_init(&res_bar[w], 1); mbar_init(&res_bar1[w], 1); }
+    mbar_init(xpanel_free, 16);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);
@@ -139,7 +142,8 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       uint32_t wphase = 0;
       int it = 0;
       for (int t = gid; t < tiles; t += ngroups, ++it) {
-        mbar_wait(x_empty, (it & 1) ^ 1);
+        mbar_wait(x_empty, (it & 1) ^ 1);           // the last fc1 of the previous tile has read xn ...
+        mbar_wait(xpanel_free, (it & 1) ^ 1);       // ... and its final epilogue is done with the region
         mbar_arrive_expect_tx(x_full, M2_X_BYTES);
         for (int kb = 0; kb < 4; ++kb) tma_load_2d(s_x + kb * 16384, &tmX, x_full, kb * 64, (t * NCTA + (int)rank) * 128);
         for (int s = 0; s <= nch; ++s) {
@@ -250,6 +254,12 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const uint32_t buf_s = smem_u32(buf_ptr);
     const uint32_t my_row = buf_s + lane * 128;
     uint64_t* rbar = &res_bar[warp - 2];
+    // second panel buffer: a 4 KB slice of the xn tile, idle from the last fc1 of a tile until the next tile's
+    // xn is loaded - its residual panel is fetched two MMA groups before the final epilogue needs it
+    uint8_t* bufx_ptr = s_x + (part * 4 + q) * 4096;
+    const uint32_t bufx_s = smem_u32(bufx_ptr);
+    const uint32_t my_rowx = bufx_s + lane * 128;
+    uint64_t* rbar1 = &res_bar1[warp - 2];
     uint32_t rphase = 0;
     uint32_t g = 0;                             // chunk counter
     int it = 0;
@@ -261,6 +271,11 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         if (lane < 16) bv = __ldg(reinterpret_cast<const float4*>(args.b1 + c * M2_NC + part * 64) + lane);
         mbar_wait(acc1_full, g & 1);
         tc_fence_after();
+        if (c == nch - 1 && lane == 0) {
+          // every fc1 of this tile has completed: the xn region is free -> prefetch residual panel 1 into it
+          mbar_arrive_expect_tx(rbar1, 4096);
+          tma_load_2d(bufx_ptr, &tmRes, rbar1, part * 64 + 32, m_base);
+        }
         uint32_t r0[32], r1[32];
         const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + part * 64;
         tmem_ld_32x32b_x32(tcol, r0);
@@ -306,16 +321,18 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + part * 64;
       const int sl7 = lane & 7;
       float s1 = 0.f, s2 = 0.f;
+      // panel 1 first (its residual has been in the xn-region buffer for a while), then panel 0 (fetched above)
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
+      for (int pi = 0; pi < 2; ++pi) {
+        const int p = 1 - pi;
+        const uint32_t prow = p ? my_rowx : my_row;
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + p * 32, r);
-        mbar_wait(rbar, rphase);
-        rphase ^= 1;
+        mbar_wait(p ? rbar1 : rbar, rphase);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const uint32_t a = my_row + ((j ^ sl7) << 4);
+          const uint32_t a = prow + ((j ^ sl7) << 4);
           const float4 b = __ldg(reinterpret_cast<const float4*>(args.b2 + part * 64 + p * 32) + j);
           const uint4 x = ld_shared_v4(a);
           const float v0 = __uint_as_float(r[4 * j]) + b.x + __uint_as_float(x.x);
@@ -334,16 +351,16 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tmY, buf_s, part * 64 + p * 32, m_base);
+          tma_store_2d(&tmY, p ? bufx_s : buf_s, part * 64 + p * 32, m_base);
           bulk_store_commit();
-          bulk_store_wait_read();
-          if (p == 0) {
-            mbar_arrive_expect_tx(rbar, 4096);
-            tma_load_2d(buf_ptr, &tmRes, rbar, part * 64 + 32, m_base);
-          }
         }
-        __syncwarp();
       }
+      rphase ^= 1;
+      if (lane == 0) {
+        bulk_store_wait_read();                       // both result panels have been read out of shared memory
+        mbar_arrive(xpanel_free);                     // the producer may load the next tile's xn
+      }
+      __syncwarp();
       if constexpr (LN) {
         tmem_st_wait();
         *reinterpret_cast<float2*>(buf_ptr + lane * 8) = make_float2(s1, s2);

@@ -20,6 +20,8 @@ struct SgemmArgs {
 
 int launch_sgemm(const SgemmArgs& a, cudaStream_t st);
 int pick_splitk(int M, int N, int K);
+int launch_rowdot(const float* x, long long ldx, const float* w, const float* bias, float* y, int M, int N, int K,
+                  cudaStream_t st);
 int launch_patch_gather(const float* x, void* out, int out_f32, int B, int X, int Y, int Z, int p0, int p1, int p2,
                         cudaStream_t st);
 int launch_cls_rows(const float* cls, const float* pos, float* tokens, int B, int S, int H, cudaStream_t st);

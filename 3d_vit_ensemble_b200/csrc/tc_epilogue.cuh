@@ -158,7 +158,9 @@ __device__ __forceinline__ void epilogue_rows(const TcEpilogue& ep, const CUtens
             const long long orow = ep.row_group > 0 ? (long long)m + m / ep.row_group + 1 : (long long)m;
             float* o = reinterpret_cast<float*>(ep.out) + orow * N + col;
             if (ep.atomic) {
-              atomicAdd(o, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w);
+              // one 16-byte vector reduction instead of four scalar ones (split-K weight gradients)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                           : "memory");
             } else {
               if (ep.pre) *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.pre) + orow * N + col) = v;
               if (ep.act == VIT3D_ACT_GELU) { v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w); }
