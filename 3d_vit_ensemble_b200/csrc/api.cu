@@ -46,7 +46,6 @@ static void tuning_defaults() {
   g_tuning[VIT3D_TUNE_EPI_LEAN] = env("VIT3D_EPI_LEAN", 1);
   g_tuning[VIT3D_TUNE_STORE_WIDE] = env("VIT3D_STORE_WIDE", 0);
   g_tuning[VIT3D_TUNE_L2_AHEAD] = env("VIT3D_L2_AHEAD", 0);
-  g_tuning[VIT3D_TUNE_MLP_V2] = env("VIT3D_MLP_V2", 1);
   g_tuning[VIT3D_TUNE_MLP_PAIR] = env("VIT3D_MLP_PAIR", 0);
   g_tuning[VIT3D_TUNE_ATTN_THREADS] = env("VIT3D_ATTN_THREADS", 0);
   g_tuning_init = true;
@@ -295,11 +294,9 @@ int vit3d_mlp_fwd(const void* xn, const void* w1_lp, const float* b1, const void
   V3_REQUIRE(xn && w1_lp && b1 && w2_lp && b2 && residual && out, "mlp_fwd: null pointer");
   V3_REQUIRE(M >= 0 && H > 0 && d > 0, "mlp_fwd: bad shape");
   if (M == 0) return VIT3D_OK;
-  if (tuning(VIT3D_TUNE_MLP_V2) != 0 && tc_mlp2_supported(M, H, d))
-    return tc_mlp2_fwd(xn, w1_lp, b1, w2_lp, b2, residual, out, nullptr, nullptr, 0.f, nullptr, M, H, d, as_stream(stream));
-  return tc_mlp_fwd(xn, w1_lp, b1, w2_lp, b2, residual, out, M, H, d, as_stream(stream));
+  return tc_mlp2_fwd(xn, w1_lp, b1, w2_lp, b2, residual, out, nullptr, nullptr, 0.f, nullptr, M, H, d, as_stream(stream));
 }
-int vit3d_mlp_supported(int M, int H, int d) { return (tc_mlp_supported(M, H, d) || tc_mlp2_supported(M, H, d)) ? 1 : 0; }
+int vit3d_mlp_supported(int M, int H, int d) { return tc_mlp2_supported(M, H, d) ? 1 : 0; }
 
 int vit3d_mlp_ln_supported(int M, int H, int d) { return tc_mlp2_supported(M, H, d) ? 1 : 0; }
 int vit3d_mlp_ln_fwd(const void* xn, const void* w1_lp, const float* b1, const void* w2_h, const float* b2,

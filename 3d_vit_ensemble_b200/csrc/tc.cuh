@@ -38,11 +38,6 @@ bool tc_patch_embed_supported(int B, int X, int Y, int Z, int p0, int p1, int p2
 int tc_patch_embed_fwd(const float* x, const float* w, const float* bias, const float* pos, float* tokens, int B, int X,
                        int Y, int Z, int p0, int p1, int p2, int H, cudaStream_t st);
 
-// out[M,H] = residual + fc2(GELU(fc1(xn))) in one kernel (inference); xn/w1/w2 bf16, H = 256
-bool tc_mlp_supported(int M, int H, int d);
-int tc_mlp_fwd(const void* xn, const void* w1, const float* b1, const void* w2, const float* b2, const float* residual,
-               float* out, int M, int H, int d, cudaStream_t st);
-
 // k_tc_mlp2.cu: chunked fused MLP (256 fc1 columns per chunk, optional CTA pairs), + residual, + fused LayerNorm
 bool tc_mlp2_supported(int M, int H, int d);
 int tc_mlp2_fwd(const void* xn, const void* w1, const float* b1, const void* w2_h, const float* b2, const float* residual,

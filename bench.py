@@ -352,7 +352,7 @@ def main():
     roof = None
     cpu_base = None
     if rank == 0:
-        roof = roofline_probe(args, cfgs[0], B, dev)
+        roof = roofline_probe(args, cfgs[0], B, dev, train)
         if not args.no_cpu_baseline:
             sample = min(args.cpu_sample, B)
             v, ms = cpu_arm(args, cfgs, train, 3, 1, sample)
@@ -395,48 +395,110 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def roofline_probe(args, cfg, B, dev):
-    """Times the dominant kernel (the fc1 GELU GEMM, [B*65,256]x[256,d]) alone with CUDA events on the
-    launching stream and reports achieved TFLOP/s against the measured burst bf16 peak."""
+def _time_launches(fn, iters=10, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures under profiles/
+# (only valid for the captured shape: conf 5, batch 1024, bf16)
+NCU_TRAFFIC = {"mlp_ln": 163.0e6, "fc1_gelu": 257.2e6}
+
+
+def roofline_probe(args, cfg, B, dev, train=False):
+    """Times the dominant kernel alone with CUDA events on the launching stream.
+
+    Inference in BF16 mode: the fused MLP block (fc1 -> GELU -> fc2 -> + residual -> next LayerNorm,
+    vit3d_mlp_ln_fwd), 44 % of the step and 75-82 % of the model's FLOPs: tensor bound, 4*S*H*d FLOP per volume
+    per launch.  Otherwise (training / other precisions): the fc1 + GELU GEMM.  `others` carries the HBM-bound
+    kernels of a layer against the measured copy bandwidth."""
     import torch
     from vit3d_b200 import _lib
     from vit3d_b200._lib import PREC, call, ptr, stream
     peaks = load_peaks()
-    M, K, N = B * 65, cfg.hidden_size, cfg.transformer["mlp_dim"]
+    L = _lib.lib()
+    M, H, d = B * 65, cfg.hidden_size, cfg.transformer["mlp_dim"]
+    heads = cfg.transformer["num_heads"]
     prec = args.precision
-    adt = torch.bfloat16 if prec == "bf16" else torch.float32
-    x = (torch.randn(M, K, device=dev) * 0.5).to(adt)
-    w = torch.randn(N, K, device=dev) * 0.05
-    wl = w.to(torch.bfloat16) if prec == "bf16" else None
-    b = torch.randn(N, device=dev) * 0.01
-    y = torch.empty(M, N, device=dev, dtype=adt)
-    tc = bool(_lib.lib().vit3d_tc_supported(PREC[prec], M, N, K))
-
-    def run():
-        call("vit3d_linear_fwd", ptr(x), K, int(adt == torch.float32), ptr(w), ptr(wl), ptr(b), None, ptr(y),
-             int(adt == torch.float32), None, 1, M, N, K, PREC[prec], stream())
-    for _ in range(3):
-        run()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    iters = 10
-    e0.record()
-    for _ in range(iters):
-        run()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    flops = 2.0 * M * N * K
-    ach = flops / (ms * 1e-3) / 1e12
-    return {"kernel": "fc1+GELU GEMM (vit3d_linear_fwd, M=%d N=%d K=%d, %s)" % (M, N, K, "tcgen05" if tc else "fp32 FMA fallback"),
-            "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": ach / peaks["bf16_tflops"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one ncu --set full capture
-            # (profiles/r01_fc1_gelu_gemm_ncu_full_raw.csv); only valid for the captured shape
-            "traffic": 254.8e6 if (M == 66560 and N == 2048 and K == 256 and prec == "bf16" and tc) else None,
-            "traffic_unit": "bytes per launch", "algorithmic_bytes": float(M * K * 2 + N * K * 2 + M * N * 2) if prec == "bf16" else None,
-            "ms_per_launch": ms,
-            "peak_source": peaks.get("source"), "how": "kernel timed alone, 10 launches, CUDA events (burst peak applies)"}
+    lp = prec == "bf16"
+    adt = torch.bfloat16 if lp else torch.float32
+    xn = (torch.randn(M, H, device=dev) * 0.5).to(adt)
+    w1 = torch.randn(d, H, device=dev) * 0.05
+    b1 = torch.randn(d, device=dev) * 0.01
+    captured = (M == 66560 and d == 2048 and H == 256 and lp)
+    others = []
+    fused = (not train) and lp and H == 256 and bool(L.vit3d_mlp_ln_supported(M, H, d))
+    if fused:
+        w1l = w1.to(torch.bfloat16)
+        w2h = (torch.randn(H, d, device=dev) / d ** 0.5).to(torch.float16)
+        b2 = torch.randn(H, device=dev) * 0.01
+        x32 = torch.randn(M, H, device=dev)
+        y32 = torch.empty(M, H, device=dev)
+        yn = torch.empty(M, H, device=dev, dtype=torch.bfloat16)
+        g, be = torch.ones(H, device=dev), torch.zeros(H, device=dev)
+        ms = _time_launches(lambda: call("vit3d_mlp_ln_fwd", ptr(xn), ptr(w1l), ptr(b1), ptr(w2h), ptr(b2), ptr(x32), ptr(y32),
+                                         ptr(g), ptr(be), 1e-6, ptr(yn), M, H, d, stream()))
+        flops = 4.0 * M * H * d
+        ach = flops / (ms * 1e-3) / 1e12
+        roof = {"kernel": "fused MLP block: fc1 + GELU + fc2 + residual + LayerNorm (vit3d_mlp_ln_fwd, tc_mlp2_kernel, "
+                          "M=%d H=%d d=%d, tcgen05)" % (M, H, d),
+                "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_tflops"],
+                "traffic": NCU_TRAFFIC["mlp_ln"] if captured else None, "traffic_unit": "bytes per launch",
+                "algorithmic_bytes": float(M * H * (2 + 4 + 4 + 2) + 2 * H * d * 2),
+                "algorithmic_flops": flops, "ms_per_launch": ms, "peak_source": peaks.get("source"),
+                "how": "kernel timed alone, 10 launches, CUDA events (burst peak applies)"}
+        # HBM-bound kernels of the same layer (bytes = what the kernel must read + write once)
+        hbm = peaks["hbm_gbs"]
+        qkv = (torch.randn(M, 3 * H, device=dev) * 0.5).to(torch.bfloat16)
+        ctx = torch.empty(M, H, device=dev, dtype=torch.bfloat16)
+        probs = torch.empty(B, heads, 65, 65, device=dev) if args.vis else None
+        t = _time_launches(lambda: call("vit3d_attn_fwd", ptr(qkv), ptr(ctx), ptr(probs), B, 65, heads, H // heads,
+                                        PREC["bf16"], stream()))
+        nb = M * 4 * H * 2 + (B * heads * 65 * 65 * 4 if args.vis else 0)
+        others.append({"kernel": "attention forward (attn_fwd_tc_kernel, vis=%s)" % bool(args.vis), "bound": "hbm",
+                       "achieved": nb / (t * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": nb / (t * 1e-3) / 1e9 / hbm,
+                       "ms_per_launch": t})
+        wo = (torch.randn(H, H, device=dev) / 16).to(torch.bfloat16)
+        t = _time_launches(lambda: call("vit3d_linear_ln_fwd", ptr(ctx), ptr(wo), ptr(b2), ptr(x32), ptr(y32), ptr(g), ptr(be),
+                                        1e-6, ptr(yn), None, None, M, H, H, stream()))
+        nb = M * H * (2 + 4 + 4 + 2)
+        others.append({"kernel": "out-projection + residual + LayerNorm (tc_gemm_res_kernel)", "bound": "hbm",
+                       "achieved": nb / (t * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": nb / (t * 1e-3) / 1e9 / hbm,
+                       "ms_per_launch": t})
+        mean, rstd = torch.empty(M, device=dev), torch.empty(M, device=dev)
+        t = _time_launches(lambda: call("vit3d_ln_fwd", ptr(x32), ptr(g), ptr(be), ptr(yn), 1, ptr(mean), ptr(rstd), M, H, 1e-6,
+                                        stream()))
+        nb = M * H * 6
+        others.append({"kernel": "LayerNorm fp32 -> bf16 (ln_fwd_kernel)", "bound": "hbm", "achieved": nb / (t * 1e-3) / 1e9,
+                       "peak": hbm, "unit": "GB/s", "frac": nb / (t * 1e-3) / 1e9 / hbm, "ms_per_launch": t})
+    # the fc1 + GELU GEMM (training forward; the inference path when the fused block is unavailable)
+    wl = w1.to(torch.bfloat16) if lp else None
+    y = torch.empty(M, d, device=dev, dtype=adt)
+    tc = bool(L.vit3d_tc_supported(PREC[prec], M, d, H))
+    ms1 = _time_launches(lambda: call("vit3d_linear_fwd", ptr(xn), H, int(adt == torch.float32), ptr(w1), ptr(wl), ptr(b1), None,
+                                      ptr(y), int(adt == torch.float32), None, 1, M, d, H, PREC[prec], stream()))
+    flops1 = 2.0 * M * d * H
+    fc1 = {"kernel": "fc1+GELU GEMM (vit3d_linear_fwd, M=%d N=%d K=%d, %s)" % (M, d, H, "tcgen05" if tc else "fp32 FMA"),
+           "bound": "tensor", "achieved": flops1 / (ms1 * 1e-3) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+           "frac": flops1 / (ms1 * 1e-3) / 1e12 / peaks["bf16_tflops"],
+           "traffic": NCU_TRAFFIC["fc1_gelu"] if captured else None, "traffic_unit": "bytes per launch",
+           "algorithmic_bytes": float(M * H * 2 + d * H * 2 + M * d * 2) if lp else None, "ms_per_launch": ms1,
+           "peak_source": peaks.get("source"), "how": "kernel timed alone, 10 launches, CUDA events (burst peak applies)"}
+    if not fused:
+        return fc1
+    others.append(fc1)
+    roof["others"] = others
+    return roof
 
 
 if __name__ == "__main__":

@@ -67,13 +67,11 @@ unsigned long long vit3d_launch_count(void);
  *   VIT3D_TUNE_L2_AHEAD      tiles of the A operand the TMA producer prefetches into L2 ahead of its shared-
  *                            memory ring (default 0 = off: measured no gain, the long operand latency under
  *                            write-saturated HBM is not an L2 miss).  Env VIT3D_L2_AHEAD.
- *   VIT3D_TUNE_MLP_V2        1 (default): vit3d_mlp_fwd runs the 256-column-chunk kernel (k_tc_mlp2.cu); 0: the
- *                            first-generation 64 / 128-column kernels.  Env VIT3D_MLP_V2.
  *   VIT3D_TUNE_MLP_PAIR      0 (default): one CTA per 128-row tile of the fused MLP; 1: clusters of two CTAs that
  *                            share every weight k-block by TMA multicast (half the L2 reads; measured equal -
  *                            the kernel is bound by its GELU / final epilogue, not by L2).  Env VIT3D_MLP_PAIR. */
 enum { VIT3D_TUNE_EPI_PANEL = 0, VIT3D_TUNE_ATTN_THREADS = 1, VIT3D_TUNE_EPI_LEAN = 2, VIT3D_TUNE_STORE_WIDE = 3,
-       VIT3D_TUNE_L2_AHEAD = 4, VIT3D_TUNE_MLP_V2 = 5, VIT3D_TUNE_MLP_PAIR = 6, VIT3D_TUNE_COUNT = 7 };
+       VIT3D_TUNE_L2_AHEAD = 4, VIT3D_TUNE_MLP_PAIR = 5, VIT3D_TUNE_COUNT = 6 };
 int vit3d_set_tuning(int key, int value);
 int vit3d_get_tuning(int key);
 /* bytes per "act" element for a precision mode */
@@ -142,7 +140,7 @@ int vit3d_linear_bwd(const void* dy, int dy_f32, const void* x, int ldx, int x_f
 
 /* ---------------------------------------------------------------- a3: Mlp.forward fused (inference)
  * out[M,H] = residual + fc2(gelu(fc1(xn) + b1)) + b2  (modeling.py:118-124 with the x + Mlp(..) add of :196;
- * dropout is the identity in eval mode).  BF16 mode, H = 256, d % 128 == 0: xn bf16 [M,H] (LayerNorm
+ * dropout is the identity in eval mode).  BF16 mode, H = 256, d % 256 == 0: xn bf16 [M,H] (LayerNorm
  * output), w1_lp bf16 [d,H], w2_h FP16 [H,d] (vit3d_cast_f32_to_f16: the GELU output is kept in fp16 -
  * 11 significant bits - and tcgen05 kind::f16 needs both operands of fc2 in the same 16-bit format); the
  * [M,d] intermediate stays on chip.  Returns VIT3D_ERR_UNSUPPORTED for other shapes (compose

@@ -115,7 +115,7 @@ def test_tc_linear_backward_bf16(shape):
 
 
 @pytest.mark.parametrize("M", [65, 130, 260, 4160, 19000])
-@pytest.mark.parametrize("d", [2048, 3072, 128])
+@pytest.mark.parametrize("d", [2048, 3072, 256])
 def test_fused_mlp_matches_fp64(M, d):
     """Single-kernel fc1 -> GELU -> fc2 (+bias, +residual) vs an fp64 evaluation on the same bf16 operands
     (the bf16 rounding of the GELU output is reproduced in the reference)."""
@@ -221,13 +221,13 @@ def test_fused_mlp_layernorm_matches_fp64(M, d, pair):
     out = res.clone()                      # in place
     yn = torch.full((M, H), float("nan"), device=DEV, dtype=torch.bfloat16)
     assert lib().vit3d_mlp_ln_supported(M, H, d) == 1
-    lib().vit3d_set_tuning(6, pair)
+    lib().vit3d_set_tuning(5, pair)
     try:
         call("vit3d_mlp_ln_fwd", ptr(xn), ptr(w1l), ptr(b1), ptr(w2l), ptr(b2), ptr(out), ptr(out), ptr(gamma), ptr(beta),
              1e-6, ptr(yn), M, H, d, stream())
         torch.cuda.synchronize()
     finally:
-        lib().vit3d_set_tuning(6, 1)
+        lib().vit3d_set_tuning(5, 0)
     h = xn.double() @ w1l.double().t() + b1.double()
     a = gelu(h).to(torch.float16).double()
     ref = a @ w2l.double().t() + b2.double() + res.double()

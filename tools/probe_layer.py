@@ -107,31 +107,29 @@ def gemm_suite(tag):
                2.0 * M * d * H, M * d * 2 + 2 * M * H * 4 + M * H * 2)
 
 
-# tuning keys: 0 panel kernel, 1 attention threads, 2 lean epilogue, 3 wide staging, 4 L2 look-ahead
+# tuning keys (include/vit3d.h): 0 panel kernel, 1 attention threads, 2 lean epilogue, 3 wide staging, 4 L2 look-ahead,
+# 5 fused-MLP weight multicast
 for ahead in (0,):
     L.vit3d_set_tuning(4, ahead)
     gemm_suite(f"[l2_ahead={ahead}]")
-L.vit3d_set_tuning(4, 4)
+L.vit3d_set_tuning(4, 0)
 L.vit3d_set_tuning(2, 0)
 L.vit3d_set_tuning(0, 0)
 gemm_suite("[generic epilogues]")
 L.vit3d_set_tuning(2, 1)
 L.vit3d_set_tuning(0, 1)
 w2h = w2.to(torch.float16)
-for v2, pair in ((0, 0), (1, 0), (1, 1)):
-    L.vit3d_set_tuning(5, v2)
-    L.vit3d_set_tuning(6, pair)
-    tag = f"[v2={v2} pair={pair}]"
+for pair in (0, 1):
+    L.vit3d_set_tuning(5, pair)
+    tag = f"[multicast pair={pair}]"
     report(f"fused MLP (fc1+GELU+fc2+res) {tag}",
            timeit(lambda: call("vit3d_mlp_fwd", ptr(xn), ptr(wl1), ptr(b1), ptr(w2h), ptr(b2), ptr(x32), ptr(y32), M, H, d,
                                stream())), 4.0 * M * d * H, M * H * 2 + 2 * M * H * 4)
-    if v2:
-        report(f"fused MLP + LN {tag}",
-               timeit(lambda: call("vit3d_mlp_ln_fwd", ptr(xn), ptr(wl1), ptr(b1), ptr(w2h), ptr(b2), ptr(x32), ptr(y32),
-                                   ptr(gamma), ptr(beta), 1e-6, ptr(yn), M, H, d, stream())),
-               4.0 * M * d * H, M * H * 2 + 2 * M * H * 4 + M * H * 2)
-L.vit3d_set_tuning(5, 1)
-L.vit3d_set_tuning(6, 1)
+    report(f"fused MLP + LN {tag}",
+           timeit(lambda: call("vit3d_mlp_ln_fwd", ptr(xn), ptr(wl1), ptr(b1), ptr(w2h), ptr(b2), ptr(x32), ptr(y32),
+                               ptr(gamma), ptr(beta), 1e-6, ptr(yn), M, H, d, stream())),
+           4.0 * M * d * H, M * H * 2 + 2 * M * H * 4 + M * H * 2)
+L.vit3d_set_tuning(5, 0)
 report("LayerNorm fp32 -> bf16",
        timeit(lambda: call("vit3d_ln_fwd", ptr(x32), ptr(gamma), ptr(beta), ptr(yn), 1, ptr(mean), ptr(rstd), M, H, 1e-6,
                            stream())), 8.0 * M * H, M * H * 4 + M * H * 2)

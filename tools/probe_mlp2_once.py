@@ -22,7 +22,7 @@ y32 = torch.empty(M, H, device=dev)
 yn = torch.empty(M, H, device=dev, dtype=torch.bfloat16)
 g = torch.ones(H, device=dev)
 be = torch.zeros(H, device=dev)
-lib().vit3d_set_tuning(6, a.pair)
+lib().vit3d_set_tuning(5, a.pair)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for i in range(a.iters + 1):
     if i == 1:
