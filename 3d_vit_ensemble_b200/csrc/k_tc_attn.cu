@@ -69,20 +69,24 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
-// THREADS: 512 (16 warps) or 640 (20 warps).  A volume is HEADS * 5 (head, 16-row tile) tasks: 40 tasks take
-// 3 rounds of 16 warps but 2 rounds of 20 (80 tasks: 5 vs 4, 20 tasks: 2 vs 1), and the fifth warp per
-// scheduler hides more of the ldmatrix / mma / MUFU / store latency.
+// THREADS compute threads: 512 (16 warps) or 640 (20 warps), plus one producer warp.  A volume is HEADS * 5
+// (head, 16-row tile) tasks: 40 tasks take 3 rounds of 16 warps but 2 rounds of 20 (80 tasks: 5 vs 4).
+// The warps are only coupled through data: the producer warp refills a volume buffer when all compute warps
+// have released it (mbarrier with one arrival per warp), and every warp ships its own context tile, so a fast
+// warp walks on into the next volume instead of waiting at a block-wide barrier (15 % of the samples before).
 template <int D, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS + 32, 1)
 attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, float* __restrict__ probs,
                    int B, float scale_log2e) {
   constexpr int HEADS = AT_A / D;
+  constexpr int NW = THREADS / 32;    // compute warps
   constexpr int KSTEPS = D / 16;      // k-steps of the Q K^T product
   constexpr int NT = 10;              // key n-tiles of 8 (80 >= 65; tiles 8.. are partly / fully padding)
   constexpr int DT = D / 8;           // output n-tiles of the P V product
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * AT_BUF);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * AT_BUF);     // [2] volume landed
+  uint64_t* freeb = full + 2;                                          // [2] every compute warp is done with it
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -90,34 +94,36 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
   if (threadIdx.x == 0) {
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
+    mbar_init(&freeb[0], NW);
+    mbar_init(&freeb[1], NW);
     fence_barrier_init();
   }
   __syncthreads();
   pdl_trigger();
   pdl_wait();
 
-  auto issue_load = [&](int b, int buf) {   // warp 0, all lanes
-    if (lane == 0) mbar_arrive_expect_tx(&full[buf], AT_S * AT_ROWB);
-    __syncwarp();
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(qkv) + (size_t)b * AT_S * AT_ROWB;
-    uint8_t* dst = smem + buf * AT_BUF;
-    for (int r = lane; r < AT_S; r += 32) bulk_g2s(dst + r * AT_PITCH, src + (size_t)r * AT_ROWB, AT_ROWB, &full[buf]);
-  };
-
-  if (warp == 0 && (int)blockIdx.x < B) issue_load(blockIdx.x, 0);
+  if (warp == NW) {
+    // ===================================================== producer warp: one bulk copy per token row
+    int it = 0;
+    for (int b = blockIdx.x; b < B; b += gridDim.x, ++it) {
+      const int buf = it & 1;
+      if (it >= 2) mbar_wait(&freeb[buf], ((it >> 1) - 1) & 1);       // volume it-2 has been consumed
+      if (lane == 0) mbar_arrive_expect_tx(&full[buf], AT_S * AT_ROWB);
+      __syncwarp();
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(qkv) + (size_t)b * AT_S * AT_ROWB;
+      uint8_t* dst = smem + buf * AT_BUF;
+      for (int r = lane; r < AT_S; r += 32) bulk_g2s(dst + r * AT_PITCH, src + (size_t)r * AT_ROWB, AT_ROWB, &full[buf]);
+    }
+    return;
+  }
 
   int it = 0;
   for (int b = blockIdx.x; b < B; b += gridDim.x, ++it) {
     const int buf = it & 1;
-    if (warp == 0) {
-      const int nb = b + gridDim.x;
-      bulk_wait_read0();                 // the context stores that read buffer buf^1 have drained
-      if (nb < B) issue_load(nb, buf ^ 1);
-    }
     mbar_wait(&full[buf], (it >> 1) & 1);
     const uint32_t sb = smem_u32(smem + buf * AT_BUF);
 
-    for (int task = warp; task < HEADS * 5; task += THREADS / 32) {
+    for (int task = warp; task < HEADS * 5; task += NW) {
       const int h = task / 5, rt = task % 5;
       const int r0 = rt * 16;
       // ---- Q fragments (A operand), rows clamped to the last token
@@ -160,7 +166,7 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
       float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
+      for (int nt = 0; nt < 9; ++nt) {
         const int c = nt * 8 + 2 * t;
         const bool v0 = c < AT_S, v1 = c + 1 < AT_S;
         s[nt][0] = v0 ? ex2_approx((s[nt][0] - mx0) * scale_log2e) : 0.f;
@@ -234,7 +240,8 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
           mma_bf16(o[dt], a0, a1, a2, a3, b0, b1);
         }
       }
-      // ---- context tile overwrites the Q tile it came from (only this task reads that block)
+      // ---- the context tile overwrites the Q tile it came from (only this task reads that block) and the warp
+      //      ships it itself: 16-byte chunks, a store instruction covers whole 32/64/128-byte row segments
       __syncwarp();
       uint8_t* base = smem + buf * AT_BUF;
 #pragma unroll
@@ -243,17 +250,23 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
         if (row0 < AT_S) *reinterpret_cast<uint32_t*>(base + row0 * AT_PITCH + col * 2) = pack_bf16(o[dt][0] * inv0, o[dt][1] * inv0);
         if (row1 < AT_S) *reinterpret_cast<uint32_t*>(base + row1 * AT_PITCH + col * 2) = pack_bf16(o[dt][2] * inv1, o[dt][3] * inv1);
       }
+      __syncwarp();
+      {
+        constexpr int CPR = D / 8;                  // 16-byte chunks per row of the tile
+        uint8_t* gdst = reinterpret_cast<uint8_t*>(ctx) + ((size_t)b * AT_S * AT_A + h * D) * 2;
+#pragma unroll
+        for (int i = lane; i < 16 * CPR; i += 32) {
+          const int row = r0 + i / CPR, ch = i % CPR;
+          if (row < AT_S)
+            *reinterpret_cast<uint4*>(gdst + (size_t)row * AT_A * 2 + ch * 16) =
+                *reinterpret_cast<const uint4*>(base + row * AT_PITCH + h * D * 2 + ch * 16);
+        }
+      }
     }
-    fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the bulk-copy engine
-    __syncthreads();
-    if (warp == 0) {
-      uint8_t* dst = reinterpret_cast<uint8_t*>(ctx) + (size_t)b * AT_S * AT_A * 2;
-      const uint8_t* src = smem + buf * AT_BUF;
-      for (int r = lane; r < AT_S; r += 32) bulk_s2g(dst + (size_t)r * AT_A * 2, src + r * AT_PITCH, AT_A * 2);
-      bulk_commit();
-    }
+    // this warp no longer reads the volume buffer
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&freeb[buf]);
   }
-  if (warp == 0) bulk_wait0();
 }
 
 bool tc_attn_supported(int S, int heads, int D) {
@@ -266,7 +279,7 @@ static int launch_attn(const void* qkv, void* ctx, float* probs, int B, cudaStre
   V3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
   const int grid = B < sm_count() ? B : sm_count();
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)D);
-  V3_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), (size_t)AT_SMEM, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
+  V3_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS + 32), (size_t)AT_SMEM, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
                      reinterpret_cast<__nv_bfloat16*>(ctx), probs, B, scale_log2e));
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
