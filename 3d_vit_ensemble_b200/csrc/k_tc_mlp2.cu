@@ -55,11 +55,16 @@ struct Mlp2Args {
   int M = 0, d = 0;
 };
 
-// GELU of a packed-half pair, result packed fp16 (the A operand of fc2): 9 HFMA2-pipe ops + 2 MUFU + 1 PRMT
+// GELU of a packed-half pair, result packed fp16 (the A operand of fc2), tanh form
+//     y = hx + hx * tanh(x * (c0 + c1 x^2)),  hx = x / 2,  c0 = sqrt(2/pi), c1 = 0.044715 c0
+// = 7 HFMA2-pipe ops + 2 MUFU + 1 PRMT per pair.  The argument is monotone, so no clamp is needed (x^2
+// overflowing to +inf in half precision gives tanh(+-inf) = +-1, the correct limit).  Against the exact erf
+// GELU of the reference (modeling.py:52) the form itself is off by <= 4.7e-4 absolute; measured on the logits
+// of conf 5 / conf 18 that is 2-4e-4, below the 7.6e-4 the fp16 rounding of the GELU tile contributes and far
+// inside the 2e-2 bf16-mode tolerance (the training path keeps the 3-term fit with 3e-5).
 __device__ __forceinline__ uint32_t gelu_h2(__half2 x) {
-  const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(100.f));
-  __half2 p = __hfma2(x2, __float2half2_rn(-3.58732362e-4f), __float2half2_rn(0.0370503451f));
-  p = __hfma2(x2, p, __float2half2_rn(0.797458471f));
+  const __half2 x2 = __hmul2(x, x);
+  const __half2 p = __hfma2(x2, __float2half2_rn(0.0356774081f), __float2half2_rn(0.797884561f));
   const __half2 u = __hmul2(x, p);
   uint32_t ti;
   asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
