@@ -59,6 +59,7 @@ SIGNATURES = {
     "vit3d_mlp_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "vit3d_mlp_supported": (_i, [_i, _i, _i]),
     "vit3d_mlp_ln_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _i, _i, _i, _p]),
+    "vit3d_mlp_lnf_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _i, _i, _i, _p]),
     "vit3d_mlp_ln_supported": (_i, [_i, _i, _i]),
     "vit3d_attn_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "vit3d_attn_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),

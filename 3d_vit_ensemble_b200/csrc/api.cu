@@ -294,7 +294,7 @@ int vit3d_mlp_fwd(const void* xn, const void* w1_lp, const float* b1, const void
   V3_REQUIRE(xn && w1_lp && b1 && w2_lp && b2 && residual && out, "mlp_fwd: null pointer");
   V3_REQUIRE(M >= 0 && H > 0 && d > 0, "mlp_fwd: bad shape");
   if (M == 0) return VIT3D_OK;
-  return tc_mlp2_fwd(xn, w1_lp, b1, w2_lp, b2, residual, out, nullptr, nullptr, 0.f, nullptr, M, H, d, as_stream(stream));
+  return tc_mlp2_fwd(xn, w1_lp, b1, w2_lp, b2, residual, out, nullptr, nullptr, 0.f, nullptr, 0, M, H, d, as_stream(stream));
 }
 int vit3d_mlp_supported(int M, int H, int d) { return tc_mlp2_supported(M, H, d) ? 1 : 0; }
 
@@ -305,7 +305,15 @@ int vit3d_mlp_ln_fwd(const void* xn, const void* w1_lp, const float* b1, const v
   V3_REQUIRE(xn && w1_lp && b1 && w2_h && b2 && residual && out && gamma && beta && ln_out, "mlp_ln_fwd: null pointer");
   V3_REQUIRE(M >= 0 && H > 0 && d > 0, "mlp_ln_fwd: bad shape");
   if (M == 0) return VIT3D_OK;
-  return tc_mlp2_fwd(xn, w1_lp, b1, w2_h, b2, residual, out, gamma, beta, eps, ln_out, M, H, d, as_stream(stream));
+  return tc_mlp2_fwd(xn, w1_lp, b1, w2_h, b2, residual, out, gamma, beta, eps, ln_out, 0, M, H, d, as_stream(stream));
+}
+int vit3d_mlp_lnf_fwd(const void* xn, const void* w1_lp, const float* b1, const void* w2_h, const float* b2,
+                      const float* residual, const float* gamma, const float* beta, float eps, float* ln_out, int M, int H,
+                      int d, vit3d_stream_t stream) {
+  V3_REQUIRE(xn && w1_lp && b1 && w2_h && b2 && residual && gamma && beta && ln_out, "mlp_lnf_fwd: null pointer");
+  V3_REQUIRE(M >= 0 && H > 0 && d > 0, "mlp_lnf_fwd: bad shape");
+  if (M == 0) return VIT3D_OK;
+  return tc_mlp2_fwd(xn, w1_lp, b1, w2_h, b2, residual, nullptr, gamma, beta, eps, ln_out, 1, M, H, d, as_stream(stream));
 }
 
 // ------------------------------------------------------------------------- attention core

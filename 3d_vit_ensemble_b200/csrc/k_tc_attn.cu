@@ -69,12 +69,28 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
+// Predicated stores as single instructions (the compiler turns `if (lane_predicate) *p = v;` into a divergent
+// branch with a BSSY/BSYNC pair and re-materialised descriptor registers around every store).
+__device__ __forceinline__ void st_global_f2_if(bool pred, float* p, float x, float y) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.global.v2.f32 [%0], {%1, %2};\n\t}" ::"l"(p), "f"(x), "f"(y),
+               "r"((uint32_t)pred)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_f1_if(bool pred, float* p, float x) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}" ::"l"(p), "f"(x), "r"((uint32_t)pred)
+               : "memory");
+}
+__device__ __forceinline__ void st_shared_u32_if(bool pred, uint32_t addr, uint32_t v) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.b32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"((uint32_t)pred)
+               : "memory");
+}
+
 // THREADS compute threads: 512 (16 warps) or 640 (20 warps), plus one producer warp.  A volume is HEADS * 5
 // (head, 16-row tile) tasks: 40 tasks take 3 rounds of 16 warps but 2 rounds of 20 (80 tasks: 5 vs 4).
 // The warps are only coupled through data: the producer warp refills a volume buffer when all compute warps
 // have released it (mbarrier with one arrival per warp), and every warp ships its own context tile, so a fast
 // warp walks on into the next volume instead of waiting at a block-wide barrier (15 % of the samples before).
-template <int D, int THREADS>
+template <int D, int THREADS, bool VIS>
 __global__ void __launch_bounds__(THREADS + 32, 1)
 attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, float* __restrict__ probs,
                    int B, float scale_log2e) {
@@ -152,73 +168,80 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
           }
         }
       }
-      // ---- softmax over the 65 valid keys (rows g and g+8 of the tile)
+      // ---- softmax over the 65 valid keys (rows g and g+8 of the tile).  Columns 0..63 (n-tiles 0..7) are
+      //      valid in every lane; column 64 is element [0] / [2] of n-tile 8 in the lanes with t == 0.
+      const bool tail = t == 0;
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int nt = 0; nt < 9; ++nt) {
-        const int c = nt * 8 + 2 * t;
-        if (c < AT_S) { mx0 = fmaxf(mx0, s[nt][0]); mx1 = fmaxf(mx1, s[nt][2]); }
-        if (c + 1 < AT_S) { mx0 = fmaxf(mx0, s[nt][1]); mx1 = fmaxf(mx1, s[nt][3]); }
+      for (int nt = 0; nt < 8; ++nt) {
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
       }
+      if (tail) { mx0 = fmaxf(mx0, s[8][0]); mx1 = fmaxf(mx1, s[8][2]); }
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float m0 = mx0 * scale_log2e, m1 = mx1 * scale_log2e;
       float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-      for (int nt = 0; nt < 9; ++nt) {
-        const int c = nt * 8 + 2 * t;
-        const bool v0 = c < AT_S, v1 = c + 1 < AT_S;
-        s[nt][0] = v0 ? ex2_approx((s[nt][0] - mx0) * scale_log2e) : 0.f;
-        s[nt][1] = v1 ? ex2_approx((s[nt][1] - mx0) * scale_log2e) : 0.f;
-        s[nt][2] = v0 ? ex2_approx((s[nt][2] - mx1) * scale_log2e) : 0.f;
-        s[nt][3] = v1 ? ex2_approx((s[nt][3] - mx1) * scale_log2e) : 0.f;
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = ex2_approx(fmaf(s[nt][0], scale_log2e, -m0));
+        s[nt][1] = ex2_approx(fmaf(s[nt][1], scale_log2e, -m0));
+        s[nt][2] = ex2_approx(fmaf(s[nt][2], scale_log2e, -m1));
+        s[nt][3] = ex2_approx(fmaf(s[nt][3], scale_log2e, -m1));
         sum0 += s[nt][0] + s[nt][1];
         sum1 += s[nt][2] + s[nt][3];
       }
+      s[8][0] = tail ? ex2_approx(fmaf(s[8][0], scale_log2e, -m0)) : 0.f;
+      s[8][2] = tail ? ex2_approx(fmaf(s[8][2], scale_log2e, -m1)) : 0.f;
+      s[8][1] = s[8][3] = 0.f;
+      sum0 += s[8][0];
+      sum1 += s[8][2];
       sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
       sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
       sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
       sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
       const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
       const int row0 = r0 + g, row1 = r0 + g + 8;
-      if (probs) {
-        // The probabilities leave from the accumulator registers.  What bounds this kernel with vis=True is the
-        // L1 store path (one wavefront per row and instruction), so every store carries a PAIR of columns as
-        // one 8-byte word.  Rows of 65 floats start at alternating 8-byte phases: where (head block + row) is
+      // which of this lane's two rows exist: both in the row tiles 0..3, only row 64 (g == 0) in tile 4.
+      // `full` is warp-uniform, so the stores below are predicated instructions, not divergent branches.
+      const bool full = rt < 4;
+      const bool w0 = full || g == 0, w1 = full;
+      if constexpr (VIS) {
+        // The probabilities leave from the accumulator registers, normalised in place (the P V product below
+        // then needs no rescaling).  What bounds this kernel with vis=True is the L1 store path and the issue
+        // slots around it, so every store carries a PAIR of columns as one 8-byte word and the code is
+        // branch-free.  Rows of 65 floats start at alternating 8-byte phases: where (head block + row) is
         // even the pair is this thread's own (c, c+1); where it is odd the aligned pair is (c+1, c+2) and
-        // column c+2 comes from the neighbour lane of the quad by one shuffle.
-        const int bh = b * HEADS + h;
-        float* p0 = probs + ((size_t)bh * AT_S + row0) * AT_S;
-        float* p1 = probs + ((size_t)bh * AT_S + row1) * AT_S;
-        const bool odd = ((bh + row0) & 1) != 0;          // row1 = row0 + 8 has the same parity
-        const int src = (lane & ~3) | ((t + 1) & 3);
+        // column c+2 comes from the neighbour lane of the quad by one shuffle.  The pairs of n-tiles 0..7
+        // cover columns 0..63 (even rows) or 1..64 (odd rows); the remaining column - 64 or 0 - lives in the
+        // lane with t == 0 either way.
 #pragma unroll
         for (int nt = 0; nt < 9; ++nt) {
-          const int c = nt * 8 + 2 * t;
+          s[nt][0] *= inv0; s[nt][1] *= inv0;
+          s[nt][2] *= inv1; s[nt][3] *= inv1;
+        }
+        const int bh = b * HEADS + h;
+        const bool odd = ((bh + row0) & 1) != 0;          // row1 = row0 + 8 has the same parity
+        float* p0 = probs + ((size_t)bh * AT_S + row0) * AT_S + 2 * t + (odd ? 1 : 0);
+        float* p1 = p0 + 8 * AT_S;
+        const int src = (lane & ~3) | ((t + 1) & 3);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
           // what this lane hands to its left neighbour: its column c, or (t == 0) the first column of the next tile
-          const float n0 = __shfl_sync(0xffffffffu, t == 0 ? s[nt + 1][0] : s[nt][0], src) * inv0;
-          const float n1 = __shfl_sync(0xffffffffu, t == 0 ? s[nt + 1][2] : s[nt][2], src) * inv1;
-          const float a0 = s[nt][0] * inv0, a1 = s[nt][1] * inv0, b0 = s[nt][2] * inv1, b1 = s[nt][3] * inv1;
-          if (!odd) {
-            if (row0 < AT_S) {
-              if (c + 1 < AT_S) *reinterpret_cast<float2*>(p0 + c) = make_float2(a0, a1);
-              else if (c < AT_S) p0[c] = a0;
-            }
-            if (row1 < AT_S) {
-              if (c + 1 < AT_S) *reinterpret_cast<float2*>(p1 + c) = make_float2(b0, b1);
-              else if (c < AT_S) p1[c] = b0;
-            }
-          } else {
-            if (row0 < AT_S) {
-              if (c + 2 < AT_S) *reinterpret_cast<float2*>(p0 + c + 1) = make_float2(a1, n0);
-              if (c == 0) p0[0] = a0;
-            }
-            if (row1 < AT_S) {
-              if (c + 2 < AT_S) *reinterpret_cast<float2*>(p1 + c + 1) = make_float2(b1, n1);
-              if (c == 0) p1[0] = b0;
-            }
-          }
+          const float n0 = __shfl_sync(0xffffffffu, tail ? s[nt + 1][0] : s[nt][0], src);
+          const float n1 = __shfl_sync(0xffffffffu, tail ? s[nt + 1][2] : s[nt][2], src);
+          const float2 v0 = make_float2(odd ? s[nt][1] : s[nt][0], odd ? n0 : s[nt][1]);
+          const float2 v1 = make_float2(odd ? s[nt][3] : s[nt][2], odd ? n1 : s[nt][3]);
+          st_global_f2_if(w0, p0 + nt * 8, v0.x, v0.y);
+          st_global_f2_if(w1, p1 + nt * 8, v1.x, v1.y);
+        }
+        {
+          // in the lanes with t == 0, p0 points at column (odd ? 1 : 0)
+          const int off = odd ? -1 : 64;
+          st_global_f1_if(tail && w0, p0 + off, odd ? s[0][0] : s[8][0]);
+          st_global_f1_if(tail && w1, p1 + off, odd ? s[0][2] : s[8][2]);
         }
       }
       // ---- O = P V  (P from the accumulator registers; keys 65..79 carry p = 0)
@@ -247,8 +270,9 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
 #pragma unroll
       for (int dt = 0; dt < DT; ++dt) {
         const int col = h * D + dt * 8 + 2 * t;
-        if (row0 < AT_S) *reinterpret_cast<uint32_t*>(base + row0 * AT_PITCH + col * 2) = pack_bf16(o[dt][0] * inv0, o[dt][1] * inv0);
-        if (row1 < AT_S) *reinterpret_cast<uint32_t*>(base + row1 * AT_PITCH + col * 2) = pack_bf16(o[dt][2] * inv1, o[dt][3] * inv1);
+        const float c0 = VIS ? 1.f : inv0, c1 = VIS ? 1.f : inv1;      // VIS: P was normalised before the product
+        st_shared_u32_if(w0, sb + row0 * AT_PITCH + col * 2, pack_bf16(o[dt][0] * c0, o[dt][1] * c0));
+        st_shared_u32_if(w1, sb + row1 * AT_PITCH + col * 2, pack_bf16(o[dt][2] * c1, o[dt][3] * c1));
       }
       __syncwarp();
       {
@@ -273,9 +297,9 @@ bool tc_attn_supported(int S, int heads, int D) {
   return S == AT_S && heads * D == AT_A && (D == 16 || D == 32 || D == 64);
 }
 
-template <int D, int THREADS>
-static int launch_attn(const void* qkv, void* ctx, float* probs, int B, cudaStream_t st) {
-  auto kern = attn_fwd_tc_kernel<D, THREADS>;
+template <int D, int THREADS, bool VIS>
+static int launch_attn_v(const void* qkv, void* ctx, float* probs, int B, cudaStream_t st) {
+  auto kern = attn_fwd_tc_kernel<D, THREADS, VIS>;
   V3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
   const int grid = B < sm_count() ? B : sm_count();
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)D);
@@ -284,12 +308,18 @@ static int launch_attn(const void* qkv, void* ctx, float* probs, int B, cudaStre
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
-// 0 = automatic: 20 warps (a volume of 8 heads is exactly two rounds of (head, row-tile) tasks), except for
-// 16 heads with the probabilities written, where 16 warps measured faster (120 vs 135 us at batch 1024)
+template <int D, int THREADS>
+static int launch_attn(const void* qkv, void* ctx, float* probs, int B, cudaStream_t st) {
+  return probs ? launch_attn_v<D, THREADS, true>(qkv, ctx, probs, B, st) : launch_attn_v<D, THREADS, false>(qkv, ctx, probs, B, st);
+}
+// 0 = automatic.  20 warps make a volume of 8 heads exactly two rounds of (head, row-tile) tasks and are the
+// faster choice without the probabilities; with them (vis=True) the kernel is bound by its store path and 16
+// warps measured faster for 8 and 16 heads (63.5 vs 67.6 us, 110.9 vs 111.3 us at batch 1024), 20 for 4 heads
+// (45.7 vs 49.9 us).
 static int attn_threads(int D, bool vis) {
   const int v = tuning(VIT3D_TUNE_ATTN_THREADS);
   if (v == 512 || v == 640) return v;
-  return (D == 16 && vis) ? 512 : 640;
+  return (D <= 32 && vis) ? 512 : 640;
 }
 
 int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int heads, int D, cudaStream_t st) {

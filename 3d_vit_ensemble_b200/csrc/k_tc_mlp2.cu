@@ -74,7 +74,11 @@ __device__ __forceinline__ uint32_t gelu_h2(__half2 x) {
   return *reinterpret_cast<const uint32_t*>(&y);
 }
 
-template <bool MC, bool LN>
+// LN: 0 = y only; 1 = y and bf16 LayerNorm(y) (the next Block's attention_norm); 2 = fp32 LayerNorm(y) ONLY
+// (encoder_norm after the last Block, modeling.py:253: the block output itself is not needed at inference, so
+// the kernel writes the normalised rows through tmY and the separate LayerNorm pass - 68 MB in, 68 MB out at
+// batch 1024 - disappears)
+template <bool MC, int LN>
 __global__ void __cluster_dims__(MC ? 2 : 1, 1, 1) __launch_bounds__(M2_THREADS, 1)
 tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmY,
@@ -344,29 +348,32 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           const float v1 = __uint_as_float(r[4 * j + 1]) + b.y + __uint_as_float(x.y);
           const float v2 = __uint_as_float(r[4 * j + 2]) + b.z + __uint_as_float(x.z);
           const float v3 = __uint_as_float(r[4 * j + 3]) + b.w + __uint_as_float(x.w);
-          st_shared_v4(a, __float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
-          if constexpr (LN) {
+          if constexpr (LN != 2)
+            st_shared_v4(a, __float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
+          if constexpr (LN != 0) {
             s1 += (v0 + v1) + (v2 + v3);
             s2 = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, s2))));
             r[4 * j] = __float_as_uint(v0); r[4 * j + 1] = __float_as_uint(v1);
             r[4 * j + 2] = __float_as_uint(v2); r[4 * j + 3] = __float_as_uint(v3);
           }
         }
-        if constexpr (LN) tmem_st_32x32b_x32(taddr + p * 32, r);
-        fence_proxy_async_smem();
+        if constexpr (LN != 0) tmem_st_32x32b_x32(taddr + p * 32, r);
+        if constexpr (LN != 2) fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tmY, p ? bufx_s : buf_s, part * 64 + p * 32, m_base);
-          bulk_store_commit();
+        if constexpr (LN != 2) {
+          if (lane == 0) {
+            tma_store_2d(&tmY, p ? bufx_s : buf_s, part * 64 + p * 32, m_base);
+            bulk_store_commit();
+          }
         }
       }
       rphase ^= 1;
       if (lane == 0) {
-        bulk_store_wait_read();                       // both result panels have been read out of shared memory
+        if constexpr (LN != 2) bulk_store_wait_read();   // both result panels have been read out of shared memory
         mbar_arrive(xpanel_free);                     // the producer may load the next tile's xn
       }
       __syncwarp();
-      if constexpr (LN) {
+      if constexpr (LN != 0) {
         tmem_st_wait();
         *reinterpret_cast<float2*>(buf_ptr + lane * 8) = make_float2(s1, s2);
         asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(128) : "memory");
@@ -380,6 +387,38 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         const float mean = t1 * (1.0f / M2_H);
         const float rstd = rsqrtf(fmaxf(t2 * (1.0f / M2_H) - mean * mean, 0.f) + args.eps);
         const float shift = -mean * rstd;
+        if constexpr (LN == 2) {
+          // fp32 rows, one [32 x 32] panel at a time through the warp's 4 KB buffer (SWIZZLE_128B, as the y panels)
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(taddr + p * 32, r);
+            tmem_ld_wait();
+            if (p == 1) {
+              if (lane == 0) bulk_store_wait_read();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 ga = __ldg(reinterpret_cast<const float4*>(args.gamma + part * 64 + p * 32) + j);
+              const float4 be = __ldg(reinterpret_cast<const float4*>(args.beta + part * 64 + p * 32) + j);
+              const float y0 = fmaf(fmaf(__uint_as_float(r[4 * j]), rstd, shift), ga.x, be.x);
+              const float y1 = fmaf(fmaf(__uint_as_float(r[4 * j + 1]), rstd, shift), ga.y, be.y);
+              const float y2 = fmaf(fmaf(__uint_as_float(r[4 * j + 2]), rstd, shift), ga.z, be.z);
+              const float y3 = fmaf(fmaf(__uint_as_float(r[4 * j + 3]), rstd, shift), ga.w, be.w);
+              st_shared_v4(my_row + ((j ^ sl7) << 4), __float_as_uint(y0), __float_as_uint(y1), __float_as_uint(y2),
+                           __float_as_uint(y3));
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmY, buf_s, part * 64 + p * 32, m_base);
+              bulk_store_commit();
+            }
+          }
+          if (lane == 0) bulk_store_wait_read();
+          __syncwarp();
+        } else {
         const int sw3 = (lane >> 1) & 3;
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
@@ -413,6 +452,7 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           bulk_store_wait_read();
         }
         __syncwarp();
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -428,7 +468,7 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
 bool tc_mlp2_supported(int M, int H, int d) { return M > 0 && H == M2_H && d % M2_NC == 0 && d >= M2_NC; }
 
-template <bool MC, bool LN>
+template <bool MC, int LN>
 static int launch_mlp2(const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& ty,
                        const CUtensorMap& tr, const CUtensorMap& tl, const Mlp2Args& a, cudaStream_t st) {
   auto kern = tc_mlp2_kernel<MC, LN>;
@@ -448,11 +488,13 @@ static int launch_mlp2(const CUtensorMap& tx, const CUtensorMap& tw1, const CUte
   return VIT3D_OK;
 }
 
-// xn [M,256] bf16, w1 [d,256] bf16, w2 [256,d] FP16, residual / y [M,256] fp32 (may alias), ln_out [M,256] bf16 or null
+// xn [M,256] bf16, w1 [d,256] bf16, w2 [256,d] FP16, residual / y [M,256] fp32 (may alias), ln_out [M,256] bf16 or null.
+// ln_f32 != 0: ln_out is FP32 and is the only output (y is not written and may be null).
 int tc_mlp2_fwd(const void* xn, const void* w1, const float* b1, const void* w2_h, const float* b2, const float* residual,
-                float* y, const float* gamma, const float* beta, float eps, void* ln_out, int M, int H, int d,
+                float* y, const float* gamma, const float* beta, float eps, void* ln_out, int ln_f32, int M, int H, int d,
                 cudaStream_t st) {
   if (!tc_mlp2_supported(M, H, d)) V3_UNSUPPORTED("fused MLP: unsupported shape M=%d H=%d d=%d", M, H, d);
+  if (ln_f32 && !ln_out) { set_error("fused MLP: fp32 LayerNorm output requested without a buffer"); return VIT3D_ERR_INVALID; }
   const bool pair = M > 128 && tuning(VIT3D_TUNE_MLP_PAIR) != 0;
   CUtensorMap tx, tw1, tw2, ty, tr, tl;
   int rc = make_tmap_2d(&tx, xn, 2, M, H, H, 128, 64, 128);
@@ -461,19 +503,24 @@ int tc_mlp2_fwd(const void* xn, const void* w1, const float* b1, const void* w2_
   if (rc != VIT3D_OK) return rc;
   rc = make_tmap_2d(&tw2, w2_h, 2, H, d, d, pair ? 128 : 256, 64, 128);    // W2 [256, d] (fp16 bits)
   if (rc != VIT3D_OK) return rc;
-  rc = make_tmap_2d(&ty, y, 4, M, H, H, 32, 32, 128);
+  rc = make_tmap_2d(&ty, ln_f32 ? ln_out : (void*)y, 4, M, H, H, 32, 32, 128);
   if (rc != VIT3D_OK) return rc;
   rc = make_tmap_2d(&tr, residual, 4, M, H, H, 32, 32, 128);
   if (rc != VIT3D_OK) return rc;
   tl = ty;
-  if (ln_out) {
+  if (ln_out && !ln_f32) {
     rc = make_tmap_2d(&tl, ln_out, 2, M, H, H, 32, 32, 64);
     if (rc != VIT3D_OK) return rc;
   }
   Mlp2Args a;
   a.b1 = b1; a.b2 = b2; a.gamma = gamma; a.beta = beta; a.eps = eps; a.M = M; a.d = d;
-  if (pair) return ln_out ? launch_mlp2<true, true>(tx, tw1, tw2, ty, tr, tl, a, st) : launch_mlp2<true, false>(tx, tw1, tw2, ty, tr, tl, a, st);
-  return ln_out ? launch_mlp2<false, true>(tx, tw1, tw2, ty, tr, tl, a, st) : launch_mlp2<false, false>(tx, tw1, tw2, ty, tr, tl, a, st);
+  const int mode = ln_f32 ? 2 : (ln_out ? 1 : 0);
+  if (pair) {
+    if (mode == 2) return launch_mlp2<true, 2>(tx, tw1, tw2, ty, tr, tl, a, st);
+    return mode ? launch_mlp2<true, 1>(tx, tw1, tw2, ty, tr, tl, a, st) : launch_mlp2<true, 0>(tx, tw1, tw2, ty, tr, tl, a, st);
+  }
+  if (mode == 2) return launch_mlp2<false, 2>(tx, tw1, tw2, ty, tr, tl, a, st);
+  return mode ? launch_mlp2<false, 1>(tx, tw1, tw2, ty, tr, tl, a, st) : launch_mlp2<false, 0>(tx, tw1, tw2, ty, tr, tl, a, st);
 }
 
 }  // namespace vit3d

@@ -41,7 +41,7 @@ int tc_patch_embed_fwd(const float* x, const float* w, const float* bias, const 
 // k_tc_mlp2.cu: chunked fused MLP (256 fc1 columns per chunk, optional CTA pairs), + residual, + fused LayerNorm
 bool tc_mlp2_supported(int M, int H, int d);
 int tc_mlp2_fwd(const void* xn, const void* w1, const float* b1, const void* w2_h, const float* b2, const float* residual,
-                float* y, const float* gamma, const float* beta, float eps, void* ln_out, int M, int H, int d,
+                float* y, const float* gamma, const float* beta, float eps, void* ln_out, int ln_f32, int M, int H, int d,
                 cudaStream_t st);
 
 bool tc_attn_supported(int S, int heads, int D);

@@ -377,6 +377,23 @@ def mlp_fused_ln(xn, w1, b1, w2, b2, residual, ln_weight, ln_bias, eps):
     return out.reshape(residual.shape), yn.reshape(residual.shape)
 
 
+def mlp_fused_final_ln(xn, w1, b1, w2, b2, residual, ln_weight, ln_bias, eps):
+    """Inference-only: the last Block's MLP with the encoder's final LayerNorm folded in (modeling.py:196, :253).
+    Returns `LayerNorm(residual + fc2(GELU(fc1(xn))))` as fp32; the un-normalised sum is never written."""
+    _need_cuda(xn, w1, b1, w2, b2, residual, ln_weight, ln_bias)
+    H = xn.shape[-1]
+    d = w1.shape[0]
+    x2 = _c(xn).reshape(-1, H)
+    if x2.dtype != torch.bfloat16:
+        x2 = x2.to(torch.bfloat16)
+    M = x2.shape[0]
+    res = _c(residual.float()).reshape(M, H)
+    out = torch.empty(M, H, device=xn.device, dtype=torch.float32)
+    call("vit3d_mlp_lnf_fwd", ptr(x2), ptr(lp_weight(w1, "bf16")), ptr(_c(b1)), ptr(lp_weight(w2, "f16")), ptr(_c(b2)),
+         ptr(res), ptr(_c(ln_weight)), ptr(_c(ln_bias)), float(eps), ptr(out), M, H, d, stream())
+    return out.reshape(residual.shape)
+
+
 def mlp_fused_ln_supported(M: int, H: int, d: int) -> bool:
     return bool(_lib.lib().vit3d_mlp_ln_supported(M, H, d))
 

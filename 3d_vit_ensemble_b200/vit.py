@@ -103,16 +103,24 @@ class Mlp(nn.Module):
         nn.init.normal_(self.fc1.bias, std=1e-6)
         nn.init.normal_(self.fc2.bias, std=1e-6)
 
-    def forward(self, x, residual=None, step=None, next_ln=None):
+    def forward(self, x, residual=None, step=None, next_ln=None, final=False):
         """next_ln (inference): LayerNorm applied to the block output inside the fc2 kernel; the call then
-        returns (out, LN(out) or None)."""
+        returns (out, LN(out) or None).  final=True (last Block, next_ln = encoder_norm): the fused kernel
+        writes ONLY the fp32 LayerNorm output and the call returns (None, LN(out)); if the fused kernel
+        cannot run it returns (out, None) like the other fallbacks."""
         if next_ln is not None:
             prec = self.precision
             infer = (not (self.training and self.dropout.p > 0.0) and residual is not None
                      and not torch.is_grad_enabled())
-            if (infer and self.fused and prec == "bf16" and self.fc1.weight.is_contiguous()
-                    and self.fc2.weight.is_contiguous()
-                    and F.mlp_fused_ln_supported(x.numel() // x.shape[-1], x.shape[-1], self.fc1.weight.shape[0])):
+            can_fuse = (infer and self.fused and prec == "bf16" and self.fc1.weight.is_contiguous()
+                        and self.fc2.weight.is_contiguous()
+                        and F.mlp_fused_ln_supported(x.numel() // x.shape[-1], x.shape[-1], self.fc1.weight.shape[0]))
+            if final:
+                if can_fuse:
+                    return None, F.mlp_fused_final_ln(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
+                                                      residual, next_ln.weight, next_ln.bias, next_ln.eps)
+                return self.forward(x, residual=residual, step=step), None
+            if can_fuse:
                 # one kernel: fc1 -> GELU -> fc2 -> + residual -> next LayerNorm
                 return F.mlp_fused_ln(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, residual,
                                       next_ln.weight, next_ln.bias, next_ln.eps)
@@ -192,11 +200,12 @@ class Block(nn.Module):
         self.attn = Attention(config, vis)
         self.precision = F.get_precision()
 
-    def forward(self, x, step=None, normed=None, next_ln=None):
+    def forward(self, x, step=None, normed=None, next_ln=None, final=False):
         """The reference signature is forward(x).  `normed` / `next_ln` are the inference fast path of
         Encoder.forward: `normed` = attention_norm(x) already produced by the previous block's fc2 kernel,
         `next_ln` = the LayerNorm that will consume this block's output (the next block's attention_norm);
-        with next_ln the call returns (x, weights, next_ln(x) or None)."""
+        with next_ln the call returns (x, weights, next_ln(x) or None).  final=True: this is the last Block and
+        next_ln the encoder_norm - when the fused kernel runs, x comes back as None (only next_ln(x), fp32, exists)."""
         prec = self.precision
         x = x.float()
         h = x
@@ -214,7 +223,7 @@ class Block(nn.Module):
         if xn is None:
             xn = F.LayerNormFn.apply(x, self.ffn_norm.weight, self.ffn_norm.bias, self.ffn_norm.eps, lp)
         if next_ln is not None and fuse:
-            x, xn_next = self.ffn(xn, residual=h, step=step, next_ln=next_ln)
+            x, xn_next = self.ffn(xn, residual=h, step=step, next_ln=next_ln, final=final)
             return x, weights, xn_next
         x = self.ffn(xn, residual=h, step=step)
         if next_ln is not None:
@@ -249,6 +258,15 @@ class Encoder(nn.Module):
             if chain and i + 1 < n_layers:
                 hidden_states, weights, normed = layer_block(hidden_states, step=step, normed=normed,
                                                              next_ln=self.layer[i + 1].attention_norm)
+            elif chain:
+                # last Block: encoder_norm rides in its MLP kernel, which then writes only `encoded`
+                hidden_states, weights, encoded = layer_block(hidden_states, step=step, normed=normed,
+                                                              next_ln=self.encoder_norm, final=True)
+                if self.vis:
+                    attn_weights.append(weights)
+                if encoded is not None:
+                    return encoded, attn_weights
+                break
             else:
                 hidden_states, weights = layer_block(hidden_states, step=step, normed=normed)
                 normed = None

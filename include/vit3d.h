@@ -155,6 +155,13 @@ int vit3d_mlp_ln_fwd(const void* xn, const void* w1_lp, const float* b1, const v
                      const float* residual, float* out, const float* gamma, const float* beta, float eps, void* ln_out,
                      int M, int H, int d, vit3d_stream_t stream);
 int vit3d_mlp_ln_supported(int M, int H, int d);
+/* The LAST Block's MLP with the encoder's final LayerNorm (Encoder.forward, modeling.py:253) folded in:
+ * ln_out[M,H] = LayerNorm(residual + fc2(gelu(fc1(xn) + b1)) + b2) * gamma + beta as FP32 - the `encoded`
+ * tensor VisionTransformer.forward returns (modeling.py:280,288).  The un-normalised block output is not
+ * written (nothing reads it at inference).  Same shape support as vit3d_mlp_ln_fwd. */
+int vit3d_mlp_lnf_fwd(const void* xn, const void* w1_lp, const float* b1, const void* w2_h, const float* b2,
+                      const float* residual, const float* gamma, const float* beta, float eps, float* ln_out, int M, int H,
+                      int d, vit3d_stream_t stream);
 
 /* ---------------------------------------------------------------- a2: scaled-dot-product attention core
  * scores = q k^T / sqrt(D); probs = softmax(scores); ctx = probs v  (modeling.py:83-96).

@@ -58,7 +58,7 @@ def test_tc_linear_matches_fp64(prec, shape, mode):
         assert errp <= tol, (errp, tol)
 
 
-@pytest.mark.parametrize("B", [1, 2, 3, 37])
+@pytest.mark.parametrize("B", [1, 2, 3, 37, 597])
 @pytest.mark.parametrize("H", [256, 64])
 def test_tc_patch_embedding_matches_oracle(B, H):
     """TMA-im2col TF32 patch embedding (+bias, +position rows, cls rows) vs the fp64 oracle."""
@@ -239,3 +239,48 @@ def test_fused_mlp_layernorm_matches_fp64(M, d, pair):
     ref_n = (ref - mu) / torch.sqrt(var + 1e-6) * gamma.double() + beta.double()
     en = float((yn.double() - ref_n).abs().max())
     assert np.isfinite(en) and en <= 0.02 + float(ref_n.abs().max()) / 128, en
+
+
+@pytest.mark.parametrize("M", [65, 130, 4160, 19000, 66560])
+@pytest.mark.parametrize("d", [2048, 3072])
+@pytest.mark.parametrize("pair", [0, 1])
+def test_fused_mlp_final_layernorm_fp32(M, d, pair):
+    """vit3d_mlp_lnf_fwd (last Block: encoder_norm folded into the MLP kernel, fp32 output only) vs an fp64
+    evaluation on the same operands, and vs LayerNorm of the y that vit3d_mlp_ln_fwd writes; the residual
+    buffer must be left untouched (the kernel has no y output)."""
+    torch.manual_seed(M + d + pair + 1)
+    H = 256
+    xn = torch.randn(M, H, device=DEV).to(torch.bfloat16)
+    w1 = (torch.randn(d, H, device=DEV) / H ** 0.5)
+    w2 = (torch.randn(H, d, device=DEV) / d ** 0.5)
+    b1 = torch.randn(d, device=DEV) * 0.1
+    b2 = torch.randn(H, device=DEV) * 0.1
+    res = torch.randn(M, H, device=DEV)
+    gamma = 1.0 + 0.1 * torch.randn(H, device=DEV)
+    beta = 0.1 * torch.randn(H, device=DEV)
+    w1l, w2l = w1.to(torch.bfloat16), w2.to(torch.float16)
+    res_in = res.clone()
+    enc = torch.full((M, H), float("nan"), device=DEV)
+    y = torch.empty(M, H, device=DEV)
+    yn = torch.empty(M, H, device=DEV, dtype=torch.bfloat16)
+    lib().vit3d_set_tuning(5, pair)
+    try:
+        call("vit3d_mlp_lnf_fwd", ptr(xn), ptr(w1l), ptr(b1), ptr(w2l), ptr(b2), ptr(res_in), ptr(gamma), ptr(beta), 1e-6,
+             ptr(enc), M, H, d, stream())
+        call("vit3d_mlp_ln_fwd", ptr(xn), ptr(w1l), ptr(b1), ptr(w2l), ptr(b2), ptr(res), ptr(y), ptr(gamma), ptr(beta),
+             1e-6, ptr(yn), M, H, d, stream())
+        torch.cuda.synchronize()
+    finally:
+        lib().vit3d_set_tuning(5, 0)
+    assert torch.equal(res_in, res)
+    # same accumulators, same statistics: LayerNorm of the other kernel's fp32 y agrees to fp32 rounding
+    ln_y = torch.nn.functional.layer_norm(y.double(), (H,), gamma.double(), beta.double(), 1e-6)
+    e1 = float((enc.double() - ln_y).abs().max())
+    assert np.isfinite(e1) and e1 <= 2e-5 * max(1.0, float(ln_y.abs().max())), e1
+    if M <= 19000:
+        h = xn.double() @ w1l.double().t() + b1.double()
+        a = gelu(h).to(torch.float16).double()
+        ref = a @ w2l.double().t() + b2.double() + res.double()
+        ref_n = torch.nn.functional.layer_norm(ref, (H,), gamma.double(), beta.double(), 1e-6)
+        en = float((enc.double() - ref_n).abs().max())
+        assert en <= 0.02, en

@@ -130,6 +130,19 @@ for pair in (0, 1):
                                ptr(gamma), ptr(beta), 1e-6, ptr(yn), M, H, d, stream())),
            4.0 * M * d * H, M * H * 2 + 2 * M * H * 4 + M * H * 2)
 L.vit3d_set_tuning(5, 0)
+vol = torch.randn(B, 1, 128, 128, 5, device=dev)
+wp = torch.randn(H, 1, 16, 16, 5, device=dev) * 0.02
+bp = torch.randn(H, device=dev) * 0.01
+cls = torch.randn(1, 1, H, device=dev) * 0.02
+pos = torch.randn(1, 65, H, device=dev) * 0.02
+tok = torch.empty(B, 65, H, device=dev)
+report("patch embedding (TF32, TMA im2col)",
+       timeit(lambda: call("vit3d_patch_embed_fwd", ptr(vol), ptr(wp), ptr(bp), ptr(cls), ptr(pos), ptr(tok), B, 128, 128, 5,
+                           16, 16, 5, H, PREC["bf16"], None, 0, stream())),
+       2.0 * B * 64 * 1280 * H, B * 327680 + B * 65 * H * 4)
+report("fused MLP + final LN (fp32 out only)",
+       timeit(lambda: call("vit3d_mlp_lnf_fwd", ptr(xn), ptr(wl1), ptr(b1), ptr(w2h), ptr(b2), ptr(x32), ptr(gamma), ptr(beta),
+                           1e-6, ptr(y32), M, H, d, stream())), 4.0 * M * d * H, M * H * 2 + 2 * M * H * 4)
 report("LayerNorm fp32 -> bf16",
        timeit(lambda: call("vit3d_ln_fwd", ptr(x32), ptr(gamma), ptr(beta), ptr(yn), 1, ptr(mean), ptr(rstd), M, H, 1e-6,
                            stream())), 8.0 * M * H, M * H * 4 + M * H * 2)
