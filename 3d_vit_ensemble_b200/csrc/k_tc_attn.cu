@@ -139,7 +139,10 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
     mbar_wait(&full[buf], (it >> 1) & 1);
     const uint32_t sb = smem_u32(smem + buf * AT_BUF);
 
-    for (int task = warp; task < HEADS * 5; task += NW) {
+    // HEADS * 5 tasks over NW warps: 40 over 16 is 2.5 per warp.  The warps are only coupled through the
+    // double-buffered volume images, so the half with three tasks in this volume takes two in the next one
+    // (the assignment rotates by NW / 2 per volume) and every warp does five tasks per two volumes.
+    for (int task = (warp + (it & 1) * (NW / 2)) % NW; task < HEADS * 5; task += NW) {
       const int h = task / 5, rt = task % 5;
       const int r0 = rt * 16;
       // ---- Q fragments (A operand), rows clamped to the last token
