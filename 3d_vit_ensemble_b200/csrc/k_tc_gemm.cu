@@ -227,9 +227,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (!slab_ready) { mbar_wait(slab_full, 0); slab_ready = true; }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
+        // lean hand-shake (k_tc_mlp2.cu explains why): no tcgen05 fence after an operand k-block has landed (the
+        // mbarrier's complete_tx orders the TMA writes before the MMAs' reads), the tile's commit rides in the
+        // election of its last k-block
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
           const uint64_t ad = ring_desc + (uint64_t)((stage * stage_bytes) >> 4);
           const uint64_t bd = stat ? slab_desc + (uint64_t)((kb * Cfg::B_BYTES) >> 4) : ad + (uint64_t)(Cfg::A_BYTES >> 4);
           if (elect_one()) {
@@ -237,12 +239,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int k = 0; k < 4; ++k)     // 4 x 32 bytes of K per stage
               umma<TF32>(d_tmem, ad + k * kstep, bd + k * kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+            if (kb == kb1 - 1) umma_commit(&tmem_full[buf]);       // accumulator ready for the epilogue
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (elect_one()) umma_commit(&tmem_full[buf]);       // accumulator ready for the epilogue
-        __syncwarp();
       }
     }
     __syncwarp();

@@ -131,21 +131,21 @@ tc_gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * RS_BN;
+        // lean hand-shake (k_tc_mlp2.cu explains why): no tcgen05 fence after an operand k-block has landed, the
+        // tile's commit rides in the election of its last k-block
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
           const uint64_t ad = ring_desc + (uint64_t)((stage * RS_STAGE_BYTES) >> 4);
           const uint64_t bd = ad + (uint64_t)(RS_A_BYTES >> 4);
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma<false>(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             umma_commit(&empty_bar[stage]);
+            if (kb == nkb - 1) umma_commit(&tmem_full[buf]);
           }
           __syncwarp();
           if (++stage == RS_STAGES) { stage = 0; phase ^= 1; }
         }
-        if (elect_one()) umma_commit(&tmem_full[buf]);
-        __syncwarp();
       }
     }
     __syncwarp();

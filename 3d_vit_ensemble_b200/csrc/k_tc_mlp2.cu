@@ -198,25 +198,29 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           // ---- fc1(s): acc1 = xn * W1[s]^T
           mbar_wait(acc1_empty, (g1 & 1) ^ 1);          // the GELU warps have read the previous chunk out
           tc_fence_after();
+          // Every hand-shake between two groups of MMAs (barrier wait, election, commit) is a bubble in the tensor
+          // pipe - the issue queue is only ~2 MMAs deep (tools/mma_pipe_bench.cu: ~200 cycles per 4-MMA stage) -
+          // so the loop carries no instruction it does not need: no tcgen05 fence after a weight k-block has
+          // landed (the mbarrier's complete_tx already orders the TMA writes before the MMAs' reads; the fence
+          // above pairs with the epilogue warps' tcgen05.ld), and the group's commits ride in the election of its
+          // last k-block.
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) {
             mbar_wait(&w_full[stage], wphase);
-            tc_fence_after();
             const uint64_t ad = xdesc0 + (uint64_t)(kb * 1024);                     // k-block kb: + 16 KB (>> 4)
             const uint64_t bd = wdesc0 + (uint64_t)(stage * (W_BYTES >> 4));
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) umma<false>(tmem_base, ad + 2 * k, bd + 2 * k, idesc1, (kb | k) ? 1u : 0u);
               release_slot(&w_empty[stage]);
+              if (kb == 3) {
+                umma_commit(acc1_full);
+                if (s == nch - 1) umma_commit(x_empty);    // xn may be replaced by the next tile's
+              }
             }
             __syncwarp();
             if (++stage == NST) { stage = 0; wphase ^= 1; }
           }
-          if (elect_one()) {
-            umma_commit(acc1_full);
-            if (s == nch - 1) umma_commit(x_empty);      // xn may be replaced by the next tile's
-          }
-          __syncwarp();
           ++g1;
         }
         if (s >= 1) {
@@ -228,7 +232,6 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) {
             mbar_wait(&w_full[stage], wphase);
-            tc_fence_after();
             const uint64_t ad = adesc0 + (uint64_t)(kb * 1024);
             const uint64_t bd = wdesc0 + (uint64_t)(stage * (W_BYTES >> 4));
             if (elect_one()) {
@@ -236,15 +239,14 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
               for (int k = 0; k < 4; ++k)
                 umma<false>(tmem_base + 256, ad + 2 * k, bd + 2 * k, idesc2, (c | kb | k) ? 1u : 0u);
               release_slot(&w_empty[stage]);
+              if (kb == 3) {
+                umma_commit(a2_empty);
+                if (c == nch - 1) umma_commit(acc2_full);
+              }
             }
             __syncwarp();
             if (++stage == NST) { stage = 0; wphase ^= 1; }
           }
-          if (elect_one()) {
-            umma_commit(a2_empty);
-            if (c == nch - 1) umma_commit(acc2_full);
-          }
-          __syncwarp();
           ++g2;
         }
       }
