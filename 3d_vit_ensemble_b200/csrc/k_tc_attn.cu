@@ -104,7 +104,8 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * AT_BUF);     // [2] volume landed
   uint64_t* freeb = full + 2;                                          // [2] every compute warp is done with it
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: warp-uniform for the compiler, so the role branches are uniform control flow
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
 
   if (threadIdx.x == 0) {
@@ -374,7 +375,8 @@ attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16* 
   float* s_stat = reinterpret_cast<float*>(s_dq + AB_DO);        // [HEADS][3][80]
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_stat) + AB_STATS);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: warp-uniform for the compiler, so the role branches are uniform control flow
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   if (threadIdx.x == 0) {
     mbar_init(full, 1);

@@ -126,7 +126,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int stage_bytes = stat ? Cfg::A_BYTES : Cfg::STAGE_BYTES;
   uint8_t* ring = stat ? smem + TC_SLAB_BYTES : smem;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: warp-uniform for the compiler, so the role branches are uniform control flow
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   // patch mode passes the k-block count as K; MN-major stages hold 64 reduction rows
   const int nkb = patch_blocks > 0 ? K : (mn_major ? (K + 63) / 64 : (K + BLOCK_K - 1) / BLOCK_K);
   const int kb_per = (nkb + splits - 1) / splits;
@@ -203,9 +204,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================================================== MMA issuer: all 32 lanes walk the schedule (uniform
-    // control flow, descriptors in uniform registers), one elected lane issues the tcgen05 instructions
-    {
+    // ===================================================== MMA issuer: ONE thread, elected once, walks the whole
+    // schedule - waits, tcgen05.mma, commits (an election + __syncwarp per k-block costs ~60 cycles per MMA:
+    // tools/mma_pipe_bench.cu, k_tc_mlp2.cu)
+    if (elect_one()) {
       const uint32_t idesc = make_idesc(TF32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16, TC_BLOCK_M, BN, mn_major ? 1 : 0,
                                         mn_major ? 1 : 0);
       // K-major SW128: 8-row groups 1024 B apart, K advances 32 B inside the 128 B swizzle row.
@@ -227,23 +229,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (!slab_ready) { mbar_wait(slab_full, 0); slab_ready = true; }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
-        // lean hand-shake (k_tc_mlp2.cu explains why): no tcgen05 fence after an operand k-block has landed (the
-        // mbarrier's complete_tx orders the TMA writes before the MMAs' reads), the tile's commit rides in the
-        // election of its last k-block
+        // no tcgen05 fence after an operand k-block has landed: the mbarrier's complete_tx orders the TMA writes
+        // before the MMAs' reads
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           const uint64_t ad = ring_desc + (uint64_t)((stage * stage_bytes) >> 4);
           const uint64_t bd = stat ? slab_desc + (uint64_t)((kb * Cfg::B_BYTES) >> 4) : ad + (uint64_t)(Cfg::A_BYTES >> 4);
-          if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)     // 4 x 32 bytes of K per stage
-              umma<TF32>(d_tmem, ad + k * kstep, bd + k * kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
-            if (kb == kb1 - 1) umma_commit(&tmem_full[buf]);       // accumulator ready for the epilogue
-          }
-          __syncwarp();
+          for (int k = 0; k < 4; ++k)     // 4 x 32 bytes of K per stage
+            umma<TF32>(d_tmem, ad + k * kstep, bd + k * kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        umma_commit(&tmem_full[buf]);       // accumulator ready for the epilogue
       }
     }
     __syncwarp();

@@ -67,7 +67,8 @@ tc_gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* res_bar = bars + 12;                // [RS_EPI_WARPS] residual panel landed
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12 + RS_EPI_WARPS);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: warp-uniform for the compiler, so the role branches are uniform control flow
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int nkb = (K + 63) / 64;
   const int total = tiles_m * tiles_n;
 
@@ -118,9 +119,9 @@ tc_gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================================================== MMA issuer: all lanes walk the schedule, one elected
-    // lane issues (operands stay in uniform registers: see ptx.cuh elect_one)
-    {
+    // ===================================================== MMA issuer: ONE thread, elected once, walks the whole
+    // schedule (tools/mma_pipe_bench.cu, k_tc_mlp2.cu: an election per k-block costs ~60 cycles per MMA)
+    if (elect_one()) {
       const uint32_t idesc = make_idesc(UMMA_FMT_BF16, RS_BM, RS_BN, 0, 0);
       const uint64_t ring_desc = make_smem_desc(smem_u32(smem), 16, 1024, UMMA_LAYOUT_SW128);
       int stage = 0;
@@ -131,21 +132,17 @@ tc_gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * RS_BN;
-        // lean hand-shake (k_tc_mlp2.cu explains why): no tcgen05 fence after an operand k-block has landed, the
-        // tile's commit rides in the election of its last k-block
+        // no tcgen05 fence after an operand k-block has landed (the mbarrier's complete_tx orders the TMA writes)
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           const uint64_t ad = ring_desc + (uint64_t)((stage * RS_STAGE_BYTES) >> 4);
           const uint64_t bd = ad + (uint64_t)(RS_A_BYTES >> 4);
-          if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma<false>(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&empty_bar[stage]);
-            if (kb == nkb - 1) umma_commit(&tmem_full[buf]);
-          }
-          __syncwarp();
+          for (int k = 0; k < 4; ++k) umma<false>(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
           if (++stage == RS_STAGES) { stage = 0; phase ^= 1; }
         }
+        umma_commit(&tmem_full[buf]);
       }
     }
     __syncwarp();

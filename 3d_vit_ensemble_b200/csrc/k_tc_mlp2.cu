@@ -110,7 +110,9 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   uint64_t* xpanel_free = bars + 52;   // 16: the final epilogue no longer uses the xn region
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 53);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: tells the compiler it is warp-uniform, so the role branches below are uniform
+  // control flow and the MMA / TMA warps keep their operands in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t rank = MC ? cluster_ctarank() : 0u;
   const int M = args.M, d = args.d;
   const int nch = d / M2_NC;
@@ -177,8 +179,11 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================================================== MMA issuer: all 32 lanes walk the schedule (uniform
-    // control flow, operands in uniform registers), one elected lane issues the tcgen05 instructions
+    // ===================================================== MMA issuer: ONE thread, elected once, walks the whole
+    // schedule (barrier waits, tcgen05.mma, commits).  tools/mma_pipe_bench.cu: with an election and a __syncwarp
+    // per k-block (all lanes walking the loop) a 4-MMA stage costs 186-193 cycles per MMA - the warp-level
+    // election / reconvergence sits between the last MMA of one stage and the first of the next and the issue
+    // queue is only ~2 MMAs deep - while a single elected thread running the same hand-shake reaches 128.1.
     constexpr uint32_t idesc1 = make_idesc(UMMA_FMT_BF16, 128, M2_NC, 0, 0);
     constexpr uint32_t idesc2 = make_idesc_ab(UMMA_FMT_F16, UMMA_FMT_F16, 128, M2_H);   // fp16 GELU tile x fp16 W2
     const uint64_t xdesc0 = make_smem_desc(smem_u32(s_x), 16, 1024, UMMA_LAYOUT_SW128);
@@ -187,70 +192,59 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     auto release_slot = [&](uint64_t* bar) {        // ring slot consumed: tell every producer of the cluster
       if constexpr (MC) umma_commit_mcast(bar, (uint16_t)3); else umma_commit(bar);
     };
-    int stage = 0;
-    uint32_t wphase = 0;
-    int it = 0;
-    uint32_t g1 = 0, g2 = 0;              // chunk counters of fc1 / fc2 (phases of the per-chunk barriers)
-    for (int t = gid; t < tiles; t += ngroups, ++it) {
-      mbar_wait(x_full, it & 1);
-      for (int s = 0; s <= nch; ++s) {
-        if (s < nch) {
-          // ---- fc1(s): acc1 = xn * W1[s]^T
-          mbar_wait(acc1_empty, (g1 & 1) ^ 1);          // the GELU warps have read the previous chunk out
-          tc_fence_after();
-          // Every hand-shake between two groups of MMAs (barrier wait, election, commit) is a bubble in the tensor
-          // pipe - the issue queue is only ~2 MMAs deep (tools/mma_pipe_bench.cu: ~200 cycles per 4-MMA stage) -
-          // so the loop carries no instruction it does not need: no tcgen05 fence after a weight k-block has
-          // landed (the mbarrier's complete_tx already orders the TMA writes before the MMAs' reads; the fence
-          // above pairs with the epilogue warps' tcgen05.ld), and the group's commits ride in the election of its
-          // last k-block.
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t wphase = 0;
+      int it = 0;
+      uint32_t g1 = 0, g2 = 0;              // chunk counters of fc1 / fc2 (phases of the per-chunk barriers)
+      for (int t = gid; t < tiles; t += ngroups, ++it) {
+        mbar_wait(x_full, it & 1);
+        for (int s = 0; s <= nch; ++s) {
+          if (s < nch) {
+            // ---- fc1(s): acc1 = xn * W1[s]^T
+            mbar_wait(acc1_empty, (g1 & 1) ^ 1);          // the GELU warps have read the previous chunk out
+            tc_fence_after();
+            // no tcgen05 fence after a weight k-block has landed: the mbarrier's complete_tx already orders the TMA
+            // writes before the MMAs' reads (the fence above pairs with the epilogue warps' tcgen05.ld)
 #pragma unroll
-          for (int kb = 0; kb < 4; ++kb) {
-            mbar_wait(&w_full[stage], wphase);
-            const uint64_t ad = xdesc0 + (uint64_t)(kb * 1024);                     // k-block kb: + 16 KB (>> 4)
-            const uint64_t bd = wdesc0 + (uint64_t)(stage * (W_BYTES >> 4));
-            if (elect_one()) {
+            for (int kb = 0; kb < 4; ++kb) {
+              mbar_wait(&w_full[stage], wphase);
+              const uint64_t ad = xdesc0 + (uint64_t)(kb * 1024);                     // k-block kb: + 16 KB (>> 4)
+              const uint64_t bd = wdesc0 + (uint64_t)(stage * (W_BYTES >> 4));
 #pragma unroll
               for (int k = 0; k < 4; ++k) umma<false>(tmem_base, ad + 2 * k, bd + 2 * k, idesc1, (kb | k) ? 1u : 0u);
               release_slot(&w_empty[stage]);
-              if (kb == 3) {
-                umma_commit(acc1_full);
-                if (s == nch - 1) umma_commit(x_empty);    // xn may be replaced by the next tile's
-              }
+              if (++stage == NST) { stage = 0; wphase ^= 1; }
             }
-            __syncwarp();
-            if (++stage == NST) { stage = 0; wphase ^= 1; }
+            umma_commit(acc1_full);
+            if (s == nch - 1) umma_commit(x_empty);      // xn may be replaced by the next tile's
+            ++g1;
           }
-          ++g1;
-        }
-        if (s >= 1) {
-          // ---- fc2(s-1): acc2 += GELU tile * W2[:, s-1]^T
-          const int c = s - 1;
-          if (c == 0) mbar_wait(acc2_empty, (it & 1) ^ 1);   // previous tile's final epilogue has drained acc2
-          mbar_wait(a2_full, g2 & 1);
-          tc_fence_after();
+          if (s >= 1) {
+            // ---- fc2(s-1): acc2 += GELU tile * W2[:, s-1]^T
+            const int c = s - 1;
+            if (c == 0) mbar_wait(acc2_empty, (it & 1) ^ 1);   // previous tile's final epilogue has drained acc2
+            mbar_wait(a2_full, g2 & 1);
+            tc_fence_after();
 #pragma unroll
-          for (int kb = 0; kb < 4; ++kb) {
-            mbar_wait(&w_full[stage], wphase);
-            const uint64_t ad = adesc0 + (uint64_t)(kb * 1024);
-            const uint64_t bd = wdesc0 + (uint64_t)(stage * (W_BYTES >> 4));
-            if (elect_one()) {
+            for (int kb = 0; kb < 4; ++kb) {
+              mbar_wait(&w_full[stage], wphase);
+              const uint64_t ad = adesc0 + (uint64_t)(kb * 1024);
+              const uint64_t bd = wdesc0 + (uint64_t)(stage * (W_BYTES >> 4));
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma<false>(tmem_base + 256, ad + 2 * k, bd + 2 * k, idesc2, (c | kb | k) ? 1u : 0u);
               release_slot(&w_empty[stage]);
-              if (kb == 3) {
-                umma_commit(a2_empty);
-                if (c == nch - 1) umma_commit(acc2_full);
-              }
+              if (++stage == NST) { stage = 0; wphase ^= 1; }
             }
-            __syncwarp();
-            if (++stage == NST) { stage = 0; wphase ^= 1; }
+            umma_commit(a2_empty);
+            if (c == nch - 1) umma_commit(acc2_full);
+            ++g2;
           }
-          ++g2;
         }
       }
     }
+    __syncwarp();
   } else {
     // ===================================================== GELU / final epilogue warps (own 128 rows)
     const int q = warp & 3;                     // TMEM lane quarter

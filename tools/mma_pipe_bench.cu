@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(96, 1) pipe_kernel(const uint8_t* src, int sta
   const uint32_t tmem_base = tmem_ptr;
   const int sring = stages < MAXST ? stages : MAXST;      // smem slots (more barriers than slots just alias the data)
   if (warp == 0) {
-    if (lane == 0 && (var == 0 || var == 4 || var == 6)) {
+    if (lane == 0 && (var == 0 || var == 4 || var == 6 || var == 7 || var == 8)) {
       int s = 0; uint32_t ph = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&empty[s], ph ^ 1);
@@ -94,6 +94,32 @@ __global__ void __launch_bounds__(96, 1) pipe_kernel(const uint8_t* src, int sta
       if (elect_one()) umma_commit(&done);
       __syncwarp();
       mbar_wait(&done, 0);
+    } else if (style == 2) {
+      // one election for the whole loop: a single thread waits, issues and commits (var 7), optionally with the
+      // try_wait for the NEXT stage issued between the 2nd and 3rd MMA of the current one (var 8), i.e. while the
+      // thread would be blocked on the full MMA queue anyway
+      if (elect_one()) {
+        int s = 0; uint32_t ph = 0;
+        bool ready = false;
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (!ready) mbar_wait(&full[s], ph);
+          const uint64_t ad = ring + (uint64_t)(((s % sring) * STAGE_BYTES) >> 4);
+          const uint64_t bd = ad + (uint64_t)(16384 >> 4);
+          int s2 = s + 1; uint32_t ph2 = ph;
+          if (s2 == stages) { s2 = 0; ph2 ^= 1; }
+          ready = false;
+#pragma unroll
+          for (int k = 0; k < MPK; ++k) {
+            umma<false>(tmem_base, ad + 2 * (k & 3), bd + 2 * (k & 3), idesc, (kb | k) ? 1u : 0u);
+            if (var == 8 && k == 1 && kb + 1 < nkb) ready = mbar_try_wait(&full[s2], ph2);
+          }
+          umma_commit(&empty[s]);
+          s = s2; ph = ph2;
+        }
+        umma_commit(&done);
+      }
+      __syncwarp();
+      mbar_wait(&done, 0);
     } else if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int kb = 0; kb < nkb; ++kb) {
@@ -131,14 +157,14 @@ int main() {
   CK(cudaFuncSetAttribute(pipe_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXST * STAGE_BYTES));
   long long* h = (long long*)malloc(sizeof(long long) * sms);
   const int total_mma = 16384;
-  const char* vn[7] = {"hand-shake", "commit only", "wait only (ready barrier)", "bare", "hand-shake, wait hoisted", "bare, no tcgen05.fence", "hand-shake, no tcgen05.fence"};
-  for (int var : {0, 3, 5, 6})
+  const char* vn[9] = {"hand-shake", "commit only", "wait only (ready barrier)", "bare", "hand-shake, wait hoisted", "bare, no tcgen05.fence", "hand-shake, no tcgen05.fence", "one thread, hand-shake", "one thread, early try_wait"};
+  for (int var : {0, 3, 5, 6, 7, 8})
     for (int mpk : {4, 8, 16})
       for (int stages : {4}) {
         const int nkb = total_mma / mpk;
-        if (mpk == 4) pipe_kernel<4><<<sms, 96, MAXST * STAGE_BYTES>>>(src, stages, mpk, nkb, 0, 0, var, out);
-        else if (mpk == 8) pipe_kernel<8><<<sms, 96, MAXST * STAGE_BYTES>>>(src, stages, mpk, nkb, 0, 0, var, out);
-        else pipe_kernel<16><<<sms, 96, MAXST * STAGE_BYTES>>>(src, stages, mpk, nkb, 0, 0, var, out);
+        if (mpk == 4) pipe_kernel<4><<<sms, 96, MAXST * STAGE_BYTES>>>(src, stages, mpk, nkb, var >= 7 ? 2 : 0, 0, var, out);
+        else if (mpk == 8) pipe_kernel<8><<<sms, 96, MAXST * STAGE_BYTES>>>(src, stages, mpk, nkb, var >= 7 ? 2 : 0, 0, var, out);
+        else pipe_kernel<16><<<sms, 96, MAXST * STAGE_BYTES>>>(src, stages, mpk, nkb, var >= 7 ? 2 : 0, 0, var, out);
         CK(cudaDeviceSynchronize());
         CK(cudaMemcpy(h, out, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
         double c = 0;
