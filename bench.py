@@ -215,6 +215,9 @@ def main():
     elif args.graphs and not train and sharded is None:
         from vit3d_b200.graphs import GraphedInference
         graphed = GraphedInference(model)
+        # the resident batch lives in the graph's own input buffer (no device-to-device copy per replay); the
+        # end-to-end loop below passes its double-buffered H2D targets, which the call copies in
+        x_dev = graphed.input_like(x_dev)
 
     def step_dev(x, y):
         if graphed is not None:

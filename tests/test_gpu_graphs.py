@@ -34,6 +34,28 @@ def test_graphed_inference_equals_eager(prec):
         assert torch.equal(le, lg) and torch.equal(ee, eg) and torch.equal(ae[-1], ag[-1])
 
 
+def test_graphed_inference_input_buffer_in_place():
+    """`input_like` hands out the graph's own input buffer: batches written into it in place (no device-to-device
+    copy at replay) give the same results as the eager call, and ordinary tensors still work afterwards."""
+    cfg, m = make("bf16")
+    m.eval()
+    g = GraphedInference(m)
+    buf = g.input_like(O.synth_volumes(4, seed=1).to(DEV))
+    assert g.input_like(torch.empty_like(buf)) is buf          # one buffer per input shape
+    for seed in (2, 3):
+        x = O.synth_volumes(4, seed=seed).to(DEV)
+        with torch.no_grad():
+            le, _, ee = m(x)
+        le, ee = le.clone(), ee.clone()
+        buf.copy_(x)
+        lg, _, eg = g(buf)
+        assert torch.equal(le, lg) and torch.equal(ee, eg)
+    x = O.synth_volumes(4, seed=4).to(DEV)
+    with torch.no_grad():
+        le = m(x)[0].clone()
+    assert torch.equal(le, g(x)[0])
+
+
 @pytest.mark.parametrize("opt_name", ["sgd", "adam"])
 def test_graphed_train_step_equals_eager(opt_name):
     """Same batches, dropout off: weights after 3 warm-up + 4 replayed steps == 7 eager steps."""
