@@ -56,11 +56,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// One elected lane of a fully active warp.  The MMA-issuing warp runs its loops with ALL lanes (warp-uniform
-// control flow and operands, which the compiler keeps in uniform registers) and wraps only the tcgen05.mma /
-// commit instructions in `if (elect_one())`: issuing from inside an `if (lane == 0)` region instead makes
-// every operand a per-thread register that has to be broadcast back (7 R2UR + an election loop per MMA,
-// ~100 cycles of issue time against the 128 cycles the instruction occupies the tensor pipe).
+// One elected lane of a fully active warp.  The MMA-issuing warp elects ONCE and the elected thread runs the
+// whole schedule (barrier waits, tcgen05.mma, commits) on its own: `if (elect_one()) { for (...) {...} }`.
+// Electing inside the loop - all lanes walking it, `if (elect_one())` + `__syncwarp()` around every stage's
+// MMAs - puts a warp-wide election / reconvergence between the last MMA of one stage and the first of the next
+// and costs 60 cycles per MMA at four MMAs per stage (tools/mma_pipe_bench.cu); issuing from an
+// `if (lane == 0)` region is worse still (the compiler then broadcasts every operand back with R2UR).
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
