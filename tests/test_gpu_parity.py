@@ -336,6 +336,41 @@ def test_full_size_batch_properties():
     assert float((enc0[pick].cpu() - ref_enc[:, 0]).abs().max()) <= 0.05 * float(ref_enc.abs().max())
 
 
+def test_full_size_training_step_linearity():
+    """BASELINE.json's training configuration (conf 18, batch 256, bf16): BCE is a mean over the batch, so with a
+    fixed pos_weight the loss and every parameter gradient of the full batch equal the average over its two halves
+    (eval mode: no dropout noise).  Checks the backward kernels at the bench's tile counts."""
+    cfg = vit3d_b200.north_star_config(18)
+    sd = O.init_state_dict(cfg, seed=42)
+    m = VisionTransformer(cfg, 128, zero_head=True, num_classes=1, precision="bf16", vis=False)
+    m.load_state_dict(sd)
+    m.to(DEV).eval()
+    B = 256
+    x = O.synth_volumes(B, seed=7).to(DEV)
+    y = O.synth_labels(B).to(DEV)
+    w = 1.7
+
+    def run(xs, ys):
+        m.zero_grad(set_to_none=True)
+        loss = m(xs, ys, w)
+        loss.backward()
+        return float(loss.detach()), {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+
+    lf, gf = run(x, y)
+    la, ga = run(x[:128], y[:128])
+    lb, gb = run(x[128:], y[128:])
+    assert np.isfinite(lf) and abs(lf - 0.5 * (la + lb)) <= 2e-3 * max(1.0, abs(lf))
+    worst = 0.0
+    for k in gf:
+        ref = 0.5 * (ga[k] + gb[k])
+        scale = float(ref.abs().max()) + 1e-12
+        worst = max(worst, float((gf[k] - ref).abs().max()) / scale)
+        assert torch.isfinite(gf[k]).all(), k
+    # bf16 operands: the halves round their activations exactly like the full batch (rows are independent), what
+    # differs is the summation order of the weight-gradient reductions (split-K atomics)
+    assert worst <= 2e-2, worst
+
+
 # ----------------------------------------------------------------------------- N1 optimizers
 def test_fused_sgd_and_adam_match_torch():
     from vit3d_b200._lib import call, ptr, stream
