@@ -272,6 +272,8 @@ def main():
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    # timing rule: at least 3 untimed warm-up steps, whatever was asked for (the JSON line reports what was run)
+    args.warmup = max(3, args.warmup)
     ms_dev, launches = timed(lambda: step_dev(x_dev, y_dev), args.steps, args.warmup)
     clk = clocks.stop() if rank == 0 else None
 
