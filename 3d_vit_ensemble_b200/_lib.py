@@ -82,6 +82,18 @@ SIGNATURES = {
     "vit3d_meta_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "vit3d_sgd_step": (_i, [_p, _p, _p, _ll, _f, _f, _f, _i, _f, _p, _p]),
     "vit3d_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _i, _f, _p, _p, _p]),
+    "vit3d_memset_zero": (_i, [_p, _sz, _p]),
+    "vit3d_train_supported": (_i, [_i, _i, _i, _i, _i]),
+    "vit3d_dropout_bits": (_i, [_p, _i, C.POINTER(_u), C.POINTER(_ll), _f, _ull, _u, _p, _p]),
+    "vit3d_ln256_fwd": (_i, [_p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _i, _f, _p]),
+    "vit3d_ln256_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _f, _i, _p, _p, _p, _p, _p, _i, _p]),
+    "vit3d_gelu_mask_bwd": (_i, [_p, _p, _p, _f, _p, _p, _i, _i, _p]),
+    "vit3d_head_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "vit3d_refresh_shadows": (_i, [_p, _i, _i, _p, _p]),
+    "vit3d_fc1_train_fwd": (_i, [_p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _p]),
+    "vit3d_linear_res_train_fwd": (_i, [_p, _p, _p, _p, _p, _p, _f, _p, _p, _f, _p, _p, _p, _i, _i, _i, _p]),
+    "vit3d_wgrad": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "vit3d_attn_bwd_bias": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
 }
 
 

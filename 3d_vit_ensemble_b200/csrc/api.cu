@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc.cuh"
@@ -37,22 +39,24 @@ int sm_count() {
 }
 
 // tuning switches: A/B selection of kernel variants without rebuilding (defaults: environment, else built-in)
+// (process-wide; read and written with relaxed atomics, initialised exactly once: the entry points are re-entrant)
 static int g_tuning[VIT3D_TUNE_COUNT];
-static bool g_tuning_init = false;
+static std::once_flag g_tuning_once;
 static void tuning_defaults() {
-  if (g_tuning_init) return;
-  auto env = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
-  g_tuning[VIT3D_TUNE_EPI_PANEL] = env("VIT3D_EPI_PANEL", 1);
-  g_tuning[VIT3D_TUNE_EPI_LEAN] = env("VIT3D_EPI_LEAN", 1);
-  g_tuning[VIT3D_TUNE_STORE_WIDE] = env("VIT3D_STORE_WIDE", 0);
-  g_tuning[VIT3D_TUNE_L2_AHEAD] = env("VIT3D_L2_AHEAD", 0);
-  g_tuning[VIT3D_TUNE_MLP_PAIR] = env("VIT3D_MLP_PAIR", 0);
-  g_tuning[VIT3D_TUNE_ATTN_THREADS] = env("VIT3D_ATTN_THREADS", 0);
-  g_tuning_init = true;
+  std::call_once(g_tuning_once, [] {
+    auto env = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+    auto set = [](int key, int v) { __atomic_store_n(&g_tuning[key], v, __ATOMIC_RELAXED); };
+    set(VIT3D_TUNE_EPI_PANEL, env("VIT3D_EPI_PANEL", 1));
+    set(VIT3D_TUNE_EPI_LEAN, env("VIT3D_EPI_LEAN", 1));
+    set(VIT3D_TUNE_STORE_WIDE, env("VIT3D_STORE_WIDE", 0));
+    set(VIT3D_TUNE_L2_AHEAD, env("VIT3D_L2_AHEAD", 0));
+    set(VIT3D_TUNE_MLP_PAIR, env("VIT3D_MLP_PAIR", 0));
+    set(VIT3D_TUNE_ATTN_THREADS, env("VIT3D_ATTN_THREADS", 0));
+  });
 }
 int tuning(int key) {
   tuning_defaults();
-  return (key >= 0 && key < VIT3D_TUNE_COUNT) ? g_tuning[key] : 0;
+  return (key >= 0 && key < VIT3D_TUNE_COUNT) ? __atomic_load_n(&g_tuning[key], __ATOMIC_RELAXED) : 0;
 }
 
 static inline int act_f32(int prec) { return prec != VIT3D_PREC_BF16; }
@@ -78,7 +82,7 @@ int vit3d_device_info(int* sms, int* cc) {
 int vit3d_set_tuning(int key, int value) {
   V3_REQUIRE(key >= 0 && key < VIT3D_TUNE_COUNT, "set_tuning: unknown key %d", key);
   tuning_defaults();
-  g_tuning[key] = value;
+  __atomic_store_n(&g_tuning[key], value, __ATOMIC_RELAXED);
   return VIT3D_OK;
 }
 int vit3d_get_tuning(int key) { return tuning(key); }
@@ -329,7 +333,7 @@ int vit3d_attn_bwd(const void* dctx, const void* qkv, void* dqkv, int B, int S, 
                    vit3d_stream_t stream) {
   V3_REQUIRE(dctx && qkv && dqkv, "attn_bwd: null pointer");
   V3_REQUIRE(B >= 0 && S > 0 && heads > 0 && D > 0, "attn_bwd: bad shape");
-  if (prec == VIT3D_PREC_BF16 && tc_attn_supported(S, heads, D)) return tc_attn_bwd(dctx, qkv, dqkv, B, S, heads, D, as_stream(stream));
+  if (prec == VIT3D_PREC_BF16 && tc_attn_supported(S, heads, D)) return tc_attn_bwd(dctx, qkv, dqkv, nullptr, nullptr, nullptr, B, S, heads, D, as_stream(stream));
   return launch_attn_bwd_generic(dctx, qkv, act_f32(prec), dqkv, B, S, heads, D, as_stream(stream));
 }
 
@@ -427,6 +431,105 @@ int vit3d_adam_step(float* p, const float* g, float* m, float* v, long long n, f
   V3_REQUIRE(p && g && m && v && n >= 0 && (step >= 1 || step_dev), "adam_step: bad argument");
   return launch_adam(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, lr_dev, step_dev,
                      as_stream(stream));
+}
+
+// ------------------------------------------------------------------------- fused BF16 training step (a8)
+int vit3d_memset_zero(void* p, size_t bytes, vit3d_stream_t stream) {
+  V3_REQUIRE(p || bytes == 0, "memset_zero: null pointer");
+  if (bytes == 0) return VIT3D_OK;
+  V3_CUDA(cudaMemsetAsync(p, 0, bytes, as_stream(stream)));
+  return VIT3D_OK;
+}
+int vit3d_dropout_bits(uint32_t* bits, int nseg, const unsigned* sites, const long long* nelems, float p,
+                       unsigned long long seed, unsigned step, const unsigned* step_dev, vit3d_stream_t stream) {
+  V3_REQUIRE(bits && sites && nelems && nseg > 0 && nseg <= VIT3D_MAX_DROP_SEGS && p >= 0.f && p < 1.f,
+             "dropout_bits: bad argument");
+  for (int i = 0; i < nseg; ++i) V3_REQUIRE(nelems[i] >= 0 && nelems[i] % 32 == 0, "dropout_bits: segment %d is not a multiple of 32 elements", i);
+  return launch_dropout_bits(bits, nseg, sites, nelems, p, seed, step, step_dev, as_stream(stream));
+}
+int vit3d_ln256_fwd(const float* x, const void* drop_bits, float drop_scale, float* x_dropped, const float* gamma,
+                    const float* beta, void* y_bf16, float* y_f32, float* mean, float* rstd, int M, float eps,
+                    vit3d_stream_t stream) {
+  V3_REQUIRE(x && gamma && beta && (y_bf16 || y_f32) && M >= 0, "ln256_fwd: bad argument");
+  V3_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_dropped) | reinterpret_cast<uintptr_t>(y_bf16) |
+               reinterpret_cast<uintptr_t>(y_f32) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
+             "ln256_fwd: buffers must be 16-byte aligned");
+  return launch_ln256_fwd(x, reinterpret_cast<const uint8_t*>(drop_bits), drop_scale, x_dropped, gamma, beta, y_bf16, y_f32,
+                          mean, rstd, M, eps, as_stream(stream));
+}
+int vit3d_ln256_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                    const float* dres, const void* drop_bits, float drop_scale, int mask_f32, float* dx, void* dx_bf16,
+                    float* dgamma, float* dbeta, float* dbias, int M, vit3d_stream_t stream) {
+  V3_REQUIRE(dy && x && mean && rstd && gamma && (dx || dx_bf16) && M >= 0, "ln256_bwd: bad argument");
+  V3_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dres) |
+               reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dx_bf16) | reinterpret_cast<uintptr_t>(gamma)) & 15) == 0,
+             "ln256_bwd: buffers must be 16-byte aligned");
+  return launch_ln256_bwd(dy, x, mean, rstd, gamma, dres, reinterpret_cast<const uint8_t*>(drop_bits), drop_scale, mask_f32, dx,
+                          dx_bf16, dgamma, dbeta, dbias, M, as_stream(stream));
+}
+int vit3d_gelu_mask_bwd(const void* da, const void* pre, const void* drop_bits, float drop_scale, void* dh, float* db, int M,
+                        int d, vit3d_stream_t stream) {
+  V3_REQUIRE(da && pre && dh && M >= 0 && d > 0 && d % 8 == 0, "gelu_mask_bwd: bad argument");
+  V3_REQUIRE(((reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(dh)) & 15) == 0,
+             "gelu_mask_bwd: buffers must be 16-byte aligned");
+  return launch_gelu_mask_bwd(da, pre, reinterpret_cast<const uint8_t*>(drop_bits), drop_scale, dh, db, M, d, as_stream(stream));
+}
+int vit3d_head_bwd(const float* dlogits, const float* encoded, const float* w, float* dencoded, float* dw, float* db, int B,
+                   int S, int H, vit3d_stream_t stream) {
+  V3_REQUIRE(dlogits && encoded && w && dencoded && dw && db && B >= 0 && S > 0, "head_bwd: bad argument");
+  if (H != 256) V3_UNSUPPORTED("head_bwd: hidden size 256 only (got %d)", H);
+  return launch_head_bwd(dlogits, encoded, w, dencoded, dw, db, B, S, as_stream(stream));
+}
+int vit3d_refresh_shadows(const void* jobs, int njobs, int total_tiles, unsigned* step_dev, vit3d_stream_t stream) {
+  V3_REQUIRE(jobs && njobs > 0 && total_tiles > 0, "refresh_shadows: bad argument");
+  return launch_refresh_shadows(jobs, njobs, total_tiles, step_dev, as_stream(stream));
+}
+int vit3d_fc1_train_fwd(const void* xn, const void* w1_lp, const float* b1, void* pre, void* act, const void* drop_bits,
+                        float drop_scale, int M, int d, int H, vit3d_stream_t stream) {
+  V3_REQUIRE(xn && w1_lp && b1 && pre && act && M >= 0 && d > 0 && H > 0, "fc1_train_fwd: bad argument");
+  if (M == 0) return VIT3D_OK;
+  if (!tc_linear_supported(VIT3D_PREC_BF16, M, d, H) || d % 32) V3_UNSUPPORTED("fc1_train_fwd: unsupported shape M=%d d=%d H=%d", M, d, H);
+  TcLinear t;
+  t.x = xn; t.w = w1_lp; t.bias = b1; t.y = act; t.y_f32 = 0; t.pre = pre; t.act = VIT3D_ACT_GELU; t.M = M; t.N = d; t.K = H;
+  t.prec = VIT3D_PREC_BF16;
+  t.drop_bits = reinterpret_cast<const uint32_t*>(drop_bits); t.drop_scale = drop_scale;
+  return tc_linear_fwd(t, as_stream(stream));
+}
+int vit3d_linear_res_train_fwd(const void* x, const void* w_lp, const float* bias, const float* residual, float* y,
+                               const void* drop_bits, float drop_scale, const float* gamma, const float* beta, float eps,
+                               void* ln_out, float* mean, float* rstd, int M, int N, int K, vit3d_stream_t stream) {
+  V3_REQUIRE(x && w_lp && bias && residual && y && M >= 0 && N > 0 && K > 0, "linear_res_train_fwd: bad argument");
+  V3_REQUIRE(!ln_out || (gamma && beta), "linear_res_train_fwd: LayerNorm needs gamma and beta");
+  if (M == 0) return VIT3D_OK;
+  if (!tc_res_supported(M, N, K, ln_out != nullptr))
+    V3_UNSUPPORTED("linear_res_train_fwd: unsupported shape M=%d N=%d K=%d", M, N, K);
+  TcLinear t;
+  t.x = x; t.w = w_lp; t.bias = bias; t.residual = residual; t.y = y; t.y_f32 = 1; t.M = M; t.N = N; t.K = K;
+  t.prec = VIT3D_PREC_BF16;
+  t.ln_gamma = gamma; t.ln_beta = beta; t.ln_out = ln_out; t.ln_mean = mean; t.ln_rstd = rstd; t.ln_eps = eps;
+  t.drop_bits = reinterpret_cast<const uint32_t*>(drop_bits); t.drop_scale = drop_scale;
+  return tc_gemm_res(t, as_stream(stream));
+}
+int vit3d_wgrad(const void* dy, const void* x, float* dw0, float* dw1, float* dw2, int seg_rows, int M, int N, int K,
+                vit3d_stream_t stream) {
+  V3_REQUIRE(dy && x && dw0 && M >= 0 && N > 0 && K > 0, "wgrad: bad argument");
+  if (M == 0) return VIT3D_OK;
+  if (!tc_wgrad_supported(VIT3D_PREC_BF16, M, N, K)) V3_UNSUPPORTED("wgrad: unsupported shape M=%d N=%d K=%d", M, N, K);
+  return tc_gemm_wgrad_seg(dy, x, dw0, dw1, dw2, seg_rows, N, K, M, as_stream(stream));
+}
+int vit3d_attn_bwd_bias(const void* dctx, const void* qkv, void* dqkv, float* db_q, float* db_k, float* db_v, int B, int S,
+                        int heads, int D, vit3d_stream_t stream) {
+  V3_REQUIRE(dctx && qkv && dqkv && db_q && db_k && db_v, "attn_bwd_bias: null pointer");
+  V3_REQUIRE(B >= 0 && S > 0 && heads > 0 && D > 0, "attn_bwd_bias: bad shape");
+  if (!tc_attn_supported(S, heads, D)) V3_UNSUPPORTED("attn_bwd_bias: unsupported shape S=%d heads=%d D=%d", S, heads, D);
+  return tc_attn_bwd(dctx, qkv, dqkv, db_q, db_k, db_v, B, S, heads, D, as_stream(stream));
+}
+int vit3d_train_supported(int B, int S, int H, int heads, int d) {
+  if (B <= 0 || H != 256 || heads <= 0 || H % heads) return 0;
+  const int M = B * S;
+  return tc_attn_supported(S, heads, H / heads) && tc_res_supported(M, H, H, true) && tc_res_supported(M, H, d, true) &&
+                 tc_linear_supported(VIT3D_PREC_BF16, M, d, H) && d % 64 == 0 && tc_wgrad_supported(VIT3D_PREC_BF16, M, d, H)
+             ? 1 : 0;
 }
 
 }  // extern "C"

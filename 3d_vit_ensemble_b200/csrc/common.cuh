@@ -104,6 +104,17 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return cdf + x * pdf;
 }
 
+// derivative of the fitted tanh-form GELU the BF16 forward evaluates, y = 0.5 x (1 + tanh(u)),
+// u = x (c0 + c1 x^2 + c2 x^4):   y' = 0.5 (1 + t) + 0.5 x (1 - t^2) (c0 + 3 c1 x^2 + 5 c2 x^4)
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  const float x2 = fminf(x * x, 100.f);
+  const float u = x * fmaf(x2, fmaf(x2, -3.58732362e-4f, 0.0370503451f), 0.797458471f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float du = fmaf(x2, fmaf(x2, 5.f * -3.58732362e-4f, 3.f * 0.0370503451f), 0.797458471f);
+  return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * du;
+}
+
 // ----------------------------------------------------------------------------- Philox4x32-10
 // Counter-based RNG for dropout: the mask of element i at (site, step) is a pure function
 // of (seed, site, step, i), so backward regenerates it instead of storing it.

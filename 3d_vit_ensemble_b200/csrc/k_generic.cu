@@ -692,17 +692,8 @@ int launch_gelu_fwd(const void* h, void* a, long long n, int f32, cudaStream_t s
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
-// bf16 fast path: 8 elements per thread (16-byte accesses); derivative of the same fitted tanh-form GELU the
-// BF16 forward evaluates, y = 0.5 x (1 + tanh(u)), u = x (c0 + c1 x^2 + c2 x^4):
-//   y' = 0.5 (1 + t) + 0.5 x (1 - t^2) (c0 + 3 c1 x^2 + 5 c2 x^4)
-__device__ __forceinline__ float gelu_grad_fast(float x) {
-  const float x2 = fminf(x * x, 100.f);
-  const float u = x * fmaf(x2, fmaf(x2, -3.58732362e-4f, 0.0370503451f), 0.797458471f);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-  const float du = fmaf(x2, fmaf(x2, 5.f * -3.58732362e-4f, 3.f * 0.0370503451f), 0.797458471f);
-  return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * du;
-}
+// bf16 fast path: 8 elements per thread (16-byte accesses); gelu_grad_fast (common.cuh) is the derivative of the
+// fitted tanh-form GELU the BF16 forward evaluates
 // DROP: the Dropout between GELU and fc2 (modeling.py:121) is undone here too - dh = keep * da / (1-p) * gelu'(h)
 // with the mask regenerated from (seed, site, step, element index), so training needs no separate dropout
 // backward pass over the [M, mlp_dim] gradient.

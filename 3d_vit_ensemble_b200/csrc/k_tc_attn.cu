@@ -362,7 +362,8 @@ constexpr int AB_SMEM = AB_QKV + 2 * AB_DO + AB_STATS + 64 + 128;
 template <int D>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16* __restrict__ qkv,
-                   __nv_bfloat16* __restrict__ dqkv, int B, float scale, float scale_log2e) {
+                   __nv_bfloat16* __restrict__ dqkv, float* __restrict__ db_q, float* __restrict__ db_k,
+                   float* __restrict__ db_v, int B, float scale, float scale_log2e) {
   constexpr int HEADS = AT_A / D;
   constexpr int KSTEPS = D / 16;
   constexpr int NT = 10;
@@ -386,6 +387,9 @@ attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16* 
   pdl_trigger();
   pdl_wait();
   const uint32_t sb = smem_u32(s_qkv), dob = smem_u32(s_do);
+  // q / k / v bias gradients = column sums of dq | dk | dv over all tokens: thread t keeps the partial sums of
+  // columns t and 512 + t of the [65 x 768] gradient image over this CTA's volumes, one atomic each at the end
+  float bsum0 = 0.f, bsum1 = 0.f;
 
   int it = 0;
   for (int b = blockIdx.x; b < B; b += gridDim.x, ++it) {
@@ -600,24 +604,52 @@ attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16* 
       }
       bulk_commit();
     }
+    if (db_q) {
+      const int c0 = threadIdx.x;                 // 0..511: dQ columns 0..255, dK columns 256..511
+      {
+        const uint8_t* base = c0 < AT_A ? s_dq + c0 * 2 : s_qkv + c0 * 2;
+        const int pitch = c0 < AT_A ? AB_DOP : AT_PITCH;
+        float a = 0.f;
+#pragma unroll 5
+        for (int r = 0; r < AT_S; ++r) a += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(base + r * pitch));
+        bsum0 += a;
+      }
+      if (c0 < AT_A) {                            // dV columns 512..767
+        const uint8_t* base = s_qkv + (2 * AT_A + c0) * 2;
+        float a = 0.f;
+#pragma unroll 5
+        for (int r = 0; r < AT_S; ++r) a += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(base + r * AT_PITCH));
+        bsum1 += a;
+      }
+      __syncthreads();       // the next volume's loads overwrite the images these sums read
+    }
+  }
+  if (db_q) {
+    const int c0 = threadIdx.x;
+    if (blockIdx.x < B) {
+      atomicAdd(c0 < AT_A ? db_q + c0 : db_k + (c0 - AT_A), bsum0);
+      if (c0 < AT_A) atomicAdd(db_v + c0, bsum1);
+    }
   }
   if (warp == 0) bulk_wait0();
 }
 
 template <int D>
-static int launch_attn_bwd(const void* dctx, const void* qkv, void* dqkv, int B, cudaStream_t st) {
+static int launch_attn_bwd(const void* dctx, const void* qkv, void* dqkv, float* db_q, float* db_k, float* db_v, int B,
+                           cudaStream_t st) {
   auto kern = attn_bwd_tc_kernel<D>;
   V3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
   const int grid = B < sm_count() ? B : sm_count();
   const float scale = 1.0f / sqrtf((float)D);
   V3_CUDA(launch_pdl(kern, dim3(grid), dim3(AT_THREADS), (size_t)AB_SMEM, st, reinterpret_cast<const __nv_bfloat16*>(dctx),
-                     reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(dqkv), B, scale,
-                     1.4426950408889634f * scale));
+                     reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(dqkv), db_q, db_k, db_v, B,
+                     scale, 1.4426950408889634f * scale));
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
 
-int tc_attn_bwd(const void* dctx, const void* qkv, void* dqkv, int B, int S, int heads, int D, cudaStream_t st) {
+int tc_attn_bwd(const void* dctx, const void* qkv, void* dqkv, float* db_q, float* db_k, float* db_v, int B, int S,
+                int heads, int D, cudaStream_t st) {
   if (!tc_attn_supported(S, heads, D)) V3_UNSUPPORTED("tc attention bwd: unsupported shape S=%d heads=%d D=%d", S, heads, D);
   if (B <= 0) return VIT3D_OK;
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(dctx) & 15) ||
@@ -625,9 +657,13 @@ int tc_attn_bwd(const void* dctx, const void* qkv, void* dqkv, int B, int S, int
     set_error("tc attention bwd: buffers must be 16-byte aligned");
     return VIT3D_ERR_INVALID;
   }
-  if (D == 16) return launch_attn_bwd<16>(dctx, qkv, dqkv, B, st);
-  if (D == 32) return launch_attn_bwd<32>(dctx, qkv, dqkv, B, st);
-  return launch_attn_bwd<64>(dctx, qkv, dqkv, B, st);
+  if ((db_q != nullptr) != (db_k != nullptr) || (db_q != nullptr) != (db_v != nullptr)) {
+    set_error("tc attention bwd: pass all three bias-gradient buffers or none");
+    return VIT3D_ERR_INVALID;
+  }
+  if (D == 16) return launch_attn_bwd<16>(dctx, qkv, dqkv, db_q, db_k, db_v, B, st);
+  if (D == 32) return launch_attn_bwd<32>(dctx, qkv, dqkv, db_q, db_k, db_v, B, st);
+  return launch_attn_bwd<64>(dctx, qkv, dqkv, db_q, db_k, db_v, B, st);
 }
 
 }  // namespace vit3d

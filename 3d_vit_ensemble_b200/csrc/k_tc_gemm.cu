@@ -279,8 +279,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + part * CW;
       const int m_base = ti.tm * TC_BLOCK_M + q * 32, n_base = ti.tn * BN + part * CW;
       if constexpr (EPI >= 0) {
+        const uint32_t* drop_row = nullptr;
+        if constexpr ((EPI & 8) != 0) {
+          if (m_base + lane < M) drop_row = ep.drop_bits + (((long long)(m_base + lane) * N + n_base) >> 5);
+        }
         epilogue_bf16_lean<CW, EPI, WIDE>(&tmC, &tmPre, taddr, stage, smem_u32(bias_stage) + part * CW * 4,
-                                    smem_u32(bias_stage) + BN * 4 + part * CW * 2, lane, m_base, n_base);
+                                    smem_u32(bias_stage) + BN * 4 + part * CW * 2, lane, m_base, n_base, drop_row,
+                                    ep.drop_scale);
       } else {
         epilogue_rows<CW, !TF32>(ep, &tmC, &tmPre, taddr, stage, lane, m_base, n_base, M, N);
       }
@@ -416,8 +421,9 @@ int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const 
   }
   // compile-time specialised epilogue for the hot bf16-output products (full column tiles)
   if (!ep.out_f32 && bn >= 128 && N % bn == 0 && tuning(VIT3D_TUNE_EPI_LEAN) != 0 &&
-      (!ep.pre || ep.act == VIT3D_ACT_GELU) && (ep.act == VIT3D_ACT_NONE || ep.bias)) {
-    const int mode = (ep.bias ? 1 : 0) | (ep.act == VIT3D_ACT_GELU ? 2 : 0) | (ep.pre ? 4 : 0);
+      (!ep.pre || ep.act == VIT3D_ACT_GELU) && (ep.act == VIT3D_ACT_NONE || ep.bias) &&
+      (!ep.drop_bits || (ep.pre && ep.bias && ep.act == VIT3D_ACT_GELU))) {
+    const int mode = (ep.bias ? 1 : 0) | (ep.act == VIT3D_ACT_GELU ? 2 : 0) | (ep.pre ? 4 : 0) | (ep.drop_bits ? 8 : 0);
     if (bn == 256 && !ep.pre && tuning(VIT3D_TUNE_STORE_WIDE) != 0) {
       // one [32 x 64] panel (128-byte rows) per epilogue warp and tile
       CUtensorMap tw;
@@ -429,8 +435,8 @@ int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const 
     }
 #define V3_LEAN(BN_, MODE_) \
   if (bn == BN_ && mode == MODE_) return launch_tc<false, BN_, MODE_>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
-    V3_LEAN(256, 0) V3_LEAN(256, 1) V3_LEAN(256, 3) V3_LEAN(256, 7)
-    V3_LEAN(128, 0) V3_LEAN(128, 1) V3_LEAN(128, 3) V3_LEAN(128, 7)
+    V3_LEAN(256, 0) V3_LEAN(256, 1) V3_LEAN(256, 3) V3_LEAN(256, 7) V3_LEAN(256, 15)
+    V3_LEAN(128, 0) V3_LEAN(128, 1) V3_LEAN(128, 3) V3_LEAN(128, 7) V3_LEAN(128, 15)
 #undef V3_LEAN
   }
   if (bn == 256) return launch_tc<false, 256>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
@@ -442,13 +448,22 @@ int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const 
 // the weight-gradient product dW[N,K] += dY[M,N]^T X[M,K].  Split over the reduction (token rows) so that
 // every SM has work; partial tiles are accumulated with fp32 atomics into `out`.
 int tc_gemm_wgrad(const void* A, const void* B, float* out, int Mo, int No, int Kred, cudaStream_t st) {
+  return tc_gemm_wgrad_seg(A, B, out, nullptr, nullptr, 0, Mo, No, Kred, st);
+}
+
+// same, output rows [i*seg_rows, (i+1)*seg_rows) accumulated into out0 / out1 / out2 (seg_rows % 128 == 0; 0 = one buffer)
+int tc_gemm_wgrad_seg(const void* A, const void* B, float* out, float* out1, float* out2, int seg_rows, int Mo, int No,
+                      int Kred, cudaStream_t st) {
   const int sms = sm_count();
   int bn = 256;
   if (No % 256) bn = 128;
   if (No % 128) bn = 64;
   const int tiles = ceil_div(Mo, TC_BLOCK_M) * ceil_div(No, bn);
   const int nkb = ceil_div(Kred, 64);
-  int splits = ceil_div(2 * sms, tiles);
+  // Every work item ends in a 128 x bn tile of fp32 atomics into the SAME few output tiles; the L2 retires about
+  // one fp32 atomic per slice and clock (~0.2 T/s chip-wide), so the atomic volume - work items x tile size -
+  // is what the small products (out-projection: 2 output tiles) pay for.  One work item per SM, not two.
+  int splits = sms / tiles;              // floor: 24 tiles x 6 slices = 144 items are one wave, 24 x 7 = 168 would be two
   if (splits > nkb) splits = nkb;
   if (splits < 1) splits = 1;
   // no K-slice may be empty (an empty slice would publish an unwritten accumulator): iterate to the
@@ -465,6 +480,13 @@ int tc_gemm_wgrad(const void* A, const void* B, float* out, int Mo, int No, int 
   if (rc != VIT3D_OK) return rc;
   TcEpilogue ep;
   ep.out = out; ep.out_f32 = 1; ep.atomic = 1;
+  if (seg_rows > 0) {
+    if (seg_rows % TC_BLOCK_M || !out1 || Mo > 3 * seg_rows || (Mo > 2 * seg_rows && !out2)) {
+      set_error("wgrad: bad output segmentation (seg_rows %d, rows %d)", seg_rows, Mo);
+      return VIT3D_ERR_INVALID;
+    }
+    ep.seg_rows = seg_rows; ep.out_seg[0] = out1; ep.out_seg[1] = out2;
+  }
   if (bn == 256) return launch_tc<false, 256>(ta, tb, ta, ta, ep, Mo, No, Kred, splits, false, st, 0, 1);
   if (bn == 128) return launch_tc<false, 128>(ta, tb, ta, ta, ep, Mo, No, Kred, splits, false, st, 0, 1);
   return launch_tc<false, 64>(ta, tb, ta, ta, ep, Mo, No, Kred, splits, false, st, 0, 1);
@@ -497,6 +519,10 @@ int tc_linear_fwd(const TcLinear& t, cudaStream_t st) {
   TcEpilogue ep;
   ep.bias = t.bias; ep.residual = t.residual; ep.out = t.y; ep.pre = t.pre; ep.out_f32 = t.y_f32; ep.act = t.act;
   ep.round_tf32 = (t.prec == VIT3D_PREC_TF32 && t.act == VIT3D_ACT_GELU && !t.residual) ? 1 : 0;
+  if (t.drop_bits) {
+    if (t.y_f32 || t.N % 32) { set_error("linear + dropout: generic path needs bf16 output and N %% 32 == 0"); return VIT3D_ERR_UNSUPPORTED; }
+    ep.drop_bits = t.drop_bits; ep.drop_scale = t.drop_scale;
+  }
   return tc_gemm(t.prec == VIT3D_PREC_TF32, t.x, t.w, t.M, t.N, t.K, ep, 1, st);
 }
 

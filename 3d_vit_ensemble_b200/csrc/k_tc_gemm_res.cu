@@ -45,16 +45,18 @@ struct ResEpilogue {
   float* rstd = nullptr;           // [M] optional (LN)
   float eps = 1e-6f;
   int l2_ahead = 0;                // tiles of A prefetched into L2 ahead of the operand ring
+  const uint32_t* drop_bits = nullptr;   // keep bits over [M,N] (MODE bit 3): (A B^T + bias) * keep * drop_scale + residual
+  float drop_scale = 1.f;
 };
 
-// MODE bit 0: bias, bit 1: residual, bit 2: fused LayerNorm output
+// MODE bit 0: bias, bit 1: residual, bit 2: fused LayerNorm output, bit 3: Dropout before the residual add (training)
 template <int MODE>
 __global__ void __launch_bounds__(RS_THREADS, 1)
 tc_gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmRes,
                    const __grid_constant__ CUtensorMap tmLn, ResEpilogue ep, int M, int N, int K, int tiles_m,
                    int tiles_n) {
-  constexpr bool BIAS = (MODE & 1) != 0, RES = (MODE & 2) != 0, LN = (MODE & 4) != 0;
+  constexpr bool BIAS = (MODE & 1) != 0, RES = (MODE & 2) != 0, LN = (MODE & 4) != 0, DROP = (MODE & 8) != 0;
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023u) __trap();
   uint8_t* panels = smem + RS_OPER_BYTES;
@@ -197,6 +199,10 @@ tc_gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int p = 0; p < 2; ++p) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + p * 32, r);
+        uint32_t mw = 0u;
+        if constexpr (DROP) {
+          if (m_base + lane < M) mw = __ldg(ep.drop_bits + (((long long)(m_base + lane) * N + n_base + p * 32) >> 5));
+        }
         if constexpr (RES) {
           mbar_wait(rbar, rphase);        // this panel of the residual has landed in the buffer
           rphase ^= 1;
@@ -210,6 +216,12 @@ tc_gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if constexpr (BIAS) {
             const uint4 b = ld_shared_v4(bias_s + (p * 32 + 4 * j) * 4);
             v0 += __uint_as_float(b.x); v1 += __uint_as_float(b.y); v2 += __uint_as_float(b.z); v3 += __uint_as_float(b.w);
+          }
+          if constexpr (DROP) {
+            v0 = ((mw >> (4 * j)) & 1u) ? v0 * ep.drop_scale : 0.f;
+            v1 = ((mw >> (4 * j + 1)) & 1u) ? v1 * ep.drop_scale : 0.f;
+            v2 = ((mw >> (4 * j + 2)) & 1u) ? v2 * ep.drop_scale : 0.f;
+            v3 = ((mw >> (4 * j + 3)) & 1u) ? v3 * ep.drop_scale : 0.f;
           }
           if constexpr (RES) {
             const uint4 x = ld_shared_v4(a);
@@ -368,7 +380,13 @@ int tc_gemm_res(const TcLinear& t, cudaStream_t st) {
   ResEpilogue ep;
   ep.l2_ahead = tuning(VIT3D_TUNE_L2_AHEAD);
   ep.bias = t.bias; ep.gamma = t.ln_gamma; ep.beta = t.ln_beta; ep.mean = t.ln_mean; ep.rstd = t.ln_rstd; ep.eps = t.ln_eps;
+  ep.drop_bits = t.drop_bits; ep.drop_scale = t.drop_scale;
   const int mode = (t.bias ? 1 : 0) | (t.residual ? 2 : 0) | (ln ? 4 : 0);
+  if (t.drop_bits) {
+    // training fc2: Dropout between the Linear and the residual add (modeling.py:123, :196)
+    if (!t.bias || !t.residual) { set_error("tc_gemm_res: the dropout variant needs bias and residual"); return VIT3D_ERR_UNSUPPORTED; }
+    return ln ? launch_res<15>(ta, tb, ty, tr, tl, ep, t.M, t.N, t.K, st) : launch_res<11>(ta, tb, ty, tr, tl, ep, t.M, t.N, t.K, st);
+  }
   switch (mode) {
     case 0: return launch_res<0>(ta, tb, ty, tr, tl, ep, t.M, t.N, t.K, st);
     case 1: return launch_res<1>(ta, tb, ty, tr, tl, ep, t.M, t.N, t.K, st);

@@ -64,4 +64,18 @@ int launch_sgd(float* p, const float* g, float* mom, long long n, float lr, floa
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                 float wd, int step, float gscale, const float* lr_dev, const int* step_dev, cudaStream_t st);
 
+// k_train.cu: bandwidth-bound passes of the fused BF16 training step
+int launch_dropout_bits(uint32_t* bits, int nseg, const unsigned* sites, const long long* nelems, float p,
+                        unsigned long long seed, unsigned step, const unsigned* step_dev, cudaStream_t st);
+int launch_ln256_fwd(const float* x, const uint8_t* bits, float sc, float* xd, const float* gamma, const float* beta,
+                     void* y_bf16, float* y_f32, float* mean, float* rstd, int M, float eps, cudaStream_t st);
+int launch_ln256_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                     const float* dres, const uint8_t* bits, float sc, int mask_f32, float* dx, void* dxb, float* dgamma,
+                     float* dbeta, float* dbias, int M, cudaStream_t st);
+int launch_gelu_mask_bwd(const void* da, const void* pre, const uint8_t* bits, float sc, void* dh, float* db, int M, int d,
+                         cudaStream_t st);
+int launch_head_bwd(const float* dlogit, const float* enc, const float* w, float* denc, float* dw, float* db, int B, int S,
+                    cudaStream_t st);
+int launch_refresh_shadows(const void* jobs, int njobs, int total_tiles, unsigned* step_dev, cudaStream_t st);
+
 }  // namespace vit3d

@@ -21,6 +21,10 @@ struct TcLinear {
   float* ln_mean = nullptr;      // [M] optional
   float* ln_rstd = nullptr;      // [M] optional
   float ln_eps = 1e-6f;
+  // training: Dropout of (x W^T + b) (fp32 outputs: before the residual add, modeling.py:123,:196) or of the
+  // activation (bf16 outputs, modeling.py:121) from a keep-bit array over the [M,N] output
+  const uint32_t* drop_bits = nullptr;
+  float drop_scale = 1.f;
 };
 bool tc_linear_ln_supported(int prec, int M, int N, int K);
 // k_tc_gemm_res.cu: fp32 output (+ bias, + residual, + fused LayerNorm) through TMA panels; N % 256 == 0
@@ -33,6 +37,8 @@ int tc_linear_fwd(const TcLinear& t, cudaStream_t st);
 // dW[N,K] += dY[M,N]^T X[M,K]  (bf16 operands, fp32 atomics)
 bool tc_wgrad_supported(int prec, int M, int N, int K);
 int tc_gemm_wgrad(const void* dy, const void* x, float* dw, int N, int K, int M, cudaStream_t st);
+int tc_gemm_wgrad_seg(const void* dy, const void* x, float* dw0, float* dw1, float* dw2, int seg_rows, int N, int K, int M,
+                      cudaStream_t st);
 
 bool tc_patch_embed_supported(int B, int X, int Y, int Z, int p0, int p1, int p2, int H);
 int tc_patch_embed_fwd(const float* x, const float* w, const float* bias, const float* pos, float* tokens, int B, int X,
@@ -46,6 +52,8 @@ int tc_mlp2_fwd(const void* xn, const void* w1, const float* b1, const void* w2_
 
 bool tc_attn_supported(int S, int heads, int D);
 int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int heads, int D, cudaStream_t st);
-int tc_attn_bwd(const void* dctx, const void* qkv, void* dqkv, int B, int S, int heads, int D, cudaStream_t st);
+// db_q / db_k / db_v (each [heads*D] fp32, all or none): += column sums of dq / dk / dv (the q, k, v bias gradients)
+int tc_attn_bwd(const void* dctx, const void* qkv, void* dqkv, float* db_q, float* db_k, float* db_v, int B, int S,
+                int heads, int D, cudaStream_t st);
 
 }  // namespace vit3d

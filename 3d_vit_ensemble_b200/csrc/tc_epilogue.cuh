@@ -24,6 +24,14 @@ struct TcEpilogue {
   int vols_per_tile = 0;            // patch-embedding mode: volumes per 128-row tile
   int round_tf32 = 0;               // fp32 output is the operand of a TF32 GEMM: round to nearest tf32
   int l2_ahead = 0;                 // producer: tiles of A to prefetch into L2 ahead of the shared-memory ring
+  // training: Dropout after the activation (modeling.py:121) applied from a keep-bit array (bit i = element i of
+  // the [M,N] output, k_train.cu dropout_bits); bf16 outputs, N % 32 == 0
+  const uint32_t* drop_bits = nullptr;
+  float drop_scale = 1.f;
+  // atomic (weight-gradient) outputs split by rows over up to three buffers: rows [i*seg_rows, (i+1)*seg_rows)
+  // go to out / out_seg[0] / out_seg[1] (the packed q|k|v weight gradient lands in three parameters' .grad)
+  float* out_seg[2] = {nullptr, nullptr};
+  int seg_rows = 0;
 };
 
 
@@ -83,6 +91,19 @@ __device__ __forceinline__ uint32_t gelu_pair_bf16(float a, float b) {
   const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
   const float2 f = __half22float2(__hfma2(hx, th, hx));
   return pack2_bf16(f.x, f.y);
+}
+// same fitted GELU, result left as two floats (the dropout variants scale before packing)
+__device__ __forceinline__ float2 gelu_pair_f2(float a, float b) {
+  const __half2 x = __floats2half2_rn(a, b);
+  const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(100.f));
+  __half2 p = __hfma2(x2, __float2half2_rn(-3.58732362e-4f), __float2half2_rn(0.0370503451f));
+  p = __hfma2(x2, p, __float2half2_rn(0.797458471f));
+  const __half2 u = __hmul2(x, p);
+  uint32_t ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
+  const __half2 th = *reinterpret_cast<const __half2*>(&ti);
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  return __half22float2(__hfma2(hx, th, hx));
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -155,8 +176,14 @@ __device__ __forceinline__ void epilogue_rows(const TcEpilogue& ep, const CUtens
             const uint4 u = ld_shared_v4(stage + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
             float4 v = make_float4(__uint_as_float(u.x) + bias.x + radd[i].x, __uint_as_float(u.y) + bias.y + radd[i].y,
                                    __uint_as_float(u.z) + bias.z + radd[i].z, __uint_as_float(u.w) + bias.w + radd[i].w);
-            const long long orow = ep.row_group > 0 ? (long long)m + m / ep.row_group + 1 : (long long)m;
-            float* o = reinterpret_cast<float*>(ep.out) + orow * N + col;
+            long long orow = ep.row_group > 0 ? (long long)m + m / ep.row_group + 1 : (long long)m;
+            float* obase = reinterpret_cast<float*>(ep.out);
+            if (ep.seg_rows > 0) {
+              const int seg = m / ep.seg_rows;
+              if (seg > 0) obase = ep.out_seg[seg - 1];
+              orow = m - seg * ep.seg_rows;
+            }
+            float* o = obase + orow * N + col;
             if (ep.atomic) {
               // one 16-byte vector reduction instead of four scalar ones (split-K weight gradients)
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
@@ -205,9 +232,23 @@ __device__ __forceinline__ void epilogue_rows(const TcEpilogue& ep, const CUtens
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
         }
+        const bool drop = pass == 1 && ep.drop_bits != nullptr;
+        if (drop) {
+          if (gelu && FAST_GELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 f = gelu_pair_f2(v[2 * j], v[2 * j + 1]);
+              v[2 * j] = f.x; v[2 * j + 1] = f.y;
+            }
+          }
+          const int m = m_base + lane;
+          const uint32_t mw = m < M ? __ldg(ep.drop_bits + (((long long)m * N + n_base + c) >> 5)) : 0u;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = ((mw >> j) & 1u) ? v[j] * ep.drop_scale : 0.f;
+        }
         if (lane == 0) bulk_store_wait_read();      // the previous round's store has finished reading the tile
         __syncwarp();
-        if (gelu && FAST_GELU) {
+        if (gelu && FAST_GELU && !drop) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             st_shared_v4(my_row + ((j ^ sw) << 4), gelu_pair_bf16(v[8 * j], v[8 * j + 1]), gelu_pair_bf16(v[8 * j + 2], v[8 * j + 3]),
@@ -256,12 +297,16 @@ __device__ __forceinline__ uint32_t gelu_pair_bf16_h2(__half2 x) {
 // WIDE (CW == 64, no pre-activation output): the warp's whole 32 x 64 slice is staged as ONE panel with
 // 128-byte rows (128B swizzle, 4 KB) and leaves by one bulk tensor store per tile instead of two stores of
 // 64-byte rows - half the TMA row transactions, and the wait for the previous store moves a whole tile away.
+//   MODE bit 3: Dropout of the output from keep bits (`drop_row` = word of column n_base of this thread's row,
+//               null for rows >= M); needs bits 0-2 (the training fc1: bias + GELU + pre-activation copy)
 template <int CW, int MODE, bool WIDE = false>
 __device__ __forceinline__ void epilogue_bf16_lean(const CUtensorMap* tmC, const CUtensorMap* tmPre, uint32_t taddr,
                                                    uint32_t stage, uint32_t bias_f32, uint32_t bias_h2, int lane,
-                                                   int m_base, int n_base) {
-  constexpr bool BIAS = (MODE & 1) != 0, GELU = (MODE & 2) != 0, PRE = (MODE & 4) != 0;
+                                                   int m_base, int n_base, const uint32_t* drop_row = nullptr,
+                                                   float drop_scale = 1.f) {
+  constexpr bool BIAS = (MODE & 1) != 0, GELU = (MODE & 2) != 0, PRE = (MODE & 4) != 0, DROP = (MODE & 8) != 0;
   static_assert(!WIDE || (CW == 64 && !PRE), "wide staging: 64 columns per warp, no pre-activation copy");
+  static_assert(!DROP || (GELU && PRE), "dropout variant = training fc1 (bias + GELU + pre-activation)");
   const uint32_t my_row = stage + lane * (WIDE ? 128 : 64);
   const int sw = WIDE ? (lane & 7) : ((lane >> 1) & 3);
 #pragma unroll
@@ -310,8 +355,19 @@ __device__ __forceinline__ void epilogue_bf16_lean(const CUtensorMap* tmC, const
           bulk_store_commit();
         }
       }
+      if constexpr (DROP) {
+        const uint32_t mw = drop_row ? __ldg(drop_row + (c >> 5)) : 0u;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) w[j] = GELU ? gelu_pair_bf16(v[2 * j], v[2 * j + 1]) : pack2_bf16(v[2 * j], v[2 * j + 1]);
+        for (int j = 0; j < 16; ++j) {
+          float2 f = gelu_pair_f2(v[2 * j], v[2 * j + 1]);
+          f.x = ((mw >> (2 * j)) & 1u) ? f.x * drop_scale : 0.f;
+          f.y = ((mw >> (2 * j + 1)) & 1u) ? f.y * drop_scale : 0.f;
+          w[j] = pack2_bf16(f.x, f.y);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = GELU ? gelu_pair_bf16(v[2 * j], v[2 * j + 1]) : pack2_bf16(v[2 * j], v[2 * j + 1]);
+      }
     }
     if (!WIDE || c == 0) {
       if (lane == 0) bulk_store_wait_read();    // the previous store has finished reading the staging tile

@@ -28,17 +28,30 @@ def world() -> Tuple[int, int]:
 
 
 # ----------------------------------------------------------------------------- DP training
-def global_pos_weight(labels: torch.Tensor, group=None) -> Optional[torch.Tensor]:
-    """sklearn 'balanced' class-weight ratio n_neg/n_pos (train_baseline_cv.py:168-169) computed over the
-    global batch (one 2-float all-reduce), so DP-N equals single-GPU training on the concatenated batch."""
+def class_pos_weight(n_pos: float, n: float) -> float:
+    """The scalar the reference passes as `pos_weight` (train_baseline_cv.py:168-169):
+    `sklearn.utils.class_weight.compute_class_weight('balanced', classes=unique(y), y=y)` gives
+    n / (n_classes_present * count_c) per class; the script takes entry [1] when both classes are in
+    the batch - n / (2 * n_pos) - and entry [0] otherwise, which is n / (1 * n) = 1.0."""
+    if n_pos <= 0 or n_pos >= n:
+        return 1.0
+    return float(n) / (2.0 * float(n_pos))
+
+
+def batch_pos_weight(labels: torch.Tensor) -> torch.Tensor:
+    """`class_pos_weight` of one batch of 0/1 labels as the 0-dim float64 tensor the scripts build."""
+    y = labels.reshape(-1)
+    return torch.tensor(class_pos_weight(float(y.sum()), float(y.numel())), dtype=torch.float64)
+
+
+def global_pos_weight(labels: torch.Tensor, group=None) -> torch.Tensor:
+    """`batch_pos_weight` over the GLOBAL batch (one 2-float all-reduce of the class counts), so DP-N
+    optimises the same loss as single-GPU training on the concatenated batch."""
     y = labels.reshape(-1).float()
     cnt = torch.stack([y.sum(), torch.tensor(float(y.numel()), device=y.device)]).to(torch.float64)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(cnt, group=group)
-    n_pos, n = float(cnt[0]), float(cnt[1])
-    if n_pos == 0 or n_pos == n:
-        return None
-    return torch.tensor((n - n_pos) / n_pos, dtype=torch.float64)
+    return torch.tensor(class_pos_weight(float(cnt[0]), float(cnt[1])), dtype=torch.float64)
 
 
 class GradReducer:
@@ -213,48 +226,131 @@ class ShardedEnsemble:
     """TransformerEnsemble.forward (modeling.py:353-356) with members x batch-slices spread over the ranks.
 
     `ensemble` is a `TransformerEnsemble` whose members all live on this rank's device (weights are small:
-    <= 60 MB per member); every rank receives the same input batch `x`."""
+    <= 60 MB per member).  Every rank is handed the same input batch `x`:
+      * a DEVICE tensor: used as is;
+      * a HOST tensor (pinned for speed; fp32 or uint8): only the batch slices of this rank's own
+        (member, slice) chunk are copied to the device - with N ranks each ships ~3/N of a batch, not all of it.
+    The member forwards of one rank run CONCURRENTLY on side streams when their slices are too small to fill the
+    GPU on their own (the reference runs them back to back, modeling.py:354)."""
 
-    def __init__(self, ensemble, costs: Optional[Sequence[float]] = None, group=None, graphs: bool = True):
+    CONCURRENT_MAX_SLICE = 256          # volumes: 256 x 65 rows = 130 row tiles < 148 SMs
+
+    def __init__(self, ensemble, costs: Optional[Sequence[float]] = None, group=None, graphs: bool = True,
+                 concurrent: Optional[bool] = None):
         """graphs=True replays each member's forward from a CUDA graph (one per member and slice shape): a rank's
-        share of a batch is small, so launch overhead would otherwise dominate."""
+        share of a batch is small, so launch overhead would otherwise dominate.  concurrent: None = automatic."""
         self.ensemble = ensemble
         self.group = group
         m = len(ensemble.transformers)
         self.costs = list(costs) if costs is not None else [1.0] * m
         self._graphed = None
+        self.concurrent = concurrent
+        self._plans = {}
+        self._streams = None
         params = list(ensemble.parameters()) if hasattr(ensemble, "parameters") else []
-        if graphs and params and params[0].is_cuda:
+        self._cuda = bool(params) and params[0].is_cuda
+        if graphs and self._cuda:
             from .graphs import GraphedInference
             self._graphed = [GraphedInference(t) for t in ensemble.transformers]
+        self.graphed = self._graphed is not None
+
+    def graph_runners(self):
+        return list(self._graphed) if self._graphed is not None else []
+
+    # ---- static plan per (batch size, world size)
+    def _plan(self, B: int, device):
+        rank, ws = world()
+        key = (B, ws, rank, str(device))
+        pl = self._plans.get(key)
+        if pl is not None:
+            return pl
+        m = len(self.ensemble.transformers)
+        parts = partition_work(self.costs, B, ws)
+        maxlen = max(1, max(sum(b1 - b0 for _, b0, b1 in p) for p in parts))
+        mine = [(j, b0, b1) for j, b0, b1 in parts[rank] if b1 > b0]
+        # merged batch intervals this rank needs (slices of consecutive members overlap or touch)
+        iv = sorted((b0, b1) for _, b0, b1 in mine)
+        merged = []
+        for lo, hi in iv:
+            if merged and lo <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], hi)
+            else:
+                merged.append([lo, hi])
+        # out[b, j] = gathered[perm[b*m + j]]
+        perm = torch.empty(B * m, dtype=torch.int64)
+        for r, p in enumerate(parts):
+            off = r * maxlen
+            for j, b0, b1 in p:
+                if b1 > b0:
+                    perm[torch.arange(b0, b1) * m + j] = torch.arange(off, off + (b1 - b0))
+                    off += b1 - b0
+        pl = dict(parts=parts, maxlen=maxlen, mine=mine, merged=[tuple(v) for v in merged], perm=perm.to(device))
+        self._plans[key] = pl
+        return pl
+
+    def gather_bytes(self, B: int) -> int:
+        _, ws = world()
+        parts = partition_work(self.costs, B, ws)
+        return 4 * ws * max(1, max(sum(b1 - b0 for _, b0, b1 in p) for p in parts))
+
+    def h2d_bytes(self, B: int, bytes_per_volume: int = 327680) -> int:
+        """Host-to-device bytes THIS rank ships for one batch handed in as a host tensor."""
+        dev = next(self.ensemble.parameters()).device
+        return sum(hi - lo for lo, hi in self._plan(B, dev)["merged"]) * bytes_per_volume
+
+    def _stage(self, x: torch.Tensor, pl, device):
+        """Host batch -> device copies of the merged intervals; returns {(b0, b1) slice -> device view}."""
+        views = {}
+        bufs = []
+        for lo, hi in pl["merged"]:
+            key = ("stage", lo, hi, x.dtype, tuple(x.shape[1:]))
+            buf = self._plans.get(key)
+            if buf is None:
+                buf = torch.empty((hi - lo,) + tuple(x.shape[1:]), dtype=x.dtype, device=device)
+                self._plans[key] = buf
+            buf.copy_(x[lo:hi], non_blocking=True)
+            bufs.append((lo, hi, buf))
+        for _, b0, b1 in pl["mine"]:
+            for lo, hi, buf in bufs:
+                if lo <= b0 and b1 <= hi:
+                    views[(b0, b1)] = buf[b0 - lo:b1 - lo]
+                    break
+        return views
 
     @torch.no_grad()
     def member_logits(self, x: torch.Tensor) -> torch.Tensor:
         rank, ws = world()
         B = x.shape[0]
-        m = len(self.ensemble.transformers)
-        parts = partition_work(self.costs, B, ws)
-        maxlen = max(sum(b1 - b0 for _, b0, b1 in p) for p in parts)
-        mine = torch.zeros(max(maxlen, 1), device=x.device, dtype=torch.float32)
+        dev = next(self.ensemble.parameters()).device if hasattr(self.ensemble, "parameters") else x.device
+        pl = self._plan(B, dev)
+        mine = pl["mine"]
+        staged = self._stage(x, pl, dev) if (x.device != dev and dev.type == "cuda") else None
+        buf = torch.zeros(pl["maxlen"], device=dev, dtype=torch.float32)
+        conc = self.concurrent
+        if conc is None:
+            conc = self._cuda and len(mine) > 1 and max(b1 - b0 for _, b0, b1 in mine) <= self.CONCURRENT_MAX_SLICE
+        if conc and self._streams is None:
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(len(self.ensemble.transformers))]
+        main = torch.cuda.current_stream(dev) if self._cuda else None
         off = 0
-        for j, b0, b1 in parts[rank]:
-            if b1 > b0:
-                member = self._graphed[j] if self._graphed is not None else self.ensemble.transformers[j]
-                lg = member(x[b0:b1])[0]
-                mine[off:off + (b1 - b0)] = lg.reshape(-1).float()
-                off += b1 - b0
+        for k, (j, b0, b1) in enumerate(mine):
+            member = self._graphed[j] if self._graphed is not None else self.ensemble.transformers[j]
+            xs = staged[(b0, b1)] if staged is not None else x[b0:b1]
+            if conc:
+                s = self._streams[k % len(self._streams)]
+                s.wait_stream(main)
+                with torch.cuda.stream(s):
+                    buf[off:off + (b1 - b0)] = member(xs)[0].reshape(-1).float()
+                main.wait_stream(s)
+            else:
+                buf[off:off + (b1 - b0)] = member(xs)[0].reshape(-1).float()
+            off += b1 - b0
         if ws > 1:
-            gathered = torch.empty(ws * mine.numel(), device=x.device, dtype=torch.float32)
-            dist.all_gather_into_tensor(gathered, mine, group=self.group)
+            gathered = torch.empty(ws * buf.numel(), device=dev, dtype=torch.float32)
+            dist.all_gather_into_tensor(gathered, buf, group=self.group)
         else:
-            gathered = mine
-        out = torch.empty(B, m, device=x.device, dtype=torch.float32)
-        for r, p in enumerate(parts):
-            off = r * mine.numel()
-            for j, b0, b1 in p:
-                out[b0:b1, j] = gathered[off:off + (b1 - b0)]
-                off += b1 - b0
-        return out
+            gathered = buf
+        return gathered[pl["perm"]].view(B, len(self.ensemble.transformers))
 
     @torch.no_grad()
     def __call__(self, x: torch.Tensor) -> torch.Tensor:

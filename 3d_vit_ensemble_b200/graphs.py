@@ -11,6 +11,7 @@ import torch
 
 from . import _lib
 from . import functional as F
+from . import fused_train
 
 
 class GraphedInference:
@@ -24,11 +25,27 @@ class GraphedInference:
         self.model = model
         self.warmup = warmup
         self._graphs = {}
+        self._params = list(model.parameters())
+        self._sig = None
         self.launches_per_replay = 0
         self.replays = 0
+        self.recaptures = 0
+
+    def _weights_signature(self):
+        """The captured kernels read cached low-precision weight shadows (functional._LP_CACHE / _QKV_CACHE); an
+        optimizer step, load_state_dict, .to() or set_precision makes the eager path rebuild those caches and free
+        the old tensors, so a graph captured before would compute with stale weights - or freed memory."""
+        return (tuple(p._version for p in self._params), tuple(p.data_ptr() for p in self._params),
+                F._STATE.get("epoch", 0), getattr(self.model, "precision", None))
 
     @torch.no_grad()
     def __call__(self, x: torch.Tensor):
+        sig = self._weights_signature()
+        if sig != self._sig:
+            if self._graphs:
+                self._graphs = {}          # weights changed since capture: every graph is stale, capture again
+                self.recaptures += 1
+            self._sig = sig
         key = (tuple(x.shape), x.dtype)
         ent = self._graphs.get(key)
         if ent is None:
@@ -95,19 +112,29 @@ class GraphedTrainStep:
         dev = optimizer.arena.flat.device
         self.lr_dev = torch.tensor([float(optimizer.param_groups[0]["lr"])], device=dev, dtype=torch.float32)
         self.pw_dev = torch.ones(1, device=dev, dtype=torch.float32)
-        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)      # dropout mask offset, Adam step
+        # dropout mask offset and Adam's t: starts at the optimizer's step count, so a resumed run (or eager steps
+        # taken before the capture) continues Adam's bias correction and the mask sequence instead of restarting them
+        self.step_dev = torch.full((1,), int(getattr(optimizer, "_steps", 0)), device=dev, dtype=torch.int32)
+        self.fused = False
         optimizer.lr_dev = self.lr_dev
         if hasattr(optimizer, "exp_avg"):
             optimizer.step_dev = self.step_dev
 
     def set_lr(self, lr: float):
-        self.lr_dev.fill_(float(lr))
+        self.lr_dev.copy_(torch.tensor([float(lr)], dtype=torch.float32))      # a copy, not a fill kernel
         self.opt.param_groups[0]["lr"] = float(lr)
 
     def _fwd_bwd(self):
+        pw = self.pw_dev if self.use_pw else None
+        if self.fused:
+            # fused BF16 step: shadow refresh (+ step counter), memset of the gradient arena, forward and backward
+            # as explicit kernel sequences - no autograd, no framework kernels inside the graph
+            fused_train.plan_of(self.model).refresh(self.step_dev, force=True)
+            self.opt.zero_grad()
+            return fused_train.loss_and_grads(self.model, self.x, self.y, pw)
         self.step_dev.add_(1)
         self.opt.zero_grad()
-        loss = self.model(self.x, self.y, self.pw_dev if self.use_pw else None)
+        loss = self.model(self.x, self.y, pw)
         loss.backward()
         return loss
 
@@ -134,6 +161,7 @@ class GraphedTrainStep:
             if self.use_pw:
                 self.pw_dev.fill_(float(pos_weight))
             F._STATE["step_dev"] = self.step_dev
+            self.fused = fused_train.supported(self.model, self.x)
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
@@ -146,20 +174,33 @@ class GraphedTrainStep:
             with torch.cuda.graph(self._graph):
                 self.loss = self._fwd_bwd() if self.dp else self._one()
             self.launches_per_replay = _lib.lib().vit3d_launch_count() - n0
+            if not self.dp:
+                self.opt._steps -= 1            # the capture recorded the optimizer launch, it did not run it
             F.invalidate_weight_shadows()       # shadows made during capture live in the graph's pool
             self._graph.replay()                # capture records, it does not execute: run the step now
-            self.replays += 1
-            if self.dp:
-                self._finish()
+            self._after_replay()
             return self.loss
         if (pos_weight is not None) != self.use_pw:
             raise ValueError("GraphedTrainStep was captured %s pos_weight" % ("with" if self.use_pw else "without"))
-        self.x.copy_(x, non_blocking=True)
-        self.y.copy_(y, non_blocking=True)
+        if x.data_ptr() != self.x.data_ptr():
+            self.x.copy_(x, non_blocking=True)
+        if y.data_ptr() != self.y.data_ptr():
+            self.y.copy_(y, non_blocking=True)
         if self.use_pw:
-            self.pw_dev.fill_(float(pos_weight))
+            self.pw_dev.copy_(torch.tensor([float(pos_weight)], dtype=torch.float32))    # a copy, not a fill kernel
         self._graph.replay()
+        self._after_replay()
+        return self.loss
+
+    def _after_replay(self):
         self.replays += 1
         if self.dp:
-            self._finish()
-        return self.loss
+            self._finish()                      # counts the optimizer step itself
+        else:
+            self.opt._steps += 1                # the captured optimizer launch ran again
+        F.invalidate_weight_shadows()           # weights moved behind torch's version counters (eager users re-derive)
+
+    def input_buffers(self):
+        """(x, y) the graph reads: write the next batch straight into them (e.g. as host-to-device copy targets)
+        and pass them to the call to skip the device-to-device copies."""
+        return self.x, self.y

@@ -62,7 +62,10 @@ class FlatArena:
             p.grad = gv
 
     def zero_grad(self):
-        self.flat_grad.zero_()
+        if self.flat_grad.is_cuda:      # a memset node, not a framework fill kernel (CUDA-graph'd steps: kernels are all ours)
+            call("vit3d_memset_zero", ptr(self.flat_grad), self.flat_grad.numel() * 4, stream())
+        else:
+            self.flat_grad.zero_()
         for p, gv in zip(self.params, self.grad_views):
             p.grad = gv
 

@@ -24,6 +24,7 @@ import torch.nn as nn
 from torch.nn import Conv3d, Dropout, LayerNorm, Linear
 
 from . import functional as F
+from . import fused_train
 from ._lib import ACT_GELU, ACT_NONE, Vit3dError
 
 Z_SIZE = 5  # slices per volume (modeling.py:134)
@@ -321,6 +322,10 @@ class VisionTransformer(nn.Module):
         F._need_cuda(x)
         if x.dtype == torch.uint8:          # N2: raw 8-bit volumes; (u8 - mean) happens on the device
             x = F.u8_volumes_to_f32(x, self.input_mean)
+        if labels is not None and fused_train.supported(self, x):
+            # BF16 mode, hidden 256: forward + loss with ONE autograd node whose backward is the fused kernel
+            # sequence of fused_train.py (the per-operator Functions below stay the generic path)
+            return fused_train.loss(self, x, labels, weights)
         x, attn_weights = self.transformer(x)
         logits = F.linear(x[:, 0], self.head.weight, self.head.bias, prec="fp32", out_f32=True)
         if labels is not None:

@@ -1,14 +1,24 @@
 #!/usr/bin/env python
-"""Headline benchmark: 3D-ViT (conf 5 by default) inference volumes/s on N B200s.
+"""Headline benchmark: 3D-ViT stacking-ensemble path, volumes/s on N B200s.
 
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
     python bench.py --impl reference ...       # the reference's CPU path (oracle port) on the host cores
 
-One JSON line on stdout (rank 0).  A "step" = one forward pass of `model(x)` (eval, no_grad, reference
-call pattern train_baseline_cv.py:79) over one batch of `--batch` synthetic volumes per GPU.
-`value` = volumes/s with the batch resident in HBM; `e2e` = the same through the public module call
-with pinned HOST input, H2D copy and D2H read of the logits inside the timed region.
+ONE JSON line on stdout (rank 0).  The headline (`value`, `e2e`, `roofline`, `cpu_baseline`) is BASELINE.json
+config 2: conf-5 inference, `model(x)` in eval / no_grad (train_baseline_cv.py:79), batch 1024 per GPU, batch
+sharded over the ranks (no data-path collective).  The same run then times short legs of the two north-star
+workloads that DO exchange data, reported under `workloads`:
+
+    conf18_train     conf-18 data-parallel training step (train_baseline_cv.py:163-182): forward + backward replayed
+                     from a CUDA graph, ONE NCCL all-reduce of the flat gradient arena, fused SGD step
+    ensemble_infer   confs 5+9+11 + meta-classifier (models/modeling.py:353-356): (member, batch-slice) work list cut
+                     into equal-FLOP chunks, one all-gather of the member logits, meta-head on every rank
+    conf5_infer_tf32 the headline workload in the TF32 (1e-3 logit tolerance) mode
+
+`value` = volumes/s with the batch resident in HBM; `e2e` = the same through the public module call with pinned HOST
+input, H2D copy and D2H read of the result inside the timed region (`e2e.variants.u8`: volumes cross PCIe as the
+8-bit images they are, N2 input path).
 """
 import argparse
 import json
@@ -24,6 +34,13 @@ if ROOT not in sys.path:
 
 METRIC = "ensemble volumes/sec (inference, fwd+bwd train) at 1/2/4/8 B200 vs CPU ref"
 UNIT = "volumes/s"
+VOL_BYTES = 327680          # one fp32 volume (1,128,128,5)
+
+WORKLOADS = {
+    "conf5_infer": dict(name="conf5 (d2048 L6 8x32 H256) inference, model(x) eval/no_grad", confs=[5], train=False, batch=1024),
+    "conf18_train": dict(name="conf18 (d3072 L8 16x16 H256) training fwd+bwd+SGD step", confs=[18], train=True, batch=256),
+    "ensemble_infer": dict(name="ensemble conf 5+9+11 + meta-classifier inference", confs=[5, 9, 11], train=False, batch=512),
+}
 
 
 def parse():
@@ -32,12 +49,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="conf5_infer",
-                    choices=["conf5_infer", "conf18_train", "ensemble_infer"])
+    ap.add_argument("--workload", default="conf5_infer", choices=list(WORKLOADS))
+    ap.add_argument("--legs", default="auto", help="extra workloads timed after the headline: 'auto' (the other two + the "
+                    "TF32 mode when the headline is conf5_infer), 'none', or a comma list")
+    ap.add_argument("--leg-steps", type=int, default=8, help="timed steps of every extra leg")
     ap.add_argument("--batch", type=int, default=0, help="volumes per GPU per step (0 = workload default)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--vis", type=int, default=1, help="materialise attention probabilities (reference default vis=True)")
-    ap.add_argument("--cpu-sample", type=int, default=64, help="volumes per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="volumes per step of the in-run cpu_baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=240.0, help="seconds the --impl reference arm may run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graphs", type=int, default=1, help="replay the step from a CUDA graph (vit3d_b200.graphs)")
     return ap.parse_args()
@@ -97,18 +117,49 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Best effort: run this rank (and first-touch its pinned staging buffers) on the CPU socket its GPU hangs off,
+    so that 8 ranks do not all stream their H2D copies out of one socket's memory.  Returns the number of CPUs
+    the rank was bound to, or None when the topology is not visible / nothing changed."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip()
+        if not out:
+            return None
+        bdf = out.lower()
+        if bdf.count(":") == 2 and len(bdf.split(":")[0]) == 8:      # 00000000:1b:00.0 -> 0000:1b:00.0
+            bdf = bdf[4:]
+        path = f"/sys/bus/pci/devices/{bdf}/local_cpulist"
+        if not os.path.exists(path):
+            return None
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        return None
+    return None
+
+
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
-def cpu_arm(args, workload_cfgs, train, steps, warmup, sample):
+def cpu_arm(cfgs, train, steps, warmup, sample, budget_s=None):
     """Times the reference's algorithm on the host cores: the oracle's functional restatement of
-    models/modeling.py (torch CPU fp32, all threads).  Bounded sample of the same workload."""
+    models/modeling.py (torch CPU fp32, all threads).  Stops early when `budget_s` is used up (returns the steps run)."""
     import torch
     from oracle import vit3d_oracle as O
     torch.set_num_threads(os.cpu_count())
-    cfgs = workload_cfgs
     sds = [O.init_state_dict(c, seed=42 + j) for j, c in enumerate(cfgs)]
     x = O.synth_volumes(sample, seed=42)
     y = O.synth_labels(sample)
-    w = O.balanced_pos_weight(y)
+    w = O.sklearn_pos_weight(y)
     ens_sd = O.ensemble_state_dict(sds) if len(cfgs) > 1 else None
 
     def step():
@@ -121,25 +172,273 @@ def cpu_arm(args, workload_cfgs, train, steps, warmup, sample):
             with torch.no_grad():
                 O.vit_forward(sds[0], cfgs[0], x)
 
+    t_start = time.perf_counter()
+    warm_done = 0
     for _ in range(warmup):
         step()
+        warm_done += 1
+        if budget_s is not None and time.perf_counter() - t_start > 0.3 * budget_s:
+            break
     t0 = time.perf_counter()
+    done = 0
     for _ in range(steps):
         step()
+        done += 1
+        if budget_s is not None and time.perf_counter() - t_start > budget_s:
+            break
     dt = time.perf_counter() - t0
-    return sample * steps / dt, dt / steps * 1e3
+    return sample * done / dt, dt / done * 1e3, done, warm_done
 
 
-def workload(args):
+def workload_config(wl, B, world, vis):
+    """`config` of the JSON line: identical for the GPU arm and the reference arm of the same workload."""
+    units = B if len(wl["confs"]) > 1 else world * B
+    if wl["train"]:
+        par = f"dp{world}: batch sharded over the ranks, gradients all-reduced (mean) before the SGD step"
+    elif len(wl["confs"]) > 1:
+        par = f"{world} ranks: (member, batch-slice) work list balanced by FLOPs, all-gather of member logits, meta-head on every rank"
+    else:
+        par = f"dp{world} (independent volumes, no data-path collective)"
+    return {"workload": wl["name"], "batch_per_gpu": B, "global_batch": units, "vis": bool(vis),
+            "l2": "inputs larger than L2 (batch of fp32 volumes = %.0f MB)" % (B * VOL_BYTES / 1e6), "parallelism": par}
+
+
+# ----------------------------------------------------------------------------- GPU legs
+class Ctx:
+    pass
+
+
+def time_region(ctx, fn, steps, warm, counter=None):
+    """`warm` untimed calls, then `steps` calls between CUDA events, barrier + synchronize on both sides, max over
+    ranks.  Returns (ms, launches of this library inside the timed region)."""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    if ctx.dist is not None:
+        ctx.dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = counter() if counter else 0
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    n1 = counter() if counter else 0
+    ms = e0.elapsed_time(e1)
+    if ctx.dist is not None:
+        t = torch.tensor([ms], device=ctx.dev)
+        ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.MAX)
+        ms = float(t)
+        ctx.dist.barrier()
+    return ms, n1 - n0
+
+
+def run_leg(ctx, args, key, steps, warmup, precision, with_u8=True):
+    """Builds one workload, times its device-resident loop and its end-to-end loop.  Returns a dict."""
+    import torch
     import vit3d_b200
-    if args.workload == "conf5_infer":
-        return dict(name="conf5 (d2048 L6 8x32 H256) inference, model(x) eval/no_grad", confs=[5], train=False,
-                    batch=args.batch or 1024)
-    if args.workload == "conf18_train":
-        return dict(name="conf18 (d3072 L8 16x16 H256) training fwd+bwd", confs=[18], train=True,
-                    batch=args.batch or 256)
-    return dict(name="ensemble conf 5+9+11 + meta-classifier inference", confs=[5, 9, 11], train=False,
-                batch=args.batch or 512)
+    from oracle import vit3d_oracle as O          # test infrastructure: synthetic inputs / seeded weights only
+    from vit3d_b200.dist import batch_pos_weight
+    from vit3d_b200.models.modeling import TransformerEnsemble, VisionTransformer
+    wl = WORKLOADS[key]
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
+    L = vit3d_b200._lib.lib()
+    B = args.batch if (args.batch and key == args.workload) else wl["batch"]
+    cfgs = [vit3d_b200.north_star_config(c) for c in wl["confs"]]
+    train = wl["train"]
+    ens = len(cfgs) > 1
+    flops_per_vol = sum(O.fwd_flops_per_volume(c) for c in cfgs) * (3.0 if train else 1.0)
+    members = []
+    for j, c in enumerate(cfgs):
+        m = VisionTransformer(c, 128, zero_head=True, num_classes=1, vis=bool(args.vis), precision=precision)
+        m.load_state_dict(O.init_state_dict(c, seed=42 + j))
+        members.append(m)
+    model = members[0] if not ens else TransformerEnsemble(*members, in_features=1)
+    model.to(dev)
+    model.train(train)
+    x_host = O.synth_volumes(B, seed=42 + (rank if not ens else 0)).pin_memory()
+    y_host = O.synth_labels(B).pin_memory()
+    x_dev = x_host.to(dev)
+    y_dev = y_host.to(dev)
+    graphed = sharded = opt = None
+    collective = None
+    bytes_coll = 0
+    if train:
+        # the reference's optimizer (train_baseline_cv.py:111-114) as one fused launch over a flat arena
+        from vit3d_b200.graphs import GraphedTrainStep
+        from vit3d_b200.optim import FusedSGD
+        opt = FusedSGD(model.parameters(), lr=1e-4, momentum=0.9, weight_decay=1e-2)
+        graphed = GraphedTrainStep(model, opt, warmup=2, data_parallel=world > 1)
+        if world > 1:
+            collective = "all_reduce(flat gradient arena, fp32) after the backward graph, before the fused SGD launch"
+            bytes_coll = opt.arena.numel * 4
+    elif ens:
+        from vit3d_b200.dist import ShardedEnsemble
+        sharded = ShardedEnsemble(model, costs=[O.fwd_flops_per_volume(c) for c in cfgs])
+        if world > 1:
+            collective = "all_gather_into_tensor(member logits of this rank's (member, batch-slice) chunk, fp32)"
+            bytes_coll = sharded.gather_bytes(B)
+    elif args.graphs:
+        from vit3d_b200.graphs import GraphedInference
+        graphed = GraphedInference(model)
+        x_dev = graphed.input_like(x_dev)       # the resident batch lives in the graph's own input buffer
+
+    def pos_weight():
+        # the scripts compute the class weight of every batch on the host from its labels (sklearn,
+        # train_baseline_cv.py:168-169); every rank holds the same synthetic labels, so local == global
+        return batch_pos_weight(y_host)
+
+    def step_dev(x, y):
+        if train:
+            return graphed(x, y, pos_weight())
+        if sharded is not None:
+            return sharded(x)
+        if graphed is not None:
+            return graphed(x)[0]
+        with torch.no_grad():
+            return model(x)[0]
+
+    def counter():
+        n = L.vit3d_launch_count()
+        for g in ([graphed] if graphed is not None else []) + (sharded.graph_runners() if sharded is not None else []):
+            n += g.replays * g.launches_per_replay
+        return n
+
+    ms_dev, launches = time_region(ctx, lambda: step_dev(x_dev, y_dev), steps, warmup, counter)
+
+    # ---- end to end: every step copies ITS batch from pinned host memory (copy stream, double buffered so the copy of
+    # step s+1 overlaps the compute of step s), runs the public call and reads the result back before it counts as done
+    res_host = torch.empty((B, 1) if not train else (), dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream()
+
+    def e2e_loop(host_x, bufs):
+        ybuf = [torch.empty_like(y_dev) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        nchunk = 4 if host_x.numel() * host_x.element_size() >= (64 << 20) else 1
+
+        def issue_copy(s):
+            b = s & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[b])
+                if nchunk == 1:
+                    bufs[b].copy_(host_x, non_blocking=True)
+                else:                                   # a few large copies keep the copy engine's queue full
+                    n = host_x.shape[0]
+                    for c in range(nchunk):
+                        lo, hi = n * c // nchunk, n * (c + 1) // nchunk
+                        bufs[b][lo:hi].copy_(host_x[lo:hi], non_blocking=True)
+                if train:
+                    ybuf[b].copy_(y_host, non_blocking=True)
+                ready[b].record(copy_stream)
+
+        def run(nsteps):
+            main = torch.cuda.current_stream()
+            for b in range(2):
+                consumed[b].record(main)
+            issue_copy(0)
+            for s in range(nsteps):
+                b = s & 1
+                main.wait_event(ready[b])
+                out = step_dev(bufs[b], ybuf[b] if train else None)
+                consumed[b].record(main)
+                if s + 1 < nsteps:
+                    issue_copy(s + 1)
+                res_host.copy_(out.detach().reshape(res_host.shape), non_blocking=True)
+                main.synchronize()
+        return run
+
+    def timed_e2e(run):
+        w = max(3, warmup // 2)
+        run(w)
+        ms, _ = time_region(ctx, lambda: run(steps), 1, 0)
+        return ms
+
+    units = B if ens else world * B
+    if sharded is not None:
+        # a rank ships only the batch slices of its own (member, slice) chunk
+        ms_e2e = timed_e2e(lambda n: [sharded_e2e_step(sharded, x_host, res_host) for _ in range(n)])
+        h2d = sharded.h2d_bytes(B)
+    else:
+        ms_e2e = timed_e2e(e2e_loop(x_host, [torch.empty_like(x_dev) for _ in range(2)]))
+        h2d = int(B * VOL_BYTES + (B * 4 if train else 0))
+    e2e = {"value": units * steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": int(res_host.numel() * 4), "ms_per_step": ms_e2e / steps,
+           "h2d_gbs_per_rank": h2d / (ms_e2e / steps * 1e-3) / 1e9}
+    if with_u8 and not train:
+        # N2: the same volumes cross PCIe as uint8 (they ARE 8-bit images minus a mean); (u8 - mean) on the device
+        u8_host, mean = O.synth_volumes_u8(B, seed=42 + (rank if not ens else 0))
+        u8_host = u8_host.pin_memory()
+        for m in members:
+            m.input_mean = mean
+        if sharded is not None:
+            ms_u8 = timed_e2e(lambda n: [sharded_e2e_step(sharded, u8_host, res_host) for _ in range(n)])
+            h2d8 = sharded.h2d_bytes(B) // 4
+        else:
+            ms_u8 = timed_e2e(e2e_loop(u8_host, [torch.empty(u8_host.shape, dtype=torch.uint8, device=dev) for _ in range(2)]))
+            h2d8 = int(B * VOL_BYTES // 4)
+        e2e["variants"] = {"u8": {"value": units * steps / (ms_u8 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d8,
+                                  "d2h_bytes_per_step": int(res_host.numel() * 4), "ms_per_step": ms_u8 / steps,
+                                  "note": "volumes shipped as uint8 + mean (N2 input path), (u8 - mean) on the device"}}
+    value = units * steps / (ms_dev * 1e-3)
+    peaks = load_peaks()
+    out = {
+        "value": value, "unit": UNIT, "ms_per_step": ms_dev / steps, "steps": steps, "warmup": warmup,
+        "scaling": "strong" if ens else "weak", "dtype": precision,
+        "config": workload_config(wl, B, world, args.vis),
+        "exec": {"precision": precision, "cuda_graph": graphed is not None or (sharded is not None and sharded.graphed),
+                 "fused_train_step": bool(getattr(graphed, "fused", False)) if train else None},
+        "model_tflops": value * flops_per_vol / 1e12,
+        "model_frac_of_bf16_sustained": value * flops_per_vol / 1e12 / (world * peaks["bf16_tflops_sustained"]),
+        "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches / max(1, steps),
+        "collective": collective, "bytes_per_collective": int(bytes_coll),
+    }
+    ctx.last = dict(cfgs=cfgs, B=B, train=train)
+    del model, members, graphed, sharded, opt
+    torch.cuda.empty_cache()
+    return out
+
+
+def ensemble_small_batch_probe(ctx, args):
+    """The reference runs the 3 members back to back (models/modeling.py:354).  At the batch sizes the scripts use
+    (4 for training, 1 for validation) one member cannot fill 148 SMs, so the members run on 3 streams here:
+    serial vs concurrent time of `ensemble(x)` per batch size, device-resident input."""
+    import torch
+    import vit3d_b200
+    from oracle import vit3d_oracle as O
+    from vit3d_b200.dist import ShardedEnsemble
+    from vit3d_b200.models.modeling import TransformerEnsemble, VisionTransformer
+    cfgs = [vit3d_b200.north_star_config(c) for c in (5, 9, 11)]
+    members = []
+    for j, c in enumerate(cfgs):
+        m = VisionTransformer(c, 128, zero_head=True, num_classes=1, vis=bool(args.vis), precision=args.precision)
+        m.load_state_dict(O.init_state_dict(c, seed=42 + j))
+        members.append(m)
+    ens = TransformerEnsemble(*members, in_features=1).to(ctx.dev).eval()
+    costs = [O.fwd_flops_per_volume(c) for c in cfgs]
+    out = {}
+    for B in (4, 16, 64):
+        x = O.synth_volumes(B, seed=1).to(ctx.dev)
+        row = {}
+        for mode, conc in (("serial", False), ("concurrent", True)):
+            se = ShardedEnsemble(ens, costs=costs, concurrent=conc)
+            ms, _ = time_region(ctx, lambda: se(x), 20, 5)
+            row[mode + "_ms"] = ms / 20
+        row["speedup"] = row["serial_ms"] / row["concurrent_ms"]
+        row["volumes_per_s"] = B / (row["concurrent_ms"] * 1e-3)
+        out[f"B={B}"] = row
+    del ens, members
+    torch.cuda.empty_cache()
+    return out
+
+
+def sharded_e2e_step(sharded, x_host, res_host):
+    import torch
+    out = sharded(x_host)                       # host tensor: the call ships this rank's batch slices itself
+    res_host.copy_(out.reshape(res_host.shape), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
 
 
 def main():
@@ -147,248 +446,96 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    wl = workload(args)
-    import torch
-    import vit3d_b200
-    from oracle import vit3d_oracle as O
-    cfgs = [vit3d_b200.north_star_config(c) for c in wl["confs"]]
-    flops_per_vol = sum(O.fwd_flops_per_volume(c) for c in cfgs) * (3.0 if wl["train"] else 1.0)
+    wl = WORKLOADS[args.workload]
+    B = args.batch or wl["batch"]
 
     if args.impl == "reference":
         if rank != 0:
             return
-        sample = min(args.cpu_sample, wl["batch"])
-        steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-        v, ms = cpu_arm(args, cfgs, wl["train"], steps, warm, sample)
+        import vit3d_b200
+        cfgs = [vit3d_b200.north_star_config(c) for c in wl["confs"]]
+        # like for like: the GPU arm's batch, the driver's --steps / --warmup (cut short only by the time budget)
+        # (the reference has no GPU path to put beside `value`: every rank of the GPU arm runs this same batch)
+        v, ms, done, warm_done = cpu_arm(cfgs, wl["train"], max(1, args.steps), max(1, args.warmup), B, budget_s=args.cpu_budget)
         print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+            "warmup": warm_done, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if len(wl["confs"]) > 1 else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "batch_per_step": sample},
+            "config": workload_config(wl, B, args.gpus, args.vis),
+            "steps_requested": args.steps, "warmup_requested": args.warmup,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                             "sample": f"{steps} steps x {sample} volumes, oracle port of models/modeling.py, torch CPU fp32"},
+                             "sample": f"{done} steps x {B} volumes (one rank's batch), oracle port of models/modeling.py, torch CPU "
+                                       f"fp32, {os.cpu_count()} threads; budget {args.cpu_budget:.0f} s"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return
 
+    import torch
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU arm"
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
+    ctx = Ctx()
+    ctx.rank, ctx.world, ctx.dev = rank, world, torch.device("cuda", local_rank)
+    ctx.numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    ctx.dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    from vit3d_b200.models.modeling import TransformerEnsemble, VisionTransformer
-    L = vit3d_b200._lib.lib()
-
-    B = wl["batch"]
-    members = []
-    for j, c in enumerate(cfgs):
-        m = VisionTransformer(c, 128, zero_head=True, num_classes=1, vis=bool(args.vis), precision=args.precision)
-        m.load_state_dict(O.init_state_dict(c, seed=42 + j))
-        members.append(m)
-    model = members[0] if len(members) == 1 else TransformerEnsemble(*members, in_features=1)
-    model.to(dev)
-    train = wl["train"]
-    model.train(train)
-    x_host = O.synth_volumes(B, seed=42 + (rank if len(members) == 1 else 0)).pin_memory()
-    y_host = O.synth_labels(B).pin_memory()
-    x_dev = x_host.to(dev)
-    y_dev = y_host.to(dev)
-    opt = reducer = sharded = None
-    if train:
-        # the reference's optimizer (train_baseline_cv.py:111-114) as one fused launch over a flat arena,
-        # gradients all-reduced per encoder Block while backward is still running
-        from vit3d_b200.dist import GradReducer, global_pos_weight
-        from vit3d_b200.optim import FusedSGD
-        opt = FusedSGD(model.parameters(), lr=1e-4, momentum=0.9, weight_decay=1e-2)
-        reducer = GradReducer(model, arena=opt.arena) if (world > 1 and not args.graphs) else None
-    elif len(members) > 1:
-        from vit3d_b200.dist import ShardedEnsemble
-        sharded = ShardedEnsemble(model, costs=[O.fwd_flops_per_volume(c) for c in cfgs])
-
-    graphed = None
-    if args.graphs and train:
-        from vit3d_b200.graphs import GraphedTrainStep
-        graphed = GraphedTrainStep(model, opt, warmup=2, data_parallel=world > 1)
-        reducer = None
-    elif args.graphs and not train and sharded is None:
-        from vit3d_b200.graphs import GraphedInference
-        graphed = GraphedInference(model)
-        # the resident batch lives in the graph's own input buffer (no device-to-device copy per replay); the
-        # end-to-end loop below passes its double-buffered H2D targets, which the call copies in
-        x_dev = graphed.input_like(x_dev)
-
-    def step_dev(x, y):
-        if graphed is not None:
-            if train:
-                return graphed(x, y, global_pos_weight(y) if world > 1 else O.balanced_pos_weight(y_host))
-            out = graphed(x)
-            return out[0] if isinstance(out, tuple) else out
-        if train:
-            pw = global_pos_weight(y) if world > 1 else O.balanced_pos_weight(y_host)
-            if reducer is not None:
-                reducer.prepare()
-            else:
-                opt.zero_grad()
-            loss = model(x, y, pw)
-            loss.backward()
-            if reducer is not None:
-                reducer.finish(scale=False)
-            opt.step(grad_scale=1.0 / world)
-            return loss
-        if sharded is not None:
-            return sharded(x)
-        with torch.no_grad():
-            out = model(x)
-        return out[0] if isinstance(out, tuple) else out
-
-    def timed(fn, steps, warm):
-        for _ in range(warm):
-            fn()
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0 = L.vit3d_launch_count()
-        r0 = graphed.replays if graphed is not None else 0
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        n1 = L.vit3d_launch_count()
-        if graphed is not None:     # kernels replayed from the captured graph (counted once, at capture)
-            n1 += (graphed.replays - r0) * graphed.launches_per_replay
-        ms = e0.elapsed_time(e1)
-        if dist is not None:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-            dist.barrier()
-        return ms, n1 - n0
+        dist.init_process_group("nccl", device_id=ctx.dev)
+        ctx.dist = dist
+    args.warmup = max(3, args.warmup)           # timing rule: at least 3 untimed warm-up steps
 
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    # timing rule: at least 3 untimed warm-up steps, whatever was asked for (the JSON line reports what was run)
-    args.warmup = max(3, args.warmup)
-    ms_dev, launches = timed(lambda: step_dev(x_dev, y_dev), args.steps, args.warmup)
+    head = run_leg(ctx, args, args.workload, args.steps, args.warmup, args.precision)
     clk = clocks.stop() if rank == 0 else None
+    head_ctx = ctx.last
 
-    res_host = torch.empty((B, 1) if not train else (), dtype=torch.float32).pin_memory()
+    legs = {}
+    if args.legs == "auto":
+        names = [k for k in WORKLOADS if k != args.workload] + (["conf5_infer_tf32"] if args.workload == "conf5_infer" and
+                                                                args.precision == "bf16" else [])
+    elif args.legs == "none":
+        names = []
+    else:
+        names = [s for s in args.legs.split(",") if s]
+    for nm in names:
+        try:
+            if nm == "conf5_infer_tf32":
+                legs[nm] = run_leg(ctx, args, "conf5_infer", args.leg_steps, 3, "tf32", with_u8=False)
+            else:
+                legs[nm] = run_leg(ctx, args, nm, args.leg_steps, 3, args.precision)
+        except Exception as e:          # a failed extra leg must not take the headline down with it
+            legs[nm] = {"error": f"{type(e).__name__}: {e}"[:400]}
+            if ctx.dist is not None:
+                raise
 
-    # End-to-end: every step copies ITS batch from pinned host memory (H2D on a copy stream, double
-    # buffered so the copy of step s+1 overlaps the compute of step s), runs the public module call and
-    # reads the result back to the host (D2H) before the step counts as done.
-    copy_stream = torch.cuda.Stream()
-    xbuf = [torch.empty_like(x_dev) for _ in range(2)]
-    ybuf = [torch.empty_like(y_dev) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
+    if world == 1 and args.legs == "auto":
+        try:
+            legs["ensemble_small_batch"] = ensemble_small_batch_probe(ctx, args)
+        except Exception as e:
+            legs["ensemble_small_batch"] = {"error": f"{type(e).__name__}: {e}"[:400]}
 
-    def issue_copy(s):
-        b = s & 1
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[b])          # the compute that read this buffer two steps ago is done
-            xbuf[b].copy_(x_host, non_blocking=True)
-            if train:
-                ybuf[b].copy_(y_host, non_blocking=True)
-            ready[b].record(copy_stream)
-
-    def run_e2e(steps):
-        main = torch.cuda.current_stream()
-        for b in range(2):
-            consumed[b].record(main)
-        issue_copy(0)
-        for s in range(steps):
-            b = s & 1
-            main.wait_event(ready[b])
-            out = step_dev(xbuf[b], ybuf[b] if train else None)
-            consumed[b].record(main)
-            if s + 1 < steps:
-                issue_copy(s + 1)
-            res_host.copy_(out.detach().reshape(res_host.shape), non_blocking=True)
-            main.synchronize()
-
-    def timed_e2e(steps, warm):
-        run_e2e(warm)
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        run_e2e(steps)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        if dist is not None:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-            dist.barrier()
-        return ms
-
-    ms_e2e = timed_e2e(args.steps, max(3, args.warmup // 2))
-
-    # N2 variant of the end-to-end number (extra, not the contract's `e2e`): the same volumes cross PCIe as
-    # uint8 (they ARE 8-bit images minus a mean) and (u8 - mean) runs on the device.
-    e2e_u8 = None
-    if not train and len(members) == 1:
-        u8_host, mean = O.synth_volumes_u8(B, seed=42 + rank)
-        u8_host = u8_host.pin_memory()
-        model.input_mean = mean
-        x_keep, xbuf_keep = x_host, xbuf
-        x_host = u8_host
-        xbuf = [torch.empty(u8_host.shape, dtype=torch.uint8, device=dev) for _ in range(2)]
-        ms_u8 = timed_e2e(args.steps, max(3, args.warmup // 2))
-        x_host, xbuf = x_keep, xbuf_keep
-        e2e_u8 = {"value": world * B * args.steps / (ms_u8 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(B * 81920),
-                  "d2h_bytes_per_step": int(res_host.numel() * 4), "ms_per_step": ms_u8 / args.steps,
-                  "note": "volumes shipped as uint8 + mean (N2 input path), (u8 - mean) on the device"}
-
-    units = B if len(members) > 1 else world * B          # the sharded ensemble splits ONE batch over the ranks
-    value = units * args.steps / (ms_dev * 1e-3)
-    e2e = units * args.steps / (ms_e2e * 1e-3)
-
-    # ---- roofline of the dominant kernel (fc1/fc2 GEMM pair = 75-82 % of the FLOPs), timed alone
-    roof = None
-    cpu_base = None
+    roof = cpu_base = None
     if rank == 0:
-        roof = roofline_probe(args, cfgs[0], B, dev, train)
-        if not args.no_cpu_baseline:
-            sample = min(args.cpu_sample, B)
-            v, ms = cpu_arm(args, cfgs, train, 3, 1, sample)
+        roof = roofline_probe(args, head_ctx["cfgs"][0], head_ctx["B"], ctx.dev, head_ctx["train"])
+        if not args.no_cpu_baseline and world == 1:
+            sample = min(args.cpu_sample, head_ctx["B"])
+            v, ms, done, _ = cpu_arm(head_ctx["cfgs"], head_ctx["train"], 3, 1, sample)
             cpu_base = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                        "sample": f"3 steps x {sample} volumes of the same workload, oracle port of models/modeling.py, "
+                        "sample": f"{done} steps x {sample} volumes of the same workload, oracle port of models/modeling.py, "
                                   f"torch CPU fp32, {os.cpu_count()} threads"}
-    if rank == 0:
-        peaks = load_peaks()
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-            "scaling": "strong" if len(members) > 1 else "weak",
-            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": wl["name"], "batch_per_gpu": B, "global_batch": units, "vis": bool(args.vis),
-                       "precision": args.precision, "cuda_graph": graphed is not None, "l2": "inputs larger than L2 (batch of fp32 volumes = %.0f MB)" % (B * 327680 / 1e6),
-                       "parallelism": (f"dp{world}: batch sharded, fwd+bwd replayed from a CUDA graph, one NCCL all-reduce of the flat gradient arena, fused SGD step"
-                                       if train else (f"{world} ranks: (member, batch-slice) work list balanced by FLOPs, all-gather of member logits, meta-head on every rank"
-                                                      if len(members) > 1 else f"dp{world} (independent volumes, no data-path collective)"))},
-            "model_tflops": value * flops_per_vol / 1e12,
-            "model_frac_of_bf16_sustained": value * flops_per_vol / 1e12 / (world * peaks["bf16_tflops_sustained"]),
-            "clocks": clk,
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * 327680 + (B * 4 if train else 0)),
-                    "d2h_bytes_per_step": int(res_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
-            "e2e_u8": e2e_u8,
-            "gpu_launches": int(launches),
-            "roofline": roof,
-            "cpu_baseline": cpu_base,
-        }
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+                "scaling": head["scaling"], "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                "config": head["config"], "exec": head["exec"], "model_tflops": head["model_tflops"],
+                "model_frac_of_bf16_sustained": head["model_frac_of_bf16_sustained"], "clocks": clk,
+                "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "launches_per_step": head["launches_per_step"],
+                "collective": head["collective"], "bytes_per_collective": head["bytes_per_collective"],
+                "numa_bound_cpus": ctx.numa_cpus, "roofline": roof, "cpu_baseline": cpu_base, "workloads": legs}
         print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    if ctx.dist is not None:
+        ctx.dist.destroy_process_group()
 
 
 def load_peaks():
@@ -415,8 +562,9 @@ def _time_launches(fn, iters=10, warm=3):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures under profiles/
-# (only valid for the captured shape: conf 5, batch 1024, bf16)
-NCU_TRAFFIC = {"mlp_ln": 162.7e6, "fc1_gelu": 257.2e6}
+# (valid only for the captured shape: conf 5, batch 1024, bf16; None otherwise)
+NCU_TRAFFIC = {"mlp_ln": (162.7e6, "profiles/r01_fused_mlp_ln_ncu_full_raw.csv"),
+               "fc1_gelu": (257.2e6, "profiles/r01_per_kernel_probe_conf5_b1024.log")}
 
 
 def roofline_probe(args, cfg, B, dev, train=False):
@@ -458,7 +606,9 @@ def roofline_probe(args, cfg, B, dev, train=False):
                           "M=%d H=%d d=%d, tcgen05)" % (M, H, d),
                 "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_tflops"],
-                "traffic": NCU_TRAFFIC["mlp_ln"] if captured else None, "traffic_unit": "bytes per launch",
+                "traffic": NCU_TRAFFIC["mlp_ln"][0] if captured else None, "traffic_unit": "bytes per launch",
+                "traffic_source": (NCU_TRAFFIC["mlp_ln"][1] + " (ncu --set full capture of this shape; constant, not re-measured "
+                                   "by this run)") if captured else None,
                 "algorithmic_bytes": float(M * H * (2 + 4 + 4 + 2) + 2 * H * d * 2),
                 "algorithmic_flops": flops, "ms_per_launch": ms, "peak_source": peaks.get("source"),
                 "how": "kernel timed alone, 10 launches, CUDA events (burst peak applies)"}
@@ -496,7 +646,8 @@ def roofline_probe(args, cfg, B, dev, train=False):
     fc1 = {"kernel": "fc1+GELU GEMM (vit3d_linear_fwd, M=%d N=%d K=%d, %s)" % (M, d, H, "tcgen05" if tc else "fp32 FMA"),
            "bound": "tensor", "achieved": flops1 / (ms1 * 1e-3) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
            "frac": flops1 / (ms1 * 1e-3) / 1e12 / peaks["bf16_tflops"],
-           "traffic": NCU_TRAFFIC["fc1_gelu"] if captured else None, "traffic_unit": "bytes per launch",
+           "traffic": NCU_TRAFFIC["fc1_gelu"][0] if captured else None, "traffic_unit": "bytes per launch",
+           "traffic_source": NCU_TRAFFIC["fc1_gelu"][1] if captured else None,
            "algorithmic_bytes": float(M * H * 2 + d * H * 2 + M * d * 2) if lp else None, "ms_per_launch": ms1,
            "peak_source": peaks.get("source"), "how": "kernel timed alone, 10 launches, CUDA events (burst peak applies)"}
     if not fused:

@@ -238,6 +238,75 @@ int vit3d_adam_step(float* p, const float* g, float* m, float* v, long long n, f
 /* lr_dev / step_dev: optional DEVICE scalars that override lr / step (CUDA-graph replays under an LR
  * schedule).  first_step may stay 0 when the momentum buffer starts zeroed (same arithmetic). */
 
+/* ---------------------------------------------------------------- a8: fused BF16 training step (hidden 256)
+ * The autograd backward of modeling.py:118-124, :187-197 (loss.backward() at train_baseline_cv.py:176) as an
+ * explicit kernel sequence, driven by 3d_vit_ensemble_b200/fused_train.py.  The pieces below are the ones the
+ * per-operator entry points above do not offer: dropout masks as bit arrays applied inside GEMM epilogues,
+ * LayerNorm backward fused with the residual-gradient add / the bf16 operand copy / the bias-gradient column
+ * sums, packed q|k|v weight gradients that land in three parameters, one-launch weight-shadow refresh. */
+#define VIT3D_MAX_DROP_SEGS 40
+#define VIT3D_SHADOW_JOB_BYTES 40
+/* cudaMemsetAsync(p, 0, bytes) on `stream` (gradient arena zeroing without a framework fill kernel) */
+int vit3d_memset_zero(void* p, size_t bytes, vit3d_stream_t stream);
+/* 1 if the fused training step serves this model shape (B volumes of S tokens, hidden H, mlp width d) */
+int vit3d_train_supported(int B, int S, int H, int heads, int d);
+/* Keep bits of ALL Dropout sites of one training step (modeling.py:121,123,174) in one launch.  Segment i
+ * covers nelems[i] (% 32 == 0) elements of dropout site sites[i]; segments are laid end to end in `bits`
+ * (bit e of 32-bit word w of a segment = element 32 w + e, i.e. byte e/8, bit e%8 in memory).  The decision
+ * for an element equals vit3d_dropout / vit3d_dropout_mask for the same (seed, site, step, index).  `sites`
+ * and `nelems` are HOST arrays (nseg <= VIT3D_MAX_DROP_SEGS); step_dev as in vit3d_dropout. */
+int vit3d_dropout_bits(uint32_t* bits, int nseg, const unsigned* sites, const long long* nelems, float p,
+                       unsigned long long seed, unsigned step, const unsigned* step_dev, vit3d_stream_t stream);
+/* LayerNorm over rows of 256 with an optional Dropout of its INPUT (Embeddings.dropout, modeling.py:174):
+ *   xd = x * keep * drop_scale  (written to x_dropped when drop_bits and x_dropped are given; else xd = x)
+ *   y  = LayerNorm(xd) * gamma + beta as bf16 (y_bf16) and/or fp32 (y_f32); mean / rstd [M] optional. */
+int vit3d_ln256_fwd(const float* x, const void* drop_bits, float drop_scale, float* x_dropped, const float* gamma,
+                    const float* beta, void* y_bf16, float* y_f32, float* mean, float* rstd, int M, float eps,
+                    vit3d_stream_t stream);
+/* LayerNorm-256 backward fused with what surrounds it in a pre-LN Block (modeling.py:187-197):
+ *   o       = (dres ? dres : 0) + LN'(dy)              gradient w.r.t. the LayerNorm input (+ the skip path)
+ *   ob      = o * keep * drop_scale (drop_bits given: the Dropout of modeling.py:123 / :174 below this point)
+ *   dx      = o, or ob when mask_f32 (fp32, optional, may alias dres)
+ *   dx_bf16 = bf16(ob) (optional): the operand of the dgrad / wgrad GEMMs of the Linear that produced this
+ *             tensor;  dbias += column sums of ob (that Linear's bias gradient, optional)
+ *   dgamma += sum dy * xhat;  dbeta += sum dy. */
+int vit3d_ln256_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                    const float* dres, const void* drop_bits, float drop_scale, int mask_f32, float* dx, void* dx_bf16,
+                    float* dgamma, float* dbeta, float* dbias, int M, vit3d_stream_t stream);
+/* dh = da * gelu'(pre) * keep * drop_scale (bf16 [M,d]; backward of Dropout(gelu(.)), modeling.py:120-121, with the
+ * mask read from keep bits, NULL = no dropout); db[d] += column sums of dh (the fc1 bias gradient, optional). */
+int vit3d_gelu_mask_bwd(const void* da, const void* pre, const void* drop_bits, float drop_scale, void* dh, float* db, int M,
+                        int d, vit3d_stream_t stream);
+/* head backward (modeling.py:281, num_classes 1): dencoded[B*S,H] = dlogits[b] * w on the cls rows, 0 elsewhere;
+ * dw[H] += sum_b dlogits[b] * encoded[b*S,:];  db[1] += sum_b dlogits[b]. */
+int vit3d_head_bwd(const float* dlogits, const float* encoded, const float* w, float* dencoded, float* dw, float* db, int B,
+                   int S, int H, vit3d_stream_t stream);
+/* Rewrites every low-precision weight shadow of a model from its fp32 masters in ONE launch.  `jobs` is a DEVICE
+ * array of njobs records of VIT3D_SHADOW_JOB_BYTES bytes, sorted by tile0:
+ *   { const float* src; void* dst; int rows, cols, ld, kind, tile0, tiles_c; }
+ * src [rows, cols] dense fp32; element (r, c) goes to dst[r*ld + c] as bf16 (kind 0), fp16 (2), fp32 rounded to
+ * TF32 (3) or fp32 (4), or to dst[c*ld + r] as bf16 (kind 1, transposed: the dgrad operand).  tile0 = index of the
+ * job's first 32 x 32 tile in the launch, tiles_c = ceil(cols/32); total_tiles = sum over jobs.  step_dev (optional
+ * device counter) is incremented by one: the dropout step of a CUDA-graph replay. */
+int vit3d_refresh_shadows(const void* jobs, int njobs, int total_tiles, unsigned* step_dev, vit3d_stream_t stream);
+/* training fc1 (modeling.py:119-121): pre = xn w1^T + b1 (bf16, saved for backward), act = Dropout(gelu(pre)) (bf16),
+ * Dropout from keep bits over [M,d] (NULL = none), all in the GEMM epilogue. */
+int vit3d_fc1_train_fwd(const void* xn, const void* w1_lp, const float* b1, void* pre, void* act, const void* drop_bits,
+                        float drop_scale, int M, int d, int H, vit3d_stream_t stream);
+/* training out-projection / fc2 (modeling.py:97,122-123 + the adds of :191,:196 + the next LayerNorm):
+ *   y = residual + Dropout(x w^T + bias) (drop_bits NULL = no dropout),  ln_out = LayerNorm(y) bf16 (optional, with
+ *   mean / rstd saved for vit3d_ln256_bwd).  N % 256 == 0 (LayerNorm: N == 256). */
+int vit3d_linear_res_train_fwd(const void* x, const void* w_lp, const float* bias, const float* residual, float* y,
+                               const void* drop_bits, float drop_scale, const float* gamma, const float* beta, float eps,
+                               void* ln_out, float* mean, float* rstd, int M, int N, int K, vit3d_stream_t stream);
+/* dw[N,K] += dy[M,N]^T x[M,K] (bf16 operands, tcgen05).  seg_rows > 0: rows [i*seg_rows, (i+1)*seg_rows) of the
+ * product accumulate into dw0 / dw1 / dw2 (the packed q|k|v projection: three parameters). */
+int vit3d_wgrad(const void* dy, const void* x, float* dw0, float* dw1, float* dw2, int seg_rows, int M, int N, int K,
+                vit3d_stream_t stream);
+/* vit3d_attn_bwd (BF16 mode) that also accumulates the q / k / v bias gradients (column sums of dqkv) */
+int vit3d_attn_bwd_bias(const void* dctx, const void* qkv, void* dqkv, float* db_q, float* db_k, float* db_v, int B, int S,
+                        int heads, int D, vit3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

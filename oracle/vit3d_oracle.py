@@ -175,13 +175,25 @@ def synth_labels(B: int, seed: int = 42) -> torch.Tensor:
 
 
 def balanced_pos_weight(y: torch.Tensor) -> Optional[torch.Tensor]:
-    """sklearn compute_class_weight('balanced') ratio w1/w0 = n_neg/n_pos used as the
-    scalar pos_weight the scripts pass (train_baseline_cv.py:168-169)."""
+    """TEST-FIXTURE weight: the ratio n_neg/n_pos.  tests/golden/*.npz were generated with this value fed
+    to the unmodified reference as `weights`, so it stays; it is NOT what the scripts compute per batch -
+    that is `sklearn_pos_weight` below (the two agree only on balanced batches)."""
     n_pos = float(y.sum())
     n_neg = float(y.numel()) - n_pos
     if n_pos == 0 or n_neg == 0:
         return None
     return torch.tensor(n_neg / n_pos, dtype=torch.float64)
+
+
+def sklearn_pos_weight(y: torch.Tensor) -> torch.Tensor:
+    """What train_baseline_cv.py:168-169 passes as pos_weight: compute_class_weight('balanced', classes=
+    unique(y), y) = n / (n_classes_present * bincount); entry [1] (= n / (2 n_pos)) when both classes are
+    present, else entry [0] = 1.0."""
+    n = float(y.numel())
+    n_pos = float(y.sum())
+    if n_pos == 0 or n_pos == n:
+        return torch.tensor(1.0, dtype=torch.float64)
+    return torch.tensor(n / (2.0 * n_pos), dtype=torch.float64)
 
 
 # --------------------------------------------------------------------------- forward

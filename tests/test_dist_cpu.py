@@ -68,7 +68,7 @@ def _dp_equals_big_batch(rank, world):
     # reference: single process, whole batch, global class weight
     ref = Toy()
     ref.load_state_dict(model.state_dict())
-    pw = (y.numel() - float(y.sum())) / float(y.sum())
+    pw = y.numel() / (2.0 * float(y.sum()))          # sklearn 'balanced' weights[1] (train_baseline_cv.py:168-169)
     loss = torch.nn.functional.binary_cross_entropy_with_logits(ref(x).reshape(-1), y, pos_weight=torch.tensor(pw))
     loss.backward()
     # DP: each rank sees its shard
@@ -156,3 +156,18 @@ def test_grad_reducer_counts_each_parameter_once():
         red._on_grad(p)
     assert all(v == 0 for v in red._pending.values()), red._pending
     red.remove()
+
+
+def test_pos_weight_matches_sklearn_balanced():
+    """dist.batch_pos_weight == what train_baseline_cv.py:168-169 computes with sklearn, including the
+    single-class batches (weights has one entry, 1.0) - ADVICE r1."""
+    import numpy as np
+    from sklearn.utils import class_weight
+    from oracle import vit3d_oracle as O
+    for labels in ([0, 0, 0, 1], [1, 1, 0, 1], [0, 1], [1, 1, 1, 1], [0, 0, 0, 0], [0, 1, 1, 0, 1, 0, 0, 0]):
+        y = np.asarray(labels, dtype=np.float32)
+        w = class_weight.compute_class_weight(class_weight="balanced", classes=np.unique(y), y=y)
+        want = float(w[1] if len(w) > 1 else w[0])
+        assert abs(float(D.batch_pos_weight(torch.tensor(y))) - want) < 1e-12, labels
+        assert abs(float(D.global_pos_weight(torch.tensor(y))) - want) < 1e-12, labels
+        assert abs(float(O.sklearn_pos_weight(torch.tensor(y))) - want) < 1e-12, labels

@@ -1,0 +1,217 @@
+"""Fused BF16 training step (fused_train.py) against the oracle (reference `loss = model(x, y, w); loss.backward()`,
+train_baseline_cv.py:171-176): eval-mode gradients, training mode with the reference's own dropout masks injected,
+training mode with the library's Philox masks, the per-operator path as a second opinion, and the CUDA-graph'd step.
+
+Tolerance: bf16 operands -> parameter gradients within 8 % relative L2 norm (measured 1-4 %), loss within 2e-2."""
+import numpy as np
+import pytest
+import torch
+
+import vit3d_b200
+from oracle import vit3d_oracle as O
+from tests.helpers import case_setup, load_golden, unpack_masks
+from vit3d_b200 import _lib, functional as F, fused_train
+from vit3d_b200.graphs import GraphedInference, GraphedTrainStep
+from vit3d_b200.optim import FusedSGD
+from vit3d_b200.models.modeling import VisionTransformer
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GRAD_RTOL = 0.08
+
+
+def build(name, dropout=None):
+    cfg, sd, x, y, w = case_setup(name)
+    if dropout is not None:
+        cfg.transformer["dropout_rate"] = dropout
+    m = VisionTransformer(cfg, 128, zero_head=True, num_classes=1, precision="bf16")
+    m.load_state_dict(sd)
+    return cfg, sd, m.to(DEV), x, y, w
+
+
+def grad_check(m, go, rtol, what, atol_scale=2e-4):
+    gscale = max(float(v.norm()) for v in go.values())
+    worst = 0.0
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        a, b = p.grad.detach().float().cpu(), go[k].float()
+        err, ref = float((a - b).norm()), float(b.norm())
+        assert err <= rtol * ref + atol_scale * gscale, (what, k, err, ref)
+        worst = max(worst, err / (ref + atol_scale * gscale))
+    return worst
+
+
+def site_masks(cfg, masks):
+    sites = {0: masks["emb"].reshape(-1)}
+    for i in range(cfg.transformer["num_layers"]):
+        sites[1 + 2 * i] = masks[("fc1", i)].reshape(-1)
+        sites[2 + 2 * i] = masks[("fc2", i)].reshape(-1)
+    return sites
+
+
+@pytest.mark.parametrize("name", ["conf5", "conf18", "conf1"])
+def test_fused_step_is_taken_and_matches_oracle_eval_mode(name):
+    cfg, sd, m, x, y, w = build(name)
+    m.eval()
+    assert fused_train.supported(m, x.to(DEV))
+    n0 = _lib.lib().vit3d_launch_count()
+    loss = m(x.to(DEV), y.to(DEV), w)
+    loss.backward()
+    launches = _lib.lib().vit3d_launch_count() - n0
+    L = cfg.transformer["num_layers"]
+    assert launches <= 17 * L + 20, launches            # 5 forward + 12 backward launches per Block
+    lo, go, _ = O.vit_loss_and_grads(sd, cfg, x, y, w, dtype=torch.float64)
+    assert abs(float(loss) - float(lo)) < 2e-2
+    grad_check(m, go, GRAD_RTOL, name)
+
+
+def test_fused_step_with_reference_dropout_masks():
+    """Training mode, the masks the unmodified reference drew (tests/golden/conf5.npz) injected as keep bits."""
+    g = load_golden("conf5")
+    cfg, sd, m, x, y, w = build("conf5")
+    masks = unpack_masks(g)
+    m.train()
+    with F.mask_injection(site_masks(cfg, masks)):
+        loss = m(x.to(DEV), y.to(DEV), w)
+        loss.backward()
+    assert abs(float(loss) - float(g["loss_train"])) < 2e-2
+    lo, go, _ = O.vit_loss_and_grads(sd, cfg, x, y, w, masks=masks, dtype=torch.float64)
+    grad_check(m, go, GRAD_RTOL, "conf5/ref-masks")
+
+
+def test_fused_step_own_masks_equal_dropout_mask_export():
+    """The keep bits vit3d_dropout_bits draws are the masks vit3d_dropout_mask exports for the same (seed, site,
+    step): the oracle with those masks reproduces the fused training step; a second step draws new masks."""
+    cfg, sd, m, x, y, w = build("conf5")
+    m.train()
+    torch.manual_seed(1234)
+    step = F._STATE["step"] + 1
+    loss = m(x.to(DEV), y.to(DEV), w)
+    loss.backward()
+    B, S, H, d = x.shape[0], 65, cfg.hidden_size, cfg.transformer["mlp_dim"]
+    p = cfg.transformer["dropout_rate"]
+    masks = {"emb": F.dropout_mask(B * S * H, p, 0, step, DEV).cpu().bool().reshape(B, S, H)}
+    for i in range(cfg.transformer["num_layers"]):
+        masks[("fc1", i)] = F.dropout_mask(B * S * d, p, 1 + 2 * i, step, DEV).cpu().bool().reshape(B, S, d)
+        masks[("fc2", i)] = F.dropout_mask(B * S * H, p, 2 + 2 * i, step, DEV).cpu().bool().reshape(B, S, H)
+    lo, go, _ = O.vit_loss_and_grads(sd, cfg, x, y, w, masks=masks, dtype=torch.float64)
+    assert abs(float(loss) - float(lo)) < 2e-2
+    grad_check(m, go, GRAD_RTOL, "conf5/own-masks")
+    m.zero_grad()
+    loss2 = m(x.to(DEV), y.to(DEV), w)
+    assert float(loss2) != float(loss)
+
+
+def test_dropout_bits_layout_and_rate():
+    """Bit e of word w = element 32 w + e; segments are laid end to end; the keep rate is 1 - p."""
+    n = [1 << 20, 1 << 18]
+    import ctypes as C
+    bits = torch.empty(sum(n) // 8, device=DEV, dtype=torch.uint8)
+    seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    _lib.call("vit3d_dropout_bits", bits.data_ptr(), 2, (C.c_uint * 2)(3, 8), (C.c_longlong * 2)(*n), 0.1, seed, 5, None,
+              torch.cuda.current_stream().cuda_stream)
+    unpacked = ((bits.view(-1, 1).to(torch.int32) >> torch.arange(8, device=DEV, dtype=torch.int32)) & 1).reshape(-1)
+    assert torch.equal(unpacked[:n[0]].to(torch.uint8), F.dropout_mask(n[0], 0.1, 3, 5, DEV))
+    assert torch.equal(unpacked[n[0]:].to(torch.uint8), F.dropout_mask(n[1], 0.1, 8, 5, DEV))
+    assert abs(float(unpacked.float().mean()) - 0.9) < 2e-3
+
+
+def test_fused_step_agrees_with_per_operator_path():
+    """Second opinion: the same bf16 arithmetic composed from the per-operator autograd Functions."""
+    cfg, sd, m, x, y, w = build("conf18")
+    m.eval()
+    loss = m(x.to(DEV), y.to(DEV), w)
+    loss.backward()
+    fused = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    m.zero_grad(set_to_none=True)
+    F._STATE["fused_train"] = False
+    try:
+        loss_op = m(x.to(DEV), y.to(DEV), w)
+        loss_op.backward()
+    finally:
+        F._STATE["fused_train"] = True
+    assert abs(float(loss) - float(loss_op)) < 5e-3
+    gmax = max(float(v.norm()) for v in fused.values())
+    for k, p in m.named_parameters():
+        err = float((p.grad - fused[k]).norm())
+        assert err <= 0.05 * float(fused[k].norm()) + 2e-4 * gmax, (k, err)
+
+
+def test_fused_step_into_flat_arena_accumulates_and_ragged_batches():
+    """Gradients accumulate (+=) straight into the optimizer's flat arena; batch sizes that do not fill 128-row
+    tiles (1, 3, 5 volumes) agree with the oracle."""
+    cfg, sd, m, x, y, w = build("conf5")
+    m.eval()
+    opt = FusedSGD(m.parameters(), lr=0.0)
+    for B in (1, 3, 5):
+        xb = O.synth_volumes(B, seed=5)
+        yb = O.synth_labels(max(B, 2))[:B]
+        opt.zero_grad()
+        for _ in range(2):                       # two backward passes: the arena holds their sum
+            loss = m(xb.to(DEV), yb.to(DEV), 1.3)
+            loss.backward()
+        assert all(p.grad.data_ptr() == gv.data_ptr() for p, gv in zip(opt.arena.params, opt.arena.grad_views))
+        lo, go, _ = O.vit_loss_and_grads(sd, cfg, xb, yb, torch.tensor(1.3), dtype=torch.float64)
+        assert abs(float(loss) - float(lo)) < 2e-2
+        grad_check(m, {k: 2 * v for k, v in go.items()}, GRAD_RTOL, f"arena/B={B}")
+    F.enable_direct_grads(False)
+
+
+def test_graphed_fused_train_step_has_only_library_kernels_and_matches_eager():
+    """GraphedTrainStep over the fused engine: same weights as eager steps (dropout off), launch budget per step."""
+    res = []
+    launches = None
+    for graphed in (False, True):
+        cfg = vit3d_b200.get_config(16, 512, 2, 256, 8, dropout_rate=0.0)
+        m = VisionTransformer(cfg, 128, zero_head=True, num_classes=1, precision="bf16")
+        m.load_state_dict(O.init_state_dict(cfg, seed=42))
+        m.to(DEV).train()
+        opt = FusedSGD(m.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-2)
+        x = O.synth_volumes(4, seed=7).to(DEV)
+        y = O.synth_labels(4).to(DEV)
+        if graphed:
+            step = GraphedTrainStep(m, opt, warmup=3)
+            for _ in range(4):
+                loss = step(x, y, 1.5)
+            assert step.fused
+            launches = step.launches_per_replay
+            assert opt._steps == 7
+        else:
+            for _ in range(7):
+                opt.zero_grad()
+                loss = m(x, y, 1.5)
+                loss.backward()
+                opt.step()
+        torch.cuda.synchronize()
+        res.append((float(loss), {k: v.detach().clone() for k, v in m.state_dict().items()}))
+        F._STATE["step_dev"] = None
+        F.enable_direct_grads(False)
+    (le, se), (lg, sg) = res
+    assert abs(le - lg) < 2e-3 * max(1.0, abs(le)), (le, lg)
+    for k in se:
+        d = float((se[k] - sg[k]).abs().max())
+        assert d <= 2e-3 * float(se[k].abs().max()) + 1e-6, (k, d)
+    assert launches is not None and launches <= 17 * 2 + 22, launches
+
+
+def test_graphed_inference_recaptures_after_weight_update():
+    """a graph captured before an optimizer step / load_state_dict must not replay stale weight shadows."""
+    cfg = vit3d_b200.get_config(16, 512, 2, 256, 8, dropout_rate=0.0)
+    m = VisionTransformer(cfg, 128, zero_head=True, num_classes=1, precision="bf16")
+    m.load_state_dict(O.init_state_dict(cfg, seed=42))
+    m.to(DEV).eval()
+    g = GraphedInference(m)
+    x = O.synth_volumes(4, seed=3).to(DEV)
+    first = g(x)[0].clone()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(1.05)                                   # bumps every parameter's version
+    with torch.no_grad():
+        eager = m(x)[0].clone()
+    again = g(x)[0].clone()
+    assert g.recaptures == 1
+    assert torch.equal(again, eager) and not torch.equal(again, first)
+    m.load_state_dict(O.init_state_dict(cfg, seed=43))
+    with torch.no_grad():
+        eager2 = m(x)[0].clone()
+    assert torch.equal(g(x)[0], eager2)

@@ -28,7 +28,7 @@ for prec, rtol in (("fp32", 2e-3), ("bf16", 6e-2)):
     ref = VisionTransformer(cfg, 128, zero_head=True, num_classes=1, precision=prec).to(dev)
     ref.load_state_dict(sd); ref.train()
     F.enable_direct_grads(False)
-    loss_ref = ref(x, y, O.balanced_pos_weight(y.cpu()))
+    loss_ref = ref(x, y, O.sklearn_pos_weight(y.cpu()))
     loss_ref.backward()
     # DP on the shard of this rank
     m = VisionTransformer(cfg, 128, zero_head=True, num_classes=1, precision=prec).to(dev)
