@@ -88,6 +88,8 @@ SIGNATURES = {
     "vit3d_ln256_fwd": (_i, [_p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _i, _f, _p]),
     "vit3d_ln256_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _f, _i, _p, _p, _p, _p, _p, _i, _p]),
     "vit3d_gelu_mask_bwd": (_i, [_p, _p, _p, _f, _p, _p, _i, _i, _p]),
+    "vit3d_mlp_bwd": (_i, [_p, _p, _p, _p, _p, _f, _p, _p, _p, _i, _i, _i, _p]),
+    "vit3d_mlp_bwd_supported": (_i, [_i, _i, _i]),
     "vit3d_head_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "vit3d_refresh_shadows": (_i, [_p, _i, _i, _p, _p]),
     "vit3d_fc1_train_fwd": (_i, [_p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _p]),

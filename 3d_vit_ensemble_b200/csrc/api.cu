@@ -524,6 +524,16 @@ int vit3d_attn_bwd_bias(const void* dctx, const void* qkv, void* dqkv, float* db
   if (!tc_attn_supported(S, heads, D)) V3_UNSUPPORTED("attn_bwd_bias: unsupported shape S=%d heads=%d D=%d", S, heads, D);
   return tc_attn_bwd(dctx, qkv, dqkv, db_q, db_k, db_v, B, S, heads, D, as_stream(stream));
 }
+int vit3d_mlp_bwd_supported(int M, int H, int d) { return tc_mlp_bwd_supported(M, H, d) ? 1 : 0; }
+int vit3d_mlp_bwd(const void* gy, const void* w2_t_lp, const void* w1_t_lp, const void* pre, const void* drop_bits,
+                  float drop_scale, void* dh, float* dxn, float* db1, int M, int H, int d, vit3d_stream_t stream) {
+  V3_REQUIRE(gy && w2_t_lp && w1_t_lp && pre && dh && dxn && M >= 0 && H > 0 && d > 0, "mlp_bwd: bad argument");
+  V3_REQUIRE(((reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(dh) |
+               reinterpret_cast<uintptr_t>(dxn)) & 15) == 0, "mlp_bwd: buffers must be 16-byte aligned");
+  if (M == 0) return VIT3D_OK;
+  return tc_mlp_bwd(gy, w2_t_lp, w1_t_lp, pre, reinterpret_cast<const uint32_t*>(drop_bits), drop_scale, dh, dxn, db1, M, H, d,
+                    as_stream(stream));
+}
 int vit3d_train_supported(int B, int S, int H, int heads, int d) {
   if (B <= 0 || H != 256 || heads <= 0 || H % heads) return 0;
   const int M = B * S;

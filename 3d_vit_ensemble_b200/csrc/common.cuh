@@ -143,17 +143,24 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
   o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
   return o;
 }
-// keep-decision for element index i (64-bit) of dropout site `site` at step `step`
+// keep-decision for element index i (64-bit) of dropout site `site` at step `step`.  One Philox block serves EIGHT
+// consecutive elements: element i reads 16-bit lane (i & 7) of block (i >> 3) - lane 2k = low half of word k, lane
+// 2k+1 = its high half - and is kept when the lane is >= thresh16, so P(keep) = 1 - thresh16 / 65536 (p = 0.1 ->
+// 0.100006).  Halving the Philox calls per element matters: a conf-18 step at batch 256 draws 4.4e8 decisions.
+__host__ __device__ __forceinline__ uint32_t dropout_lane16(const Philox4& r, int lane) {
+  const uint32_t w = r.v[lane >> 1];
+  return (lane & 1) ? (w >> 16) : (w & 0xffffu);
+}
 __host__ __device__ __forceinline__ bool dropout_keep(unsigned long long seed, uint32_t site, uint32_t step,
-                                                      unsigned long long i, uint32_t thresh) {
-  const unsigned long long blk = i >> 2;
+                                                      unsigned long long i, uint32_t thresh16) {
+  const unsigned long long blk = i >> 3;
   Philox4 r = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), site, step, (uint32_t)seed, (uint32_t)(seed >> 32));
-  return r.v[i & 3] >= thresh;   // P(keep) = 1 - thresh / 2^32
+  return dropout_lane16(r, (int)(i & 7)) >= thresh16;
 }
 static inline uint32_t dropout_thresh(float p) {
-  double t = (double)p * 4294967296.0;
+  double t = (double)p * 65536.0 + 0.5;
   if (t < 0) t = 0;
-  if (t > 4294967295.0) t = 4294967295.0;
+  if (t > 65535.0) t = 65535.0;
   return (uint32_t)t;
 }
 

@@ -708,15 +708,11 @@ __global__ void __launch_bounds__(256) gelu_bwd_bf16_kernel(const uint4* __restr
     const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
     float keep[8];
     if (DROP) {
-      // elements 8q .. 8q+7 = Philox blocks 2q and 2q+1 (4 elements per block, as in dropout4_kernel)
-      const unsigned long long b0 = 2ull * (unsigned long long)q;
+      // elements 8q .. 8q+7 = the eight 16-bit lanes of Philox block q (common.cuh dropout_keep)
+      const unsigned long long b0 = (unsigned long long)q;
       const Philox4 r0 = philox4x32_10((uint32_t)b0, (uint32_t)(b0 >> 32), site, step, (uint32_t)seed, (uint32_t)(seed >> 32));
-      const Philox4 r1 = philox4x32_10((uint32_t)(b0 + 1), (uint32_t)((b0 + 1) >> 32), site, step, (uint32_t)seed, (uint32_t)(seed >> 32));
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        keep[j] = r0.v[j] >= th ? sc : 0.f;
-        keep[4 + j] = r1.v[j] >= th ? sc : 0.f;
-      }
+      for (int j = 0; j < 8; ++j) keep[j] = dropout_lane16(r0, j) >= th ? sc : 0.f;
     }
     uint32_t ow[4];
 #pragma unroll
@@ -767,7 +763,10 @@ __global__ void __launch_bounds__(256) dropout4_kernel(const void* __restrict__ 
                                                        const unsigned* __restrict__ step_dev) {
   if (step_dev) step += *step_dev;
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
-    const Philox4 r = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), site, step, (uint32_t)seed, (uint32_t)(seed >> 32));
+    // elements 4q .. 4q+3 = 16-bit lanes 4 (q & 1) .. of Philox block q >> 1 (common.cuh dropout_keep)
+    const long long qb = q >> 1;
+    const Philox4 r = philox4x32_10((uint32_t)qb, (uint32_t)(qb >> 32), site, step, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const int l0 = (int)(q & 1) * 4;
     const long long i = q * 4;
     float v[4], res[4] = {0.f, 0.f, 0.f, 0.f};
     if (i + 3 < n) {
@@ -789,7 +788,7 @@ __global__ void __launch_bounds__(256) dropout4_kernel(const void* __restrict__ 
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = (r.v[j] >= th ? v[j] * sc : 0.f) + res[j];
+      for (int j = 0; j < 4; ++j) v[j] = (dropout_lane16(r, l0 + j) >= th ? v[j] * sc : 0.f) + res[j];
       if (F32) {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + i) = make_float4(v[0], v[1], v[2], v[3]);
       } else {
@@ -800,7 +799,7 @@ __global__ void __launch_bounds__(256) dropout4_kernel(const void* __restrict__ 
       }
     } else {
       for (int j = 0; j < 4 && i + j < n; ++j) {
-        float o = r.v[j] >= th ? ld_any(x, i + j, F32) * sc : 0.f;
+        float o = dropout_lane16(r, l0 + j) >= th ? ld_any(x, i + j, F32) * sc : 0.f;
         if (residual) o += ld_any(residual, i + j, F32);
         st_any(y, i + j, F32, o);
       }

@@ -37,15 +37,18 @@ __global__ void __launch_bounds__(256) dropout_bits_kernel(uint32_t* __restrict_
   for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
     int s = 0;
     while (s + 1 < segs.n && w >= segs.word0[s + 1]) ++s;
-    const unsigned long long blk0 = (unsigned long long)(w - segs.word0[s]) * 8ull;   // Philox block = 4 elements
+    const unsigned long long blk0 = (unsigned long long)(w - segs.word0[s]) * 4ull;   // Philox block = 8 elements
     const unsigned site = segs.site[s];
     uint32_t word = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 4; ++j) {
       const unsigned long long b = blk0 + j;
       const Philox4 r = philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), site, step, (uint32_t)seed, (uint32_t)(seed >> 32));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) word |= (r.v[k] >= th ? 1u : 0u) << (4 * j + k);
+      for (int k = 0; k < 4; ++k) {
+        word |= ((r.v[k] & 0xffffu) >= th ? 1u : 0u) << (8 * j + 2 * k);
+        word |= ((r.v[k] >> 16) >= th ? 1u : 0u) << (8 * j + 2 * k + 1);
+      }
     }
     bits[w] = word;
   }

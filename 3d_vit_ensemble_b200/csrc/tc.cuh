@@ -50,6 +50,11 @@ int tc_mlp2_fwd(const void* xn, const void* w1, const float* b1, const void* w2_
                 float* y, const float* gamma, const float* beta, float eps, void* ln_out, int ln_f32, int M, int H, int d,
                 cudaStream_t st);
 
+// k_tc_mlp_bwd.cu: fused data-gradient chain of the MLP backward (dgrad fc2 -> GELU' x dropout mask -> dgrad fc1)
+bool tc_mlp_bwd_supported(int M, int H, int d);
+int tc_mlp_bwd(const void* gy, const void* w2_t, const void* w1_t, const void* pre, const uint32_t* bits, float scale,
+               void* dh, float* dxn, float* db1, int M, int H, int d, cudaStream_t st);
+
 bool tc_attn_supported(int S, int heads, int D);
 int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int heads, int D, cudaStream_t st);
 // db_q / db_k / db_v (each [heads*D] fp32, all or none): += column sums of dq / dk / dv (the q, k, v bias gradients)

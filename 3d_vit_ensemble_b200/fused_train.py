@@ -13,7 +13,7 @@ What the per-operator path (functional.py) pays and this one does not:
   * q, k, v as one packed projection without torch.cat: packed shadows, and the packed weight gradient lands in
     the three parameters' gradients directly (vit3d_wgrad with row segments).
 
-Per encoder Block: 5 launches forward, 12 backward.  Reference line numbers: models/modeling.py.
+Per encoder Block: 5 launches forward, 10 backward.  Reference line numbers: models/modeling.py.
 """
 from __future__ import annotations
 
@@ -346,6 +346,7 @@ def backward(model, saved, dloss: Optional[torch.Tensor] = None):
     dctx = torch.empty(M, H, device=dev, dtype=bf)
     dqkv = torch.empty(M, 3 * H, device=dev, dtype=bf)
     dxn = denc                                            # fp32 [M,H] scratch for the dgrad outputs
+    fused_mlp = F._STATE.get("fused_mlp_bwd", True) and bool(_lib.lib().vit3d_mlp_bwd_supported(M, H, d))
     last = enc.layer[L - 1]
     call("vit3d_ln256_bwd", ptr(denc), ptr(saved["x_last"]), ptr(saved["mean_f"]), ptr(saved["rstd_f"]), ptr(en.weight), None,
          ptr(bits2[L - 1]), scale, 0, ptr(g), ptr(gb), G(en.weight), G(en.bias), G(last.ffn.fc2.bias), M, st)
@@ -358,12 +359,18 @@ def backward(model, saved, dloss: Optional[torch.Tensor] = None):
         r = saved["layers"][i]
         # ---- Mlp backward (modeling.py:118-124): fc2, Dropout + GELU, fc1
         call("vit3d_wgrad", ptr(gb), ptr(r["act"]), G(f.fc2.weight), None, None, 0, M, H, d, st)
-        call("vit3d_linear_fwd", ptr(gb), H, 0, ptr(sh["w2_t"]), ptr(sh["w2_t"]), None, None, ptr(dwide), 0, None, 0, M, d, H,
-             _BF16, st)
-        call("vit3d_gelu_mask_bwd", ptr(dwide), ptr(r["pre"]), ptr(bits1[i]), scale, ptr(dwide), G(f.fc1.bias), M, d, st)
-        call("vit3d_wgrad", ptr(dwide), ptr(r["xn2"]), G(f.fc1.weight), None, None, 0, M, d, H, st)
-        call("vit3d_linear_fwd", ptr(dwide), d, 0, ptr(sh["w1_t"]), ptr(sh["w1_t"]), None, None, ptr(dxn), 1, None, 0, M, H, d,
-             _BF16, st)
+        if fused_mlp:
+            # dgrad(fc2) -> GELU' x mask -> dgrad(fc1) in one kernel: `da` stays on chip, dh is written once
+            call("vit3d_mlp_bwd", ptr(gb), ptr(sh["w2_t"]), ptr(sh["w1_t"]), ptr(r["pre"]), ptr(bits1[i]), scale, ptr(dwide),
+                 ptr(dxn), G(f.fc1.bias), M, H, d, st)
+            call("vit3d_wgrad", ptr(dwide), ptr(r["xn2"]), G(f.fc1.weight), None, None, 0, M, d, H, st)
+        else:
+            call("vit3d_linear_fwd", ptr(gb), H, 0, ptr(sh["w2_t"]), ptr(sh["w2_t"]), None, None, ptr(dwide), 0, None, 0, M, d,
+                 H, _BF16, st)
+            call("vit3d_gelu_mask_bwd", ptr(dwide), ptr(r["pre"]), ptr(bits1[i]), scale, ptr(dwide), G(f.fc1.bias), M, d, st)
+            call("vit3d_wgrad", ptr(dwide), ptr(r["xn2"]), G(f.fc1.weight), None, None, 0, M, d, H, st)
+            call("vit3d_linear_fwd", ptr(dwide), d, 0, ptr(sh["w1_t"]), ptr(sh["w1_t"]), None, None, ptr(dxn), 1, None, 0, M, H,
+                 d, _BF16, st)
         # ---- ffn_norm backward + skip gradient; bf16 copy and column sums for the out-projection
         call("vit3d_ln256_bwd", ptr(dxn), ptr(r["x1"]), ptr(r["mean2"]), ptr(r["rstd2"]), ptr(blk.ffn_norm.weight), ptr(g),
              None, 1.0, 0, ptr(g1), ptr(g1b), G(blk.ffn_norm.weight), G(blk.ffn_norm.bias), G(a.out.bias), M, st)

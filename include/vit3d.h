@@ -184,7 +184,8 @@ int vit3d_gelu_dropout_bwd(const void* da, const void* h, void* dh, long long n,
                            vit3d_stream_t stream);
 /* Dropout(p) in training (modeling.py:121,123,174): y = x * keep / (1-p) (+ residual, same type, may be
  * NULL: the x + Mlp(..) add of modeling.py:196) with a counter-based Philox mask keyed by
- * (seed, site, step, element index); the same call on dy (residual NULL) gives dx. */
+ * (seed, site, step, element index); the same call on dy (residual NULL) gives dx.  One Philox4x32-10 block serves
+ * eight consecutive elements (16-bit lanes): P(drop) = round(p * 65536) / 65536. */
 /* step_dev (device, may be NULL) is added to `step` on the device: lets a captured CUDA graph draw new
  * masks at every replay. */
 int vit3d_dropout(const void* x, const void* residual, void* y, long long n, int is_f32, float p,
@@ -277,6 +278,14 @@ int vit3d_ln256_bwd(const float* dy, const float* x, const float* mean, const fl
  * mask read from keep bits, NULL = no dropout); db[d] += column sums of dh (the fc1 bias gradient, optional). */
 int vit3d_gelu_mask_bwd(const void* da, const void* pre, const void* drop_bits, float drop_scale, void* dh, float* db, int M,
                         int d, vit3d_stream_t stream);
+/* The data-gradient chain of Mlp.forward's backward (modeling.py:118-124) in ONE kernel (H = 256, d % 128 == 0):
+ *   da = gy w2 ; dh = da * gelu'(pre) * keep * drop_scale ; dxn = dh w1 ; db1 += column sums of dh
+ * gy [M,H] bf16 (gradient w.r.t. the fc2 output, its Dropout already undone); w2_t_lp = bf16 [d,H] transposed fc2
+ * weight, w1_t_lp = bf16 [H,d] transposed fc1 weight; pre [M,d] bf16 saved pre-activation; dh [M,d] bf16 is written
+ * once (the two weight-gradient GEMMs read it), dxn [M,H] fp32; `da` never reaches memory. */
+int vit3d_mlp_bwd(const void* gy, const void* w2_t_lp, const void* w1_t_lp, const void* pre, const void* drop_bits,
+                  float drop_scale, void* dh, float* dxn, float* db1, int M, int H, int d, vit3d_stream_t stream);
+int vit3d_mlp_bwd_supported(int M, int H, int d);
 /* head backward (modeling.py:281, num_classes 1): dencoded[B*S,H] = dlogits[b] * w on the cls rows, 0 elsewhere;
  * dw[H] += sum_b dlogits[b] * encoded[b*S,:];  db[1] += sum_b dlogits[b]. */
 int vit3d_head_bwd(const float* dlogits, const float* encoded, const float* w, float* dencoded, float* dw, float* db, int B,
