@@ -87,8 +87,8 @@ SIGNATURES = {
     "vit3d_dropout_bits": (_i, [_p, _i, C.POINTER(_u), C.POINTER(_ll), _f, _ull, _u, _p, _p]),
     "vit3d_ln256_fwd": (_i, [_p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _i, _f, _p]),
     "vit3d_ln256_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _f, _i, _p, _p, _p, _p, _p, _i, _p]),
-    "vit3d_gelu_mask_bwd": (_i, [_p, _p, _p, _f, _p, _p, _i, _i, _p]),
-    "vit3d_mlp_bwd": (_i, [_p, _p, _p, _p, _p, _f, _p, _p, _p, _i, _i, _i, _p]),
+    "vit3d_mul_colsum_bwd": (_i, [_p, _p, _p, _p, _i, _i, _p]),
+    "vit3d_mlp_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "vit3d_mlp_bwd_supported": (_i, [_i, _i, _i]),
     "vit3d_head_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "vit3d_refresh_shadows": (_i, [_p, _i, _i, _p, _p]),

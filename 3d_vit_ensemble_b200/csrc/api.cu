@@ -467,12 +467,11 @@ int vit3d_ln256_bwd(const float* dy, const float* x, const float* mean, const fl
   return launch_ln256_bwd(dy, x, mean, rstd, gamma, dres, reinterpret_cast<const uint8_t*>(drop_bits), drop_scale, mask_f32, dx,
                           dx_bf16, dgamma, dbeta, dbias, M, as_stream(stream));
 }
-int vit3d_gelu_mask_bwd(const void* da, const void* pre, const void* drop_bits, float drop_scale, void* dh, float* db, int M,
-                        int d, vit3d_stream_t stream) {
-  V3_REQUIRE(da && pre && dh && M >= 0 && d > 0 && d % 8 == 0, "gelu_mask_bwd: bad argument");
-  V3_REQUIRE(((reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(dh)) & 15) == 0,
-             "gelu_mask_bwd: buffers must be 16-byte aligned");
-  return launch_gelu_mask_bwd(da, pre, reinterpret_cast<const uint8_t*>(drop_bits), drop_scale, dh, db, M, d, as_stream(stream));
+int vit3d_mul_colsum_bwd(const void* da, const void* dact, void* dh, float* db, int M, int d, vit3d_stream_t stream) {
+  V3_REQUIRE(da && dact && dh && M >= 0 && d > 0 && d % 8 == 0, "mul_colsum_bwd: bad argument");
+  V3_REQUIRE(((reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(dact) | reinterpret_cast<uintptr_t>(dh)) & 15) == 0,
+             "mul_colsum_bwd: buffers must be 16-byte aligned");
+  return launch_mul_colsum_bwd(da, dact, dh, db, M, d, as_stream(stream));
 }
 int vit3d_head_bwd(const float* dlogits, const float* encoded, const float* w, float* dencoded, float* dw, float* db, int B,
                    int S, int H, vit3d_stream_t stream) {
@@ -484,15 +483,16 @@ int vit3d_refresh_shadows(const void* jobs, int njobs, int total_tiles, unsigned
   V3_REQUIRE(jobs && njobs > 0 && total_tiles > 0, "refresh_shadows: bad argument");
   return launch_refresh_shadows(jobs, njobs, total_tiles, step_dev, as_stream(stream));
 }
-int vit3d_fc1_train_fwd(const void* xn, const void* w1_lp, const float* b1, void* pre, void* act, const void* drop_bits,
+int vit3d_fc1_train_fwd(const void* xn, const void* w1_lp, const float* b1, void* dact, void* act, const void* drop_bits,
                         float drop_scale, int M, int d, int H, vit3d_stream_t stream) {
-  V3_REQUIRE(xn && w1_lp && b1 && pre && act && M >= 0 && d > 0 && H > 0, "fc1_train_fwd: bad argument");
+  V3_REQUIRE(xn && w1_lp && b1 && dact && act && M >= 0 && d > 0 && H > 0, "fc1_train_fwd: bad argument");
   if (M == 0) return VIT3D_OK;
   if (!tc_linear_supported(VIT3D_PREC_BF16, M, d, H) || d % 32) V3_UNSUPPORTED("fc1_train_fwd: unsupported shape M=%d d=%d H=%d", M, d, H);
   TcLinear t;
-  t.x = xn; t.w = w1_lp; t.bias = b1; t.y = act; t.y_f32 = 0; t.pre = pre; t.act = VIT3D_ACT_GELU; t.M = M; t.N = d; t.K = H;
+  t.x = xn; t.w = w1_lp; t.bias = b1; t.y = act; t.y_f32 = 0; t.pre = dact; t.act = VIT3D_ACT_GELU; t.M = M; t.N = d; t.K = H;
   t.prec = VIT3D_PREC_BF16;
-  t.drop_bits = reinterpret_cast<const uint32_t*>(drop_bits); t.drop_scale = drop_scale;
+  t.drop_bits = reinterpret_cast<const uint32_t*>(drop_bits); t.drop_scale = drop_bits ? drop_scale : 1.f;
+  t.store_dact = 1;
   return tc_linear_fwd(t, as_stream(stream));
 }
 int vit3d_linear_res_train_fwd(const void* x, const void* w_lp, const float* bias, const float* residual, float* y,
@@ -525,14 +525,13 @@ int vit3d_attn_bwd_bias(const void* dctx, const void* qkv, void* dqkv, float* db
   return tc_attn_bwd(dctx, qkv, dqkv, db_q, db_k, db_v, B, S, heads, D, as_stream(stream));
 }
 int vit3d_mlp_bwd_supported(int M, int H, int d) { return tc_mlp_bwd_supported(M, H, d) ? 1 : 0; }
-int vit3d_mlp_bwd(const void* gy, const void* w2_t_lp, const void* w1_t_lp, const void* pre, const void* drop_bits,
-                  float drop_scale, void* dh, float* dxn, float* db1, int M, int H, int d, vit3d_stream_t stream) {
-  V3_REQUIRE(gy && w2_t_lp && w1_t_lp && pre && dh && dxn && M >= 0 && H > 0 && d > 0, "mlp_bwd: bad argument");
-  V3_REQUIRE(((reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(dh) |
-               reinterpret_cast<uintptr_t>(dxn)) & 15) == 0, "mlp_bwd: buffers must be 16-byte aligned");
+int vit3d_mlp_bwd(const void* gy, const void* w2_t_lp, const void* w1_t_lp, const void* dact, void* dh, float* dxn, float* db1,
+                  int M, int H, int d, vit3d_stream_t stream) {
+  V3_REQUIRE(gy && w2_t_lp && w1_t_lp && dact && dh && dxn && M >= 0 && H > 0 && d > 0, "mlp_bwd: bad argument");
+  V3_REQUIRE(((reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(dh) | reinterpret_cast<uintptr_t>(dxn)) & 15) == 0,
+             "mlp_bwd: buffers must be 16-byte aligned");
   if (M == 0) return VIT3D_OK;
-  return tc_mlp_bwd(gy, w2_t_lp, w1_t_lp, pre, reinterpret_cast<const uint32_t*>(drop_bits), drop_scale, dh, dxn, db1, M, H, d,
-                    as_stream(stream));
+  return tc_mlp_bwd(gy, w2_t_lp, w1_t_lp, dact, dh, dxn, db1, M, H, d, as_stream(stream));
 }
 int vit3d_train_supported(int B, int S, int H, int heads, int d) {
   if (B <= 0 || H != 256 || heads <= 0 || H % heads) return 0;

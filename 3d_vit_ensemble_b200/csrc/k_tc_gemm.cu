@@ -280,12 +280,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m_base = ti.tm * TC_BLOCK_M + q * 32, n_base = ti.tn * BN + part * CW;
       if constexpr (EPI >= 0) {
         const uint32_t* drop_row = nullptr;
+        uint32_t mw_default = 0u;
         if constexpr ((EPI & 8) != 0) {
-          if (m_base + lane < M) drop_row = ep.drop_bits + (((long long)(m_base + lane) * N + n_base) >> 5);
+          if (ep.drop_bits == nullptr) mw_default = 0xffffffffu;
+          else if (m_base + lane < M) drop_row = ep.drop_bits + (((long long)(m_base + lane) * N + n_base) >> 5);
         }
         epilogue_bf16_lean<CW, EPI, WIDE>(&tmC, &tmPre, taddr, stage, smem_u32(bias_stage) + part * CW * 4,
                                     smem_u32(bias_stage) + BN * 4 + part * CW * 2, lane, m_base, n_base, drop_row,
-                                    ep.drop_scale);
+                                    ep.drop_scale, mw_default);
       } else {
         epilogue_rows<CW, !TF32>(ep, &tmC, &tmPre, taddr, stage, lane, m_base, n_base, M, N);
       }
@@ -422,8 +424,8 @@ int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const 
   // compile-time specialised epilogue for the hot bf16-output products (full column tiles)
   if (!ep.out_f32 && bn >= 128 && N % bn == 0 && tuning(VIT3D_TUNE_EPI_LEAN) != 0 &&
       (!ep.pre || ep.act == VIT3D_ACT_GELU) && (ep.act == VIT3D_ACT_NONE || ep.bias) &&
-      (!ep.drop_bits || (ep.pre && ep.bias && ep.act == VIT3D_ACT_GELU))) {
-    const int mode = (ep.bias ? 1 : 0) | (ep.act == VIT3D_ACT_GELU ? 2 : 0) | (ep.pre ? 4 : 0) | (ep.drop_bits ? 8 : 0);
+      (!ep.drop_bits || ep.store_dact) && (!ep.store_dact || (ep.pre && ep.bias && ep.act == VIT3D_ACT_GELU))) {
+    const int mode = (ep.bias ? 1 : 0) | (ep.act == VIT3D_ACT_GELU ? 2 : 0) | (ep.pre ? 4 : 0) | (ep.store_dact ? 8 : 0);
     if (bn == 256 && !ep.pre && tuning(VIT3D_TUNE_STORE_WIDE) != 0) {
       // one [32 x 64] panel (128-byte rows) per epilogue warp and tile
       CUtensorMap tw;
@@ -522,6 +524,13 @@ int tc_linear_fwd(const TcLinear& t, cudaStream_t st) {
   if (t.drop_bits) {
     if (t.y_f32 || t.N % 32) { set_error("linear + dropout: generic path needs bf16 output and N %% 32 == 0"); return VIT3D_ERR_UNSUPPORTED; }
     ep.drop_bits = t.drop_bits; ep.drop_scale = t.drop_scale;
+  }
+  if (t.store_dact) {
+    if (!t.pre || !t.bias || t.act != VIT3D_ACT_GELU || t.y_f32 || t.N % 32) {
+      set_error("linear: store_dact needs bias, GELU, a `pre` buffer, bf16 output and N %% 32 == 0");
+      return VIT3D_ERR_UNSUPPORTED;
+    }
+    ep.store_dact = 1;
   }
   return tc_gemm(t.prec == VIT3D_PREC_TF32, t.x, t.w, t.M, t.N, t.K, ep, 1, st);
 }

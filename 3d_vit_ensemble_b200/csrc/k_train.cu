@@ -9,7 +9,8 @@
 //   ln256_bwd         LayerNorm backward + residual-gradient add + bf16 copy (optionally dropout-masked) of the
 //                     result for the dgrad / wgrad GEMMs that follow + its column sums (the bias gradient of the
 //                     Linear below) + gamma / beta gradients
-//   gelu_mask_bwd     dh = da * gelu'(pre) * keep / (1 - p), with the fc1 bias gradient (column sums) folded in
+//   mul_colsum_bwd    dh = da * dact (dact = gelu'(pre) * keep / (1 - p) from the training fc1 epilogue), with the fc1
+//                     bias gradient (column sums) folded in - the unfused form of k_tc_mlp_bwd.cu's middle stage
 //   head_bwd          classification-head backward: d(encoded) rows, head weight / bias gradients
 //   refresh_shadows   every low-precision weight shadow of a model (bf16, transposed bf16, packed q|k|v, TF32
 //                     patch filter) from the fp32 masters in one launch, driven by a device job table
@@ -233,12 +234,13 @@ int launch_ln256_bwd(const float* dy, const float* x, const float* mean, const f
   return VIT3D_OK;
 }
 
-// ============================================================================ GELU' * dropout mask (+ fc1 bias gradient)
-// dh[m, c] = da[m, c] * gelu'(pre[m, c]) * keep[m, c] * sc;  db[c] += sum_m dh[m, c].   bf16 in / out, 8 per thread.
-__global__ void __launch_bounds__(256) gelu_mask_bwd_kernel(const uint4* __restrict__ da, const uint4* __restrict__ pre,
-                                                            const uint8_t* __restrict__ bits, float sc,
-                                                            uint4* __restrict__ dh, float* __restrict__ db, int M, int d,
-                                                            int rows_per_block) {
+// ============================================================================ dh = da * dact (+ fc1 bias gradient)
+// The unfused form of the MLP backward's element-wise stage (k_tc_mlp_bwd.cu does it inside the fused kernel; this
+// serves mlp widths that kernel does not): dh[m, c] = da[m, c] * dact[m, c], db[c] += sum_m dh[m, c].  dact = gelu'(pre) *
+// keep / (1 - p) as written by the training fc1 epilogue.  bf16 in / out, 8 per thread.
+__global__ void __launch_bounds__(256) mul_colsum_bwd_kernel(const uint4* __restrict__ da, const uint4* __restrict__ dact,
+                                                             uint4* __restrict__ dh, float* __restrict__ db, int M, int d,
+                                                             int rows_per_block) {
   __shared__ float red[8][32][9];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + lane) * 8;
@@ -250,18 +252,13 @@ __global__ void __launch_bounds__(256) gelu_mask_bwd_kernel(const uint4* __restr
   if (col < d) {
     for (int m = r0 + warp; m < r1; m += 8) {
       const size_t idx = ((size_t)m * d + col) >> 3;
-      const uint4 a = da[idx], h = pre[idx];
-      const uint32_t mk = bits ? bits[idx] : 0xffu;
+      const uint4 a = da[idx], h = dact[idx];
       const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, hw[4] = {h.x, h.y, h.z, h.w};
       uint32_t ow[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const __nv_bfloat162 av = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
-        const __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(&hw[j]);
-        float g0 = __low2float(av) * gelu_grad_fast(__low2float(hv));
-        float g1 = __high2float(av) * gelu_grad_fast(__high2float(hv));
-        g0 = ((mk >> (2 * j)) & 1u) ? g0 * sc : 0.f;
-        g1 = ((mk >> (2 * j + 1)) & 1u) ? g1 * sc : 0.f;
+        const float g0 = __uint_as_float(aw[j] << 16) * __uint_as_float(hw[j] << 16);
+        const float g1 = __uint_as_float(aw[j] & 0xffff0000u) * __uint_as_float(hw[j] & 0xffff0000u);
         cs[2 * j] += g0;
         cs[2 * j + 1] += g1;
         const __nv_bfloat162 o = __floats2bfloat162_rn(g0, g1);
@@ -285,8 +282,7 @@ __global__ void __launch_bounds__(256) gelu_mask_bwd_kernel(const uint4* __restr
   }
 }
 
-int launch_gelu_mask_bwd(const void* da, const void* pre, const uint8_t* bits, float sc, void* dh, float* db, int M, int d,
-                         cudaStream_t st) {
+int launch_mul_colsum_bwd(const void* da, const void* dact, void* dh, float* db, int M, int d, cudaStream_t st) {
   if (M <= 0 || d <= 0) return VIT3D_OK;
   const int gx = ceil_div(d, 256);
   int gy = (8 * sm_count()) / gx;
@@ -294,8 +290,8 @@ int launch_gelu_mask_bwd(const void* da, const void* pre, const uint8_t* bits, f
   int rpb = ceil_div(M, gy);
   if (rpb < 32) rpb = 32;
   gy = ceil_div(M, rpb);
-  gelu_mask_bwd_kernel<<<dim3(gx, gy), 256, 0, st>>>(reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(pre),
-                                                     bits, sc, reinterpret_cast<uint4*>(dh), db, M, d, rpb);
+  mul_colsum_bwd_kernel<<<dim3(gx, gy), 256, 0, st>>>(reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(dact),
+                                                      reinterpret_cast<uint4*>(dh), db, M, d, rpb);
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }

@@ -72,8 +72,7 @@ int launch_ln256_fwd(const float* x, const uint8_t* bits, float sc, float* xd, c
 int launch_ln256_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                      const float* dres, const uint8_t* bits, float sc, int mask_f32, float* dx, void* dxb, float* dgamma,
                      float* dbeta, float* dbias, int M, cudaStream_t st);
-int launch_gelu_mask_bwd(const void* da, const void* pre, const uint8_t* bits, float sc, void* dh, float* db, int M, int d,
-                         cudaStream_t st);
+int launch_mul_colsum_bwd(const void* da, const void* dact, void* dh, float* db, int M, int d, cudaStream_t st);
 int launch_head_bwd(const float* dlogit, const float* enc, const float* w, float* denc, float* dw, float* db, int B, int S,
                     cudaStream_t st);
 int launch_refresh_shadows(const void* jobs, int njobs, int total_tiles, unsigned* step_dev, cudaStream_t st);

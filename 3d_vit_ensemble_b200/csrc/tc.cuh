@@ -25,6 +25,7 @@ struct TcLinear {
   // activation (bf16 outputs, modeling.py:121) from a keep-bit array over the [M,N] output
   const uint32_t* drop_bits = nullptr;
   float drop_scale = 1.f;
+  int store_dact = 0;            // training fc1: `pre` receives gelu'(pre) * keep * drop_scale (TcEpilogue::store_dact)
 };
 bool tc_linear_ln_supported(int prec, int M, int N, int K);
 // k_tc_gemm_res.cu: fp32 output (+ bias, + residual, + fused LayerNorm) through TMA panels; N % 256 == 0
@@ -52,8 +53,8 @@ int tc_mlp2_fwd(const void* xn, const void* w1, const float* b1, const void* w2_
 
 // k_tc_mlp_bwd.cu: fused data-gradient chain of the MLP backward (dgrad fc2 -> GELU' x dropout mask -> dgrad fc1)
 bool tc_mlp_bwd_supported(int M, int H, int d);
-int tc_mlp_bwd(const void* gy, const void* w2_t, const void* w1_t, const void* pre, const uint32_t* bits, float scale,
-               void* dh, float* dxn, float* db1, int M, int H, int d, cudaStream_t st);
+int tc_mlp_bwd(const void* gy, const void* w2_t, const void* w1_t, const void* dact, void* dh, float* dxn, float* db1, int M,
+               int H, int d, cudaStream_t st);
 
 bool tc_attn_supported(int S, int heads, int D);
 int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int heads, int D, cudaStream_t st);

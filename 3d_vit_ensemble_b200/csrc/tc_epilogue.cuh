@@ -28,6 +28,10 @@ struct TcEpilogue {
   // the [M,N] output, k_train.cu dropout_bits); bf16 outputs, N % 32 == 0
   const uint32_t* drop_bits = nullptr;
   float drop_scale = 1.f;
+  // training fc1: the `pre` output receives d act / d pre = gelu'(pre) * keep * drop_scale - the factor the backward
+  // multiplies the incoming gradient by - instead of the pre-activation itself (the backward then needs neither the
+  // GELU derivative nor the keep bits; computed here it hides under this kernel's store-bound time)
+  int store_dact = 0;
   // atomic (weight-gradient) outputs split by rows over up to three buffers: rows [i*seg_rows, (i+1)*seg_rows)
   // go to out / out_seg[0] / out_seg[1] (the packed q|k|v weight gradient lands in three parameters' .grad)
   float* out_seg[2] = {nullptr, nullptr};
@@ -104,6 +108,26 @@ __device__ __forceinline__ float2 gelu_pair_f2(float a, float b) {
   const __half2 th = *reinterpret_cast<const __half2*>(&ti);
   const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
   return __half22float2(__hfma2(hx, th, hx));
+}
+// fitted GELU and its derivative for a pair, sharing the tanh (packed half):
+//   y = hx (1 + t), y' = 0.5 (1 + t) + hx (1 - t^2) (c0 + 3 c1 x^2 + 5 c2 x^4),  t = tanh(x (c0 + c1 x^2 + c2 x^4)), hx = x / 2
+__device__ __forceinline__ void gelu_and_grad_pair(float a, float b, float2& y, float2& dy) {
+  const __half2 x = __floats2half2_rn(a, b);
+  const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(100.f));
+  __half2 p = __hfma2(x2, __float2half2_rn(-3.58732362e-4f), __float2half2_rn(0.0370503451f));
+  p = __hfma2(x2, p, __float2half2_rn(0.797458471f));
+  const __half2 u = __hmul2(x, p);
+  uint32_t ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
+  const __half2 t = *reinterpret_cast<const __half2*>(&ti);
+  const __half2 half = __float2half2_rn(0.5f);
+  const __half2 hx = __hmul2(x, half);
+  y = __half22float2(__hfma2(hx, t, hx));
+  __half2 q = __hfma2(x2, __float2half2_rn(5.f * -3.58732362e-4f), __float2half2_rn(3.f * 0.0370503451f));
+  q = __hfma2(x2, q, __float2half2_rn(0.797458471f));
+  const __half2 a1 = __hfma2(t, half, half);                              // 0.5 (1 + t)
+  const __half2 s = __hfma2(__hneg2(t), t, __float2half2_rn(1.f));        // 1 - t^2
+  dy = __half22float2(__hfma2(__hmul2(hx, s), q, a1));
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -223,10 +247,45 @@ __device__ __forceinline__ void epilogue_rows(const TcEpilogue& ep, const CUtens
           }
         }
       }
+      float dq[32];
+      if (ep.store_dact) {
+        // training fc1: (gelu, gelu') per element, both multiplied by keep * scale; `pre` receives the derivative
+        const int m = m_base + lane;
+        uint32_t mw = 0xffffffffu;
+        if (ep.drop_bits) mw = m < M ? __ldg(ep.drop_bits + (((long long)m * N + n_base + c) >> 5)) : 0u;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float2 y, g;
+          gelu_and_grad_pair(v[2 * j], v[2 * j + 1], y, g);
+          const float k0 = ((mw >> (2 * j)) & 1u) ? ep.drop_scale : 0.f, k1 = ((mw >> (2 * j + 1)) & 1u) ? ep.drop_scale : 0.f;
+          v[2 * j] = y.x * k0; v[2 * j + 1] = y.y * k1;
+          dq[2 * j] = g.x * k0; dq[2 * j + 1] = g.y * k1;
+        }
+      }
 #pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {
         // pass 0: pre-activation copy (training), pass 1: output
         if (pass == 0 && ep.pre == nullptr) continue;
+        if (ep.store_dact) {
+          if (lane == 0) bulk_store_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (pass == 0)
+              st_shared_v4(my_row + ((j ^ sw) << 4), pack2_bf16(dq[8 * j], dq[8 * j + 1]), pack2_bf16(dq[8 * j + 2], dq[8 * j + 3]),
+                           pack2_bf16(dq[8 * j + 4], dq[8 * j + 5]), pack2_bf16(dq[8 * j + 6], dq[8 * j + 7]));
+            else
+              st_shared_v4(my_row + ((j ^ sw) << 4), pack2_bf16(v[8 * j], v[8 * j + 1]), pack2_bf16(v[8 * j + 2], v[8 * j + 3]),
+                           pack2_bf16(v[8 * j + 4], v[8 * j + 5]), pack2_bf16(v[8 * j + 6], v[8 * j + 7]));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(pass == 0 ? tmPre : tmC, stage, n_base + c, m_base);
+            bulk_store_commit();
+          }
+          continue;
+        }
         const bool gelu = pass == 1 && ep.act == VIT3D_ACT_GELU;
         if (gelu && !FAST_GELU) {
 #pragma unroll
@@ -297,13 +356,15 @@ __device__ __forceinline__ uint32_t gelu_pair_bf16_h2(__half2 x) {
 // WIDE (CW == 64, no pre-activation output): the warp's whole 32 x 64 slice is staged as ONE panel with
 // 128-byte rows (128B swizzle, 4 KB) and leaves by one bulk tensor store per tile instead of two stores of
 // 64-byte rows - half the TMA row transactions, and the wait for the previous store moves a whole tile away.
-//   MODE bit 3: Dropout of the output from keep bits (`drop_row` = word of column n_base of this thread's row,
-//               null for rows >= M); needs bits 0-2 (the training fc1: bias + GELU + pre-activation copy)
+//   MODE bit 3: the training fc1 (needs bits 0-2): output = gelu(v) * keep * scale, and the `pre` output receives
+//               d act / d pre = gelu'(v) * keep * scale (TcEpilogue::store_dact).  Keep bits: `drop_row` = word of
+//               column n_base of this thread's row; where it is null the word is `mw_default` (0 for rows >= M,
+//               all ones when the call has no dropout)
 template <int CW, int MODE, bool WIDE = false>
 __device__ __forceinline__ void epilogue_bf16_lean(const CUtensorMap* tmC, const CUtensorMap* tmPre, uint32_t taddr,
                                                    uint32_t stage, uint32_t bias_f32, uint32_t bias_h2, int lane,
                                                    int m_base, int n_base, const uint32_t* drop_row = nullptr,
-                                                   float drop_scale = 1.f) {
+                                                   float drop_scale = 1.f, uint32_t mw_default = 0u) {
   constexpr bool BIAS = (MODE & 1) != 0, GELU = (MODE & 2) != 0, PRE = (MODE & 4) != 0, DROP = (MODE & 8) != 0;
   static_assert(!WIDE || (CW == 64 && !PRE), "wide staging: 64 columns per warp, no pre-activation copy");
   static_assert(!DROP || (GELU && PRE), "dropout variant = training fc1 (bias + GELU + pre-activation)");
@@ -341,13 +402,29 @@ __device__ __forceinline__ void epilogue_bf16_lean(const CUtensorMap* tmC, const
           v[j + 2] += __uint_as_float(b.z); v[j + 3] += __uint_as_float(b.w);
         }
       }
+      uint32_t dq[16];
+      if constexpr (DROP) {
+        const uint32_t mw = drop_row ? __ldg(drop_row + (c >> 5)) : mw_default;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float2 y, g;
+          gelu_and_grad_pair(v[2 * j], v[2 * j + 1], y, g);
+          const float k0 = ((mw >> (2 * j)) & 1u) ? drop_scale : 0.f, k1 = ((mw >> (2 * j + 1)) & 1u) ? drop_scale : 0.f;
+          w[j] = pack2_bf16(y.x * k0, y.y * k1);
+          dq[j] = pack2_bf16(g.x * k0, g.y * k1);
+        }
+      }
       if constexpr (PRE) {
         if (lane == 0) bulk_store_wait_read();
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          st_shared_v4(my_row + ((j ^ sw) << 4), pack2_bf16(v[8 * j], v[8 * j + 1]), pack2_bf16(v[8 * j + 2], v[8 * j + 3]),
-                       pack2_bf16(v[8 * j + 4], v[8 * j + 5]), pack2_bf16(v[8 * j + 6], v[8 * j + 7]));
+        for (int j = 0; j < 4; ++j) {
+          if constexpr (DROP)
+            st_shared_v4(my_row + ((j ^ sw) << 4), dq[4 * j], dq[4 * j + 1], dq[4 * j + 2], dq[4 * j + 3]);
+          else
+            st_shared_v4(my_row + ((j ^ sw) << 4), pack2_bf16(v[8 * j], v[8 * j + 1]), pack2_bf16(v[8 * j + 2], v[8 * j + 3]),
+                         pack2_bf16(v[8 * j + 4], v[8 * j + 5]), pack2_bf16(v[8 * j + 6], v[8 * j + 7]));
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -355,16 +432,7 @@ __device__ __forceinline__ void epilogue_bf16_lean(const CUtensorMap* tmC, const
           bulk_store_commit();
         }
       }
-      if constexpr (DROP) {
-        const uint32_t mw = drop_row ? __ldg(drop_row + (c >> 5)) : 0u;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float2 f = gelu_pair_f2(v[2 * j], v[2 * j + 1]);
-          f.x = ((mw >> (2 * j)) & 1u) ? f.x * drop_scale : 0.f;
-          f.y = ((mw >> (2 * j + 1)) & 1u) ? f.y * drop_scale : 0.f;
-          w[j] = pack2_bf16(f.x, f.y);
-        }
-      } else {
+      if constexpr (!DROP) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) w[j] = GELU ? gelu_pair_bf16(v[2 * j], v[2 * j + 1]) : pack2_bf16(v[2 * j], v[2 * j + 1]);
       }

@@ -6,8 +6,9 @@ What the per-operator path (functional.py) pays and this one does not:
     LayerNorm backward kernel adds the skip gradient, emits the bf16 operand of the next GEMMs and the bias
     gradient's column sums in the same pass (vit3d_ln256_bwd);
   * separate Dropout / GELU' / column-sum passes over the [M, mlp_dim] tensors -> keep masks are bit arrays made
-    by one launch per step (vit3d_dropout_bits) and applied inside the GEMM epilogues; GELU' x mask x fc1-bias
-    column sums are one pass (vit3d_gelu_mask_bwd);
+    by one launch per step (vit3d_dropout_bits) and applied inside the GEMM epilogues; the fc1 epilogue saves
+    gelu'(pre) x mask instead of pre, and dgrad(fc2) -> x that factor -> dgrad(fc1) + fc1-bias column sums are ONE
+    kernel (vit3d_mlp_bwd): the [M, mlp_dim] gradient is written once, for the weight-gradient GEMMs;
   * bf16 / transposed-bf16 weight shadows re-derived by ~80 cast / transpose launches after every optimizer
     step -> one launch over a device job table (vit3d_refresh_shadows), into persistent buffers;
   * q, k, v as one packed projection without torch.cat: packed shadows, and the packed weight gradient lands in
@@ -265,13 +266,13 @@ def forward(model, x, labels, pos_weight, step: Optional[int] = None):
         call("vit3d_linear_res_train_fwd", ptr(ctx), ptr(sh["wo"]), ptr(a.out.bias), ptr(x0), ptr(x1), None, 1.0,
              ptr(blk.ffn_norm.weight), ptr(blk.ffn_norm.bias), float(blk.ffn_norm.eps), ptr(xn2), ptr(mean2), ptr(rstd2),
              M, H, H, st)
-        pre = torch.empty(M, d, device=dev, dtype=bf)
+        dact = torch.empty(M, d, device=dev, dtype=bf)       # gelu'(pre) * keep / (1-p): all the backward needs of fc1's output
         act = torch.empty(M, d, device=dev, dtype=bf)
-        call("vit3d_fc1_train_fwd", ptr(xn2), ptr(sh["w1"]), ptr(f.fc1.bias), ptr(pre), ptr(act), ptr(bits1[i]), scale,
+        call("vit3d_fc1_train_fwd", ptr(xn2), ptr(sh["w1"]), ptr(f.fc1.bias), ptr(dact), ptr(act), ptr(bits1[i]), scale,
              M, d, H, st)
         x2 = torch.empty(M, H, device=dev, dtype=f32)
         rec = dict(x0=x0, xn1=xn, mean1=mean, rstd1=rstd, qkv=qkv, ctx=ctx, x1=x1, xn2=xn2, mean2=mean2, rstd2=rstd2,
-                   pre=pre, act=act)
+                   dact=dact, act=act)
         if i + 1 < L:
             nl = enc.layer[i + 1].attention_norm
             xn = torch.empty(M, H, device=dev, dtype=bf)
@@ -361,13 +362,13 @@ def backward(model, saved, dloss: Optional[torch.Tensor] = None):
         call("vit3d_wgrad", ptr(gb), ptr(r["act"]), G(f.fc2.weight), None, None, 0, M, H, d, st)
         if fused_mlp:
             # dgrad(fc2) -> GELU' x mask -> dgrad(fc1) in one kernel: `da` stays on chip, dh is written once
-            call("vit3d_mlp_bwd", ptr(gb), ptr(sh["w2_t"]), ptr(sh["w1_t"]), ptr(r["pre"]), ptr(bits1[i]), scale, ptr(dwide),
-                 ptr(dxn), G(f.fc1.bias), M, H, d, st)
+            call("vit3d_mlp_bwd", ptr(gb), ptr(sh["w2_t"]), ptr(sh["w1_t"]), ptr(r["dact"]), ptr(dwide), ptr(dxn),
+                 G(f.fc1.bias), M, H, d, st)
             call("vit3d_wgrad", ptr(dwide), ptr(r["xn2"]), G(f.fc1.weight), None, None, 0, M, d, H, st)
         else:
             call("vit3d_linear_fwd", ptr(gb), H, 0, ptr(sh["w2_t"]), ptr(sh["w2_t"]), None, None, ptr(dwide), 0, None, 0, M, d,
                  H, _BF16, st)
-            call("vit3d_gelu_mask_bwd", ptr(dwide), ptr(r["pre"]), ptr(bits1[i]), scale, ptr(dwide), G(f.fc1.bias), M, d, st)
+            call("vit3d_mul_colsum_bwd", ptr(dwide), ptr(r["dact"]), ptr(dwide), G(f.fc1.bias), M, d, st)
             call("vit3d_wgrad", ptr(dwide), ptr(r["xn2"]), G(f.fc1.weight), None, None, 0, M, d, H, st)
             call("vit3d_linear_fwd", ptr(dwide), d, 0, ptr(sh["w1_t"]), ptr(sh["w1_t"]), None, None, ptr(dxn), 1, None, 0, M, H,
                  d, _BF16, st)

@@ -274,17 +274,17 @@ int vit3d_ln256_fwd(const float* x, const void* drop_bits, float drop_scale, flo
 int vit3d_ln256_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                     const float* dres, const void* drop_bits, float drop_scale, int mask_f32, float* dx, void* dx_bf16,
                     float* dgamma, float* dbeta, float* dbias, int M, vit3d_stream_t stream);
-/* dh = da * gelu'(pre) * keep * drop_scale (bf16 [M,d]; backward of Dropout(gelu(.)), modeling.py:120-121, with the
- * mask read from keep bits, NULL = no dropout); db[d] += column sums of dh (the fc1 bias gradient, optional). */
-int vit3d_gelu_mask_bwd(const void* da, const void* pre, const void* drop_bits, float drop_scale, void* dh, float* db, int M,
-                        int d, vit3d_stream_t stream);
-/* The data-gradient chain of Mlp.forward's backward (modeling.py:118-124) in ONE kernel (H = 256, d % 128 == 0):
- *   da = gy w2 ; dh = da * gelu'(pre) * keep * drop_scale ; dxn = dh w1 ; db1 += column sums of dh
+/* dh = da * dact (bf16 [M,d]): the element-wise stage of the MLP backward (modeling.py:120-121) with dact = gelu'(pre) *
+ * keep * drop_scale as written by vit3d_fc1_train_fwd; db[d] += column sums of dh (the fc1 bias gradient, optional).
+ * dh may alias da. */
+int vit3d_mul_colsum_bwd(const void* da, const void* dact, void* dh, float* db, int M, int d, vit3d_stream_t stream);
+/* The data-gradient chain of Mlp.forward's backward (modeling.py:118-124) in ONE kernel (H = 256, d % 256 == 0):
+ *   da = gy w2 ; dh = da * dact ; dxn = dh w1 ; db1 += column sums of dh
  * gy [M,H] bf16 (gradient w.r.t. the fc2 output, its Dropout already undone); w2_t_lp = bf16 [d,H] transposed fc2
- * weight, w1_t_lp = bf16 [H,d] transposed fc1 weight; pre [M,d] bf16 saved pre-activation; dh [M,d] bf16 is written
- * once (the two weight-gradient GEMMs read it), dxn [M,H] fp32; `da` never reaches memory. */
-int vit3d_mlp_bwd(const void* gy, const void* w2_t_lp, const void* w1_t_lp, const void* pre, const void* drop_bits,
-                  float drop_scale, void* dh, float* dxn, float* db1, int M, int H, int d, vit3d_stream_t stream);
+ * weight, w1_t_lp = bf16 [H,d] transposed fc1 weight; dact [M,d] bf16 from vit3d_fc1_train_fwd; dh [M,d] bf16 is
+ * written once (the two weight-gradient GEMMs read it), dxn [M,H] fp32; `da` never reaches memory. */
+int vit3d_mlp_bwd(const void* gy, const void* w2_t_lp, const void* w1_t_lp, const void* dact, void* dh, float* dxn, float* db1,
+                  int M, int H, int d, vit3d_stream_t stream);
 int vit3d_mlp_bwd_supported(int M, int H, int d);
 /* head backward (modeling.py:281, num_classes 1): dencoded[B*S,H] = dlogits[b] * w on the cls rows, 0 elsewhere;
  * dw[H] += sum_b dlogits[b] * encoded[b*S,:];  db[1] += sum_b dlogits[b]. */
@@ -298,9 +298,11 @@ int vit3d_head_bwd(const float* dlogits, const float* encoded, const float* w, f
  * job's first 32 x 32 tile in the launch, tiles_c = ceil(cols/32); total_tiles = sum over jobs.  step_dev (optional
  * device counter) is incremented by one: the dropout step of a CUDA-graph replay. */
 int vit3d_refresh_shadows(const void* jobs, int njobs, int total_tiles, unsigned* step_dev, vit3d_stream_t stream);
-/* training fc1 (modeling.py:119-121): pre = xn w1^T + b1 (bf16, saved for backward), act = Dropout(gelu(pre)) (bf16),
- * Dropout from keep bits over [M,d] (NULL = none), all in the GEMM epilogue. */
-int vit3d_fc1_train_fwd(const void* xn, const void* w1_lp, const float* b1, void* pre, void* act, const void* drop_bits,
+/* training fc1 (modeling.py:119-121): act = Dropout(gelu(xn w1^T + b1)) (bf16) and, instead of the pre-activation,
+ * dact = gelu'(xn w1^T + b1) * keep * drop_scale (bf16): the factor the backward multiplies the incoming gradient by
+ * (vit3d_mlp_bwd / vit3d_mul_colsum_bwd), so the backward needs neither the GELU derivative nor the keep bits.
+ * Dropout from keep bits over [M,d] (NULL = none: keep = 1, scale = 1), all in the GEMM epilogue. */
+int vit3d_fc1_train_fwd(const void* xn, const void* w1_lp, const float* b1, void* dact, void* act, const void* drop_bits,
                         float drop_scale, int M, int d, int H, vit3d_stream_t stream);
 /* training out-projection / fc2 (modeling.py:97,122-123 + the adds of :191,:196 + the next LayerNorm):
  *   y = residual + Dropout(x w^T + bias) (drop_bits NULL = no dropout),  ln_out = LayerNorm(y) bf16 (optional, with
