@@ -333,18 +333,22 @@ class ShardedEnsemble:
             self._streams = [torch.cuda.Stream(device=dev) for _ in range(len(self.ensemble.transformers))]
         main = torch.cuda.current_stream(dev) if self._cuda else None
         off = 0
+        used = []
         for k, (j, b0, b1) in enumerate(mine):
             member = self._graphed[j] if self._graphed is not None else self.ensemble.transformers[j]
             xs = staged[(b0, b1)] if staged is not None else x[b0:b1]
             if conc:
                 s = self._streams[k % len(self._streams)]
-                s.wait_stream(main)
+                if s not in used:
+                    s.wait_stream(main)          # fork: every side stream starts from the main stream's state
+                    used.append(s)
                 with torch.cuda.stream(s):
                     buf[off:off + (b1 - b0)] = member(xs)[0].reshape(-1).float()
-                main.wait_stream(s)
             else:
                 buf[off:off + (b1 - b0)] = member(xs)[0].reshape(-1).float()
             off += b1 - b0
+        for s in used:                           # join only after ALL members were launched
+            main.wait_stream(s)
         if ws > 1:
             gathered = torch.empty(ws * buf.numel(), device=dev, dtype=torch.float32)
             dist.all_gather_into_tensor(gathered, buf, group=self.group)
