@@ -7,10 +7,12 @@ NVLink 5 / NVSwitch; gloo in the CPU tests).  SURVEY.md §8e.
                                 autograd has produced its last gradient, on a side stream, overlapping the
                                 rest of backward.  `global_pos_weight` makes the per-batch class weight
                                 (train_baseline_cv.py:168-169) that of the GLOBAL batch.
-  * stacking ensemble         - `ShardedEnsemble`: the (member, volume) work list is cut into world_size
-                                contiguous chunks of equal FLOPs (3 members do not divide 2/4/8 GPUs), each
-                                rank runs its chunk, one all-gather of the (B,1) member logits rebuilds the
-                                (B, m) matrix everywhere and the 3->1 meta-classifier runs redundantly.
+  * stacking ensemble         - `ShardedEnsemble`: the (member, batch-slice) work list is cut batch-major - rank r
+                                runs every member on its 1/world_size of the batch (equal cost whatever the
+                                members' FLOPs, 3 members need not divide 2/4/8 GPUs, and a rank ships only its
+                                own slice of a host batch) - the members of a rank run concurrently on side
+                                streams, one all-gather of the member logits rebuilds the (B, m) matrix
+                                everywhere and the 3->1 meta-classifier runs redundantly.
   * CV / bootstrap sweep      - `pack_jobs`: independent jobs, replicas only, no collective.
 """
 from __future__ import annotations
@@ -222,6 +224,18 @@ def partition_work(costs: Sequence[float], batch: int, parts: int) -> List[List[
     return out
 
 
+def partition_batch_major(n_members: int, batch: int, parts: int) -> List[List[Tuple[int, int, int]]]:
+    """The (member, batch-slice) work list cut BATCH-major: part r runs every member on volumes
+    [r*batch/parts, (r+1)*batch/parts).  Every part costs the same whatever the members' FLOPs (3 members do not have
+    to divide 2/4/8 ranks), and a rank needs only its own 1/parts of the input batch - with the member-major cut of
+    `partition_work` a rank that holds one whole member needs the whole batch."""
+    out: List[List[Tuple[int, int, int]]] = []
+    for r in range(parts):
+        b0, b1 = batch * r // parts, batch * (r + 1) // parts
+        out.append([(j, b0, b1) for j in range(n_members)] if b1 > b0 else [])
+    return out
+
+
 class ShardedEnsemble:
     """TransformerEnsemble.forward (modeling.py:353-356) with members x batch-slices spread over the ranks.
 
@@ -236,11 +250,17 @@ class ShardedEnsemble:
     CONCURRENT_MAX_SLICE = 256          # volumes: 256 x 65 rows = 130 row tiles < 148 SMs
 
     def __init__(self, ensemble, costs: Optional[Sequence[float]] = None, group=None, graphs: bool = True,
-                 concurrent: Optional[bool] = None):
+                 concurrent: Optional[bool] = None, partition: str = "batch"):
         """graphs=True replays each member's forward from a CUDA graph (one per member and slice shape): a rank's
-        share of a batch is small, so launch overhead would otherwise dominate.  concurrent: None = automatic."""
+        share of a batch is small, so launch overhead would otherwise dominate.  concurrent: None = automatic.
+        partition: "batch" (default: `partition_batch_major`) or "member" (`partition_work`, FLOP-balanced contiguous
+        chunks of the member-major list)."""
         self.ensemble = ensemble
         self.group = group
+        self.partition = partition
+        self._copy_stream = None
+        self._stage_sets = {}
+        self._stage_turn = 0
         m = len(ensemble.transformers)
         self.costs = list(costs) if costs is not None else [1.0] * m
         self._graphed = None
@@ -265,7 +285,7 @@ class ShardedEnsemble:
         if pl is not None:
             return pl
         m = len(self.ensemble.transformers)
-        parts = partition_work(self.costs, B, ws)
+        parts = self._parts(B, ws)
         maxlen = max(1, max(sum(b1 - b0 for _, b0, b1 in p) for p in parts))
         mine = [(j, b0, b1) for j, b0, b1 in parts[rank] if b1 > b0]
         # merged batch intervals this rank needs (slices of consecutive members overlap or touch)
@@ -288,9 +308,14 @@ class ShardedEnsemble:
         self._plans[key] = pl
         return pl
 
+    def _parts(self, B: int, ws: int):
+        if self.partition == "member":
+            return partition_work(self.costs, B, ws)
+        return partition_batch_major(len(self.ensemble.transformers), B, ws)
+
     def gather_bytes(self, B: int) -> int:
         _, ws = world()
-        parts = partition_work(self.costs, B, ws)
+        parts = self._parts(B, ws)
         return 4 * ws * max(1, max(sum(b1 - b0 for _, b0, b1 in p) for p in parts))
 
     def h2d_bytes(self, B: int, bytes_per_volume: int = 327680) -> int:
@@ -298,33 +323,62 @@ class ShardedEnsemble:
         dev = next(self.ensemble.parameters()).device
         return sum(hi - lo for lo, hi in self._plan(B, dev)["merged"]) * bytes_per_volume
 
-    def _stage(self, x: torch.Tensor, pl, device):
-        """Host batch -> device copies of the merged intervals; returns {(b0, b1) slice -> device view}."""
+    class Staged:
+        """A host batch on its way to the device (see `stage`): pass it to the call instead of the tensor."""
+
+        def __init__(self, B, views, event, key):
+            self.B, self.views, self.event, self.key = B, views, event, key
+            self.shape = (B,)
+
+    def stage(self, x: torch.Tensor) -> "ShardedEnsemble.Staged":
+        """Starts the host-to-device copy of THIS rank's slices of the host batch `x` on a copy stream and returns a
+        handle; `self(handle)` waits for it.  Two staging-buffer sets alternate, so the copy of batch s+1 can overlap
+        the member forwards of batch s (the caller keeps at most one batch in flight ahead of the one it computes)."""
+        dev = next(self.ensemble.parameters()).device
+        B = x.shape[0]
+        pl = self._plan(B, dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        turn = self._stage_turn
+        self._stage_turn ^= 1
+        key = (turn, B, x.dtype, tuple(x.shape[1:]))
+        ent = self._stage_sets.get(key)
+        if ent is None:
+            bufs = [(lo, hi, torch.empty((hi - lo,) + tuple(x.shape[1:]), dtype=x.dtype, device=dev)) for lo, hi in pl["merged"]]
+            ent = dict(bufs=bufs, free=torch.cuda.Event())
+            ent["free"].record(torch.cuda.current_stream(dev))
+            self._stage_sets[key] = ent
+        cs = self._copy_stream
+        cs.wait_event(ent["free"])               # the forwards that read this set two batches ago are done
+        with torch.cuda.stream(cs):
+            for lo, hi, buf in ent["bufs"]:
+                buf.copy_(x[lo:hi], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
         views = {}
-        bufs = []
-        for lo, hi in pl["merged"]:
-            key = ("stage", lo, hi, x.dtype, tuple(x.shape[1:]))
-            buf = self._plans.get(key)
-            if buf is None:
-                buf = torch.empty((hi - lo,) + tuple(x.shape[1:]), dtype=x.dtype, device=device)
-                self._plans[key] = buf
-            buf.copy_(x[lo:hi], non_blocking=True)
-            bufs.append((lo, hi, buf))
         for _, b0, b1 in pl["mine"]:
-            for lo, hi, buf in bufs:
+            for lo, hi, buf in ent["bufs"]:
                 if lo <= b0 and b1 <= hi:
                     views[(b0, b1)] = buf[b0 - lo:b1 - lo]
                     break
-        return views
+        return ShardedEnsemble.Staged(B, views, ev, key)
 
     @torch.no_grad()
     def member_logits(self, x: torch.Tensor) -> torch.Tensor:
         rank, ws = world()
-        B = x.shape[0]
         dev = next(self.ensemble.parameters()).device if hasattr(self.ensemble, "parameters") else x.device
+        handle = None
+        if isinstance(x, ShardedEnsemble.Staged):
+            handle = x
+        elif x.device != dev and dev.type == "cuda":
+            handle = self.stage(x)               # host batch: ship this rank's slices now
+        B = handle.B if handle is not None else x.shape[0]
         pl = self._plan(B, dev)
         mine = pl["mine"]
-        staged = self._stage(x, pl, dev) if (x.device != dev and dev.type == "cuda") else None
+        staged = None
+        if handle is not None:
+            torch.cuda.current_stream(dev).wait_event(handle.event)
+            staged = handle.views
         buf = torch.zeros(pl["maxlen"], device=dev, dtype=torch.float32)
         conc = self.concurrent
         if conc is None:
@@ -349,6 +403,8 @@ class ShardedEnsemble:
             off += b1 - b0
         for s in used:                           # join only after ALL members were launched
             main.wait_stream(s)
+        if handle is not None:
+            self._stage_sets[handle.key]["free"].record(main)      # this staging set may be overwritten again
         if ws > 1:
             gathered = torch.empty(ws * buf.numel(), device=dev, dtype=torch.float32)
             dist.all_gather_into_tensor(gathered, buf, group=self.group)
@@ -361,6 +417,10 @@ class ShardedEnsemble:
         from . import functional as F
         feats = self.member_logits(x)
         return F.MetaFn.apply(feats, self.ensemble.classifier.weight, self.ensemble.classifier.bias)
+
+    @property
+    def copy_stream(self):
+        return self._copy_stream
 
 
 # ----------------------------------------------------------------------------- sweep packing

@@ -89,15 +89,21 @@ def build_baseline(conf: int, *, as_shipped: bool = False, img_size: int = 128, 
     return VisionTransformer(cfg, img_size, zero_head=True, num_classes=1, vis=vis, precision=precision)
 
 
-def ensemble_from_checkpoints(paths: Sequence[str], confs: Sequence[int], *, as_shipped: bool = False,
-                              device="cuda", precision: Optional[str] = None) -> TransformerEnsemble:
+def ensemble_from_checkpoints(paths: Sequence[str], confs: Optional[Sequence[int]] = None, *, configs=None,
+                              as_shipped: bool = False, device="cuda", precision: Optional[str] = None,
+                              img_size: int = 128) -> TransformerEnsemble:
     """TransformerEnsemble of baseline members restored from their `torch.save(model.state_dict())` files
-    (reference or this package: same keys and shapes).  Members output one logit each, so in_features=1."""
-    if len(paths) != len(confs):
-        raise ValueError("one checkpoint path per configuration id")
+    (reference or this package: same keys and shapes).  Members output one logit each, so in_features=1.
+    `confs`: configuration ids (README table, or as shipped); `configs`: explicit config objects instead."""
+    specs = list(configs) if configs is not None else list(confs or [])
+    if len(paths) != len(specs):
+        raise ValueError("one checkpoint path per configuration")
     members = []
-    for path, conf in zip(paths, confs):
-        m = build_baseline(conf, as_shipped=as_shipped, precision=precision)
+    for path, spec in zip(paths, specs):
+        if configs is not None:
+            m = VisionTransformer(spec, img_size, zero_head=True, num_classes=1, precision=precision)
+        else:
+            m = build_baseline(spec, as_shipped=as_shipped, precision=precision)
         sd = torch.load(path, map_location="cpu")
         missing, unexpected = m.load_state_dict(sd, strict=True)
         members.append(m)                          # the MODULE (the reference appends load_state_dict's return value)

@@ -196,7 +196,7 @@ def workload_config(wl, B, world, vis):
     if wl["train"]:
         par = f"dp{world}: batch sharded over the ranks, gradients all-reduced (mean) before the SGD step"
     elif len(wl["confs"]) > 1:
-        par = f"{world} ranks: (member, batch-slice) work list balanced by FLOPs, all-gather of member logits, meta-head on every rank"
+        par = f"{world} ranks: (member, batch-slice) work list cut batch-major, members concurrent on a rank, all-gather of member logits, meta-head on every rank"
     else:
         par = f"dp{world} (independent volumes, no data-path collective)"
     return {"workload": wl["name"], "batch_per_gpu": B, "global_batch": units, "vis": bool(vis),
@@ -359,7 +359,7 @@ def run_leg(ctx, args, key, steps, warmup, precision, with_u8=True):
     units = B if ens else world * B
     if sharded is not None:
         # a rank ships only the batch slices of its own (member, slice) chunk
-        ms_e2e = timed_e2e(lambda n: [sharded_e2e_step(sharded, x_host, res_host) for _ in range(n)])
+        ms_e2e = timed_e2e(lambda n: sharded_e2e_run(sharded, x_host, res_host, n))
         h2d = sharded.h2d_bytes(B)
     else:
         ms_e2e = timed_e2e(e2e_loop(x_host, [torch.empty_like(x_dev) for _ in range(2)]))
@@ -374,7 +374,7 @@ def run_leg(ctx, args, key, steps, warmup, precision, with_u8=True):
         for m in members:
             m.input_mean = mean
         if sharded is not None:
-            ms_u8 = timed_e2e(lambda n: [sharded_e2e_step(sharded, u8_host, res_host) for _ in range(n)])
+            ms_u8 = timed_e2e(lambda n: sharded_e2e_run(sharded, u8_host, res_host, n))
             h2d8 = sharded.h2d_bytes(B) // 4
         else:
             ms_u8 = timed_e2e(e2e_loop(u8_host, [torch.empty(u8_host.shape, dtype=torch.uint8, device=dev) for _ in range(2)]))
@@ -434,11 +434,18 @@ def ensemble_small_batch_probe(ctx, args):
     return out
 
 
-def sharded_e2e_step(sharded, x_host, res_host):
+def sharded_e2e_run(sharded, x_host, res_host, nsteps):
+    """End-to-end loop of the sharded ensemble: `stage` ships THIS rank's slice of the host batch on a copy stream, the
+    copy of step s+1 overlaps the member forwards of step s, the result is read back before a step counts as done."""
     import torch
-    out = sharded(x_host)                       # host tensor: the call ships this rank's batch slices itself
-    res_host.copy_(out.reshape(res_host.shape), non_blocking=True)
-    torch.cuda.current_stream().synchronize()
+    nxt = sharded.stage(x_host)
+    for s in range(nsteps):
+        cur = nxt
+        out = sharded(cur)
+        if s + 1 < nsteps:
+            nxt = sharded.stage(x_host)
+        res_host.copy_(out.reshape(res_host.shape), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
 
 
 def main():

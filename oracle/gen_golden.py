@@ -232,16 +232,48 @@ def run_real_volumes(M, out):
     print("real volumes:", u8.shape, "logits", logits.flatten().tolist())
 
 
+CKPT_CASES = [(16, 64, 2, 32, 4), (16, 96, 1, 32, 2), (16, 64, 3, 32, 8)]      # three small baselines (hidden 32)
+
+
+def run_checkpoints(M, out):
+    """N4: `.bin` files written by the UNMODIFIED reference classes the way train_baseline_cv.py:128-134 writes them
+    (`torch.save(model.state_dict(), path)`), plus what the reference's own TransformerEnsemble makes of them.
+    The GPU test loads these files through workflow.ensemble_from_checkpoints and must reproduce the outputs."""
+    members, paths = [], []
+    for j, args in enumerate(CKPT_CASES):
+        m = build_ref(M, O.get_config(*args), seed=100 + j)
+        path = os.path.join(out, f"ref_ckpt_member{j}.bin")
+        model_to_save = m.module if hasattr(m, "module") else m          # train_baseline_cv.py:129
+        torch.save(model_to_save.state_dict(), path)
+        members.append(m)
+        paths.append(path)
+    torch.manual_seed(11)
+    ens = M.TransformerEnsemble(*members, in_features=1)
+    ens.eval()
+    x = O.synth_volumes(3, seed=5, kind="img")
+    with torch.no_grad():
+        outp = ens(x)
+        member_logits = torch.cat([t(x)[0] for t in ens.transformers], dim=1)
+    np.savez_compressed(os.path.join(out, "ref_ckpt_ensemble.npz"), out=outp.numpy(), member_logits=member_logits.numpy(),
+                        classifier_weight=ens.classifier.weight.detach().numpy(),
+                        classifier_bias=ens.classifier.bias.detach().numpy(), cfg_args=np.array(CKPT_CASES))
+    print("reference checkpoints:", [os.path.getsize(p) for p in paths], "bytes; ensemble out", outp.flatten().tolist())
+
+
 def main():
     out = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out, exist_ok=True)
     torch.set_num_threads(8)
     M = ref_modules()
+    if "--checkpoints" in sys.argv:          # only the checkpoint fixtures (the others are unchanged)
+        run_checkpoints(M, out)
+        return
     run_init_parity(M, out)
     for name, (args, B) in CASES.items():
         run_case(M, name, args, B, out)
     run_ensemble(M, out)
     run_real_volumes(M, out)
+    run_checkpoints(M, out)
 
 
 if __name__ == "__main__":

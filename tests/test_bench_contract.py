@@ -48,6 +48,6 @@ def test_reference_arm_is_like_for_like_with_the_gpu_arm():
 def test_timed_regions_do_not_call_the_oracle():
     """bench.py may use oracle/ for synthetic inputs, seeded weights and the CPU arm only - never inside a step."""
     src = open(os.path.join(ROOT, "bench.py")).read()
-    body = src[src.index("def run_leg"):src.index("def sharded_e2e_step")]
+    body = src[src.index("def run_leg"):src.index("def ensemble_small_batch_probe")]
     step_fns = body[body.index("def pos_weight"):body.index("ms_dev, launches")]
     assert "O." not in step_fns and "oracle" not in step_fns

@@ -106,10 +106,10 @@ def _sharded_ensemble(rank, world):
         transformers = [Member(1.0), Member(-2.0), Member(0.5)]
 
     x = torch.arange(7 * 4, dtype=torch.float32).reshape(7, 4)
-    se = D.ShardedEnsemble(Ens(), costs=[1.09, 1.44, 1.01])
-    got = se.member_logits(x)
     want = torch.cat([m(x)[0] for m in Ens.transformers], dim=1)
-    torch.testing.assert_close(got, want)
+    for mode in ("batch", "member"):
+        se = D.ShardedEnsemble(Ens(), costs=[1.09, 1.44, 1.01], partition=mode)
+        torch.testing.assert_close(se.member_logits(x), want)
 
 
 def test_sharded_ensemble_allgather():
@@ -135,6 +135,23 @@ def test_partition_covers_every_pair_once_and_balances(parts, batch):
     assert len(seen) == 3 * batch
     if batch >= 64:
         assert max(loads) <= 1.05 * sum(loads) / parts + max(costs)
+
+
+@pytest.mark.parametrize("parts", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("batch", [1, 3, 64, 512])
+def test_batch_major_partition_covers_every_pair_once_and_ships_one_slice_per_rank(parts, batch):
+    p = D.partition_batch_major(3, batch, parts)
+    seen = set()
+    for chunk in p:
+        slices = {(b0, b1) for _, b0, b1 in chunk}
+        assert len(slices) <= 1                          # a rank needs ONE contiguous slice of the input batch
+        for j, b0, b1 in chunk:
+            for b in range(b0, b1):
+                assert (j, b) not in seen
+                seen.add((j, b))
+    assert len(seen) == 3 * batch
+    sizes = [sum(b1 - b0 for _, b0, b1 in c) for c in p]
+    assert max(sizes) - min(sizes) <= 3
 
 
 def test_pack_jobs():

@@ -70,3 +70,45 @@ def test_validate_matches_per_sample_loop():
     acc = float((out["predicted"] == y.long()).float().mean())
     assert abs(float(out["accuracy"]) - acc) < 1e-6
     assert 0.0 <= float(out["balanced_accuracy"]) <= 1.0
+
+
+def _ref_checkpoint_fixture():
+    import numpy as np
+    from tests.helpers import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "ref_ckpt_ensemble.npz"))
+    paths = [os.path.join(GOLDEN, f"ref_ckpt_member{j}.bin") for j in range(3)]
+    cfgs = [vit3d_b200.get_config(*[int(v) for v in a]) for a in g["cfg_args"]]
+    return g, paths, cfgs
+
+
+def test_reference_written_checkpoints_load_with_identical_keys():
+    """tests/golden/ref_ckpt_member*.bin were written by the UNMODIFIED reference (oracle/gen_golden.py --checkpoints:
+    `torch.save(model.state_dict(), path)`, train_baseline_cv.py:128-134): strict load, same keys / shapes / values."""
+    g, paths, cfgs = _ref_checkpoint_fixture()
+    ens = W.ensemble_from_checkpoints(paths, configs=cfgs, device="cpu", precision="fp32")
+    for path, m in zip(paths, ens.transformers):
+        sd = torch.load(path, map_location="cpu")
+        mine = m.state_dict()
+        assert list(sd.keys()) == list(mine.keys())
+        for k in sd:
+            assert sd[k].shape == mine[k].shape and torch.equal(sd[k], mine[k]), k
+
+
+@pytest.mark.gpu
+def test_reference_written_checkpoints_reproduce_reference_ensemble_outputs():
+    """N4 end to end on the GPU: reference `.bin` files -> ensemble_from_checkpoints -> member logits and ensemble
+    probabilities equal what the reference's own TransformerEnsemble computed from the same weights."""
+    import numpy as np
+    g, paths, cfgs = _ref_checkpoint_fixture()
+    ens = W.ensemble_from_checkpoints(paths, configs=cfgs, device="cuda:0", precision="fp32")
+    with torch.no_grad():
+        ens.classifier.weight.copy_(torch.from_numpy(g["classifier_weight"]))
+        ens.classifier.bias.copy_(torch.from_numpy(g["classifier_bias"]))
+    ens.eval()
+    x = O.synth_volumes(3, seed=5, kind="img").to("cuda:0")
+    with torch.no_grad():
+        members = torch.cat([t(x)[0] for t in ens.transformers], dim=1).cpu().numpy()
+        out = ens(x).cpu().numpy()
+    np.testing.assert_allclose(members, g["member_logits"], atol=1e-3)       # north_star: logits <= 1e-3 in fp32 mode
+    np.testing.assert_allclose(out, g["out"], atol=1e-4)
+    assert ((out > 0.5) == (g["out"] > 0.5)).all()
