@@ -246,220 +246,230 @@ tc_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     }
     __syncwarp();
   } else {
-    // ===================================================== GELU / final epilogue warps (own 128 rows)
-    const int q = warp & 3;                     // TMEM lane quarter
-    const int part = (warp - 2) >> 2;           // 64-column slice of a chunk = k-block `part` of the GELU tile
-    const int row = q * 32 + lane;
-    const uint32_t a_row = smem_u32(s_a) + part * 16384 + row * 128;
-    const int sw7 = row & 7;
-    uint8_t* b1_slot = s_b1 + (warp - 2) * 128;
-    const uint32_t b1_s = smem_u32(b1_slot);
-    // final-epilogue panel buffer = this warp's own 4 KB slice of the GELU tile (rows q*32.., k-block part)
-    uint8_t* buf_ptr = s_a + part * 16384 + q * 4096;
-    const uint32_t buf_s = smem_u32(buf_ptr);
-    const uint32_t my_row = buf_s + lane * 128;
-    uint64_t* rbar = &res_bar[warp - 2];
-    // second panel buffer: a 4 KB slice of the xn tile, idle from the last fc1 of a tile until the next tile's
-    // xn is loaded - its residual panel is fetched two MMA groups before the final epilogue needs it
-    uint8_t* bufx_ptr = s_x + (part * 4 + q) * 4096;
-    const uint32_t bufx_s = smem_u32(bufx_ptr);
-    const uint32_t my_rowx = bufx_s + lane * 128;
-    uint64_t* rbar1 = &res_bar1[warp - 2];
-    uint32_t rphase = 0;
-    uint32_t g = 0;                             // chunk counter
-    int it = 0;
-    for (int t = gid; t < tiles; t += ngroups, ++it) {
-      const int m_base = (t * NCTA + (int)rank) * 128 + q * 32;
-      for (int c = 0; c < nch; ++c, ++g) {
-        // this warp's 64 fc1 biases as packed halves (the global load overlaps the wait for the accumulator)
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < 16) bv = __ldg(reinterpret_cast<const float4*>(args.b1 + c * M2_NC + part * 64) + lane);
-        mbar_wait(acc1_full, g & 1);
-        tc_fence_after();
-        if (c == nch - 1 && lane == 0) {
-          // every fc1 of this tile has completed: the xn region is free -> prefetch residual panel 1 into it
-          mbar_arrive_expect_tx(rbar1, 4096);
-          tma_load_2d(bufx_ptr, &tmRes, rbar1, part * 64 + 32, m_base);
-        }
-        uint32_t r0[32], r1[32];
-        const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + part * 64;
-        tmem_ld_32x32b_x32(tcol, r0);
-        tmem_ld_32x32b_x32(tcol + 32, r1);
-        if (lane < 16) {
-          const __half2 h0 = __floats2half2_rn(bv.x, bv.y), h1 = __floats2half2_rn(bv.z, bv.w);
-          *reinterpret_cast<uint2*>(b1_slot + lane * 8) =
-              make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-        }
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc1_empty);       // fc1 of the next chunk may overwrite acc1
-        uint32_t pk[32];
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const uint4 ba = ld_shared_v4(b1_s + j * 4);            // halves 2j .. 2j+7
-          const uint4 bb = ld_shared_v4(b1_s + 64 + j * 4);
-          const uint32_t a4[4] = {ba.x, ba.y, ba.z, ba.w}, b4[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            __half2 x = __floats2half2_rn(__uint_as_float(r0[2 * (j + i)]), __uint_as_float(r0[2 * (j + i) + 1]));
-            pk[j + i] = gelu_h2(__hadd2(x, *reinterpret_cast<const __half2*>(&a4[i])));
-            __half2 z = __floats2half2_rn(__uint_as_float(r1[2 * (j + i)]), __uint_as_float(r1[2 * (j + i) + 1]));
-            pk[16 + j + i] = gelu_h2(__hadd2(z, *reinterpret_cast<const __half2*>(&b4[i])));
-          }
-        }
-        mbar_wait(a2_empty, (g & 1) ^ 1);   // fc2 of the previous chunk has read the GELU tile
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          st_shared_v4(a_row + ((j ^ sw7) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a2_full);
-      }
-      // ---------------- final epilogue of the tile: y = acc2 + b2 + residual (+ LayerNorm)
-      mbar_wait(acc2_full, it & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        mbar_arrive_expect_tx(rbar, 4096);
-        tma_load_2d(buf_ptr, &tmRes, rbar, part * 64, m_base);
-      }
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + part * 64;
-      const int sl7 = lane & 7;
-      float s1 = 0.f, s2 = 0.f;
-      // panel 1 first (its residual has been in the xn-region buffer for a while), then panel 0 (fetched above)
-#pragma unroll
-      for (int pi = 0; pi < 2; ++pi) {
-        const int p = 1 - pi;
-        const uint32_t prow = p ? my_rowx : my_row;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + p * 32, r);
-        mbar_wait(p ? rbar1 : rbar, rphase);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t a = prow + ((j ^ sl7) << 4);
-          const float4 b = __ldg(reinterpret_cast<const float4*>(args.b2 + part * 64 + p * 32) + j);
-          const uint4 x = ld_shared_v4(a);
-          const float v0 = __uint_as_float(r[4 * j]) + b.x + __uint_as_float(x.x);
-          const float v1 = __uint_as_float(r[4 * j + 1]) + b.y + __uint_as_float(x.y);
-          const float v2 = __uint_as_float(r[4 * j + 2]) + b.z + __uint_as_float(x.z);
-          const float v3 = __uint_as_float(r[4 * j + 3]) + b.w + __uint_as_float(x.w);
-          if constexpr (LN != 2)
-            st_shared_v4(a, __float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
-          if constexpr (LN != 0) {
-            s1 += (v0 + v1) + (v2 + v3);
-            s2 = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, s2))));
-            r[4 * j] = __float_as_uint(v0); r[4 * j + 1] = __float_as_uint(v1);
-            r[4 * j + 2] = __float_as_uint(v2); r[4 * j + 3] = __float_as_uint(v3);
-          }
-        }
-        if constexpr (LN != 0) tmem_st_32x32b_x32(taddr + p * 32, r);
-        if constexpr (LN != 2) fence_proxy_async_smem();
-        __syncwarp();
-        if constexpr (LN != 2) {
-          if (lane == 0) {
-            tma_store_2d(&tmY, p ? bufx_s : buf_s, part * 64 + p * 32, m_base);
-            bulk_store_commit();
-          }
-        }
-      }
-      rphase ^= 1;
-      if (lane == 0) {
-        if constexpr (LN != 2) bulk_store_wait_read();   // both result panels have been read out of shared memory
-        mbar_arrive(xpanel_free);                     // the producer may load the next tile's xn
-      }
-      __syncwarp();
-      if constexpr (LN != 0) {
-        tmem_st_wait();
-        *reinterpret_cast<float2*>(buf_ptr + lane * 8) = make_float2(s1, s2);
-        asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(128) : "memory");
-        float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-        for (int pp = 0; pp < 4; ++pp) {
-          const float2 s = *reinterpret_cast<const float2*>(s_a + pp * 16384 + q * 4096 + lane * 8);
-          t1 += s.x; t2 += s.y;
-        }
-        asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(128) : "memory");
-        const float mean = t1 * (1.0f / M2_H);
-        const float rstd = rsqrtf(fmaxf(t2 * (1.0f / M2_H) - mean * mean, 0.f) + args.eps);
-        const float shift = -mean * rstd;
-        if constexpr (LN == 2) {
-          // fp32 rows, one [32 x 32] panel at a time through the warp's 4 KB buffer (SWIZZLE_128B, as the y panels)
-#pragma unroll
-          for (int p = 0; p < 2; ++p) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(taddr + p * 32, r);
-            tmem_ld_wait();
-            if (p == 1) {
-              if (lane == 0) bulk_store_wait_read();
-              __syncwarp();
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 ga = __ldg(reinterpret_cast<const float4*>(args.gamma + part * 64 + p * 32) + j);
-              const float4 be = __ldg(reinterpret_cast<const float4*>(args.beta + part * 64 + p * 32) + j);
-              const float y0 = fmaf(fmaf(__uint_as_float(r[4 * j]), rstd, shift), ga.x, be.x);
-              const float y1 = fmaf(fmaf(__uint_as_float(r[4 * j + 1]), rstd, shift), ga.y, be.y);
-              const float y2 = fmaf(fmaf(__uint_as_float(r[4 * j + 2]), rstd, shift), ga.z, be.z);
-              const float y3 = fmaf(fmaf(__uint_as_float(r[4 * j + 3]), rstd, shift), ga.w, be.w);
-              st_shared_v4(my_row + ((j ^ sl7) << 4), __float_as_uint(y0), __float_as_uint(y1), __float_as_uint(y2),
-                           __float_as_uint(y3));
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&tmY, buf_s, part * 64 + p * 32, m_base);
-              bulk_store_commit();
-            }
-          }
-          if (lane == 0) bulk_store_wait_read();
-          __syncwarp();
-        } else {
-        const int sw3 = (lane >> 1) & 3;
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr + p * 32, r);
-          tmem_ld_wait();
-          const uint32_t prow = buf_s + p * 2048 + lane * 64;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t wv[4];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const float4 ga = __ldg(reinterpret_cast<const float4*>(args.gamma + part * 64 + p * 32) + 2 * j + h);
-              const float4 be = __ldg(reinterpret_cast<const float4*>(args.beta + part * 64 + p * 32) + 2 * j + h);
-              const float y0 = fmaf(fmaf(__uint_as_float(r[8 * j + 4 * h]), rstd, shift), ga.x, be.x);
-              const float y1 = fmaf(fmaf(__uint_as_float(r[8 * j + 4 * h + 1]), rstd, shift), ga.y, be.y);
-              const float y2 = fmaf(fmaf(__uint_as_float(r[8 * j + 4 * h + 2]), rstd, shift), ga.z, be.z);
-              const float y3 = fmaf(fmaf(__uint_as_float(r[8 * j + 4 * h + 3]), rstd, shift), ga.w, be.w);
-              wv[2 * h] = pack2_bf16(y0, y1);
-              wv[2 * h + 1] = pack2_bf16(y2, y3);
-            }
-            st_shared_v4(prow + ((j ^ sw3) << 4), wv[0], wv[1], wv[2], wv[3]);
-          }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tmLn, buf_s, part * 64, m_base);
-          tma_store_2d(&tmLn, buf_s + 2048, part * 64 + 32, m_base);
-          bulk_store_commit();
-          bulk_store_wait_read();
-        }
-        __syncwarp();
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc2_empty);         // fc2 of the next tile may overwrite acc2
-    }
-    if (lane == 0) bulk_store_wait_all();
+#include "tc_mlp2_epilogue.inc"
   }
   tc_fence_before();
   __syncthreads();
   if constexpr (MC) cluster_sync_all();         // nobody leaves while the partner may still multicast into this CTA
   if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ============================================================================ CTA-pair version (cta_group::2)
+// The same block on pairs of CTAs (one TPC): ONE tcgen05.mma of M = 256 covers the 128 rows of each CTA; every weight
+// k-block is split between the two CTAs (each loads and holds 128 of its 256 rows, 16 KB instead of 32 KB), so a CTA's
+// 96 KB ring holds SIX k-blocks - 3072 cycles of MMA work in flight instead of 1536.  That is what the one-CTA kernel
+// lacks: its MMA thread spends most of its waits on w_full (ncu source view, profiles/r02_*), a ring slot comes back
+// ~2500 cycles after its last MMA was issued, and halving the bytes per slot alone (timing experiment) changed nothing.
+// Only the leader CTA (rank 0) issues MMAs and commits (multicast to both CTAs' barriers); both CTAs run their own TMA
+// producer - whose loads signal the LEADER's full barriers - and their own 16 epilogue warps on their own rows.  The
+// three signals that flow from the epilogue warps to the MMA thread (acc1 drained, GELU tile written, acc2 drained)
+// stay CTA-local 16-arrival barriers; in the peer CTA the otherwise idle MMA-warp thread forwards each completion with
+// ONE remote arrive (an earlier cta_group::2 attempt let all 32 epilogue warps arrive remotely - one cluster-scope
+// release per warp and chunk - and lost more than it gained).
+template <int LN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(M2_THREADS, 1)
+tc_mlp2x_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmY,
+                const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmLn, Mlp2Args args) {
+  constexpr int NCTA = 2;
+  constexpr int W_SLOT = 128 * 128;                 // 16 KB: this CTA's 128 rows of one weight k-block
+  constexpr int NST = M2_RING_BYTES / W_SLOT;       // 6
+  constexpr uint32_t EPI_ARRIVALS = 16;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (smem_u32(smem) & 1023u) __trap();
+  uint8_t* s_x = smem;
+  uint8_t* s_a = smem + M2_X_BYTES;
+  uint8_t* s_w = s_a + M2_A_BYTES;
+  uint8_t* s_b1 = s_w + M2_RING_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_b1 + 16 * 128);
+  uint64_t* x_full = bars;             // LEADER: both CTAs' xn tiles landed
+  uint64_t* x_empty = bars + 1;        // (multicast commit) the last fc1 of the tile has read xn
+  uint64_t* w_full = bars + 2;         // [NST] LEADER: both halves of the weight k-block landed
+  uint64_t* w_empty = bars + 8;        // [NST] (multicast commit) slot may be refilled
+  uint64_t* acc1_full = bars + 14;     // (multicast commit)
+  uint64_t* acc1_empty = bars + 15;    // EPI_ARRIVALS, local
+  uint64_t* a2_full = bars + 16;       // EPI_ARRIVALS, local
+  uint64_t* a2_empty = bars + 17;      // (multicast commit)
+  uint64_t* acc2_full = bars + 18;     // (multicast commit)
+  uint64_t* acc2_empty = bars + 19;    // EPI_ARRIVALS, local
+  uint64_t* res_bar = bars + 20;       // [16]
+  uint64_t* res_bar1 = bars + 36;      // [16]
+  uint64_t* xpanel_free = bars + 52;   // 16, local
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 53);
+  uint64_t* p_acc1_empty = bars + 54;  // LEADER: 1 remote arrival per chunk (the peer's acc1_empty completed)
+  uint64_t* p_a2_full = bars + 55;     // LEADER: 1 remote arrival per chunk
+  uint64_t* p_acc2_empty = bars + 56;  // LEADER: 1 remote arrival per tile
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int M = args.M, d = args.d;
+  const int nch = d / M2_NC;
+  const int tiles = (M + 255) / 256;               // pairs of 128-row tiles
+  const int ngroups = gridDim.x / NCTA;
+  const int gid = blockIdx.x / NCTA;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmW1);
+    prefetch_tmap(&tmW2);
+    mbar_init(x_full, 1);
+    mbar_init(x_empty, 1);
+    for (int s = 0; s < NST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    mbar_init(acc1_full, 1);
+    mbar_init(acc1_empty, EPI_ARRIVALS);
+    mbar_init(a2_full, EPI_ARRIVALS);
+    mbar_init(a2_empty, 1);
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_empty, EPI_ARRIVALS);
+    for (int w = 0; w < 16; ++w) { mbar_init(&res_bar[w], 1); mbar_init(&res_bar1[w], 1); }
+    mbar_init(xpanel_free, 16);
+    mbar_init(p_acc1_empty, 1);
+    mbar_init(p_a2_full, 1);
+    mbar_init(p_acc2_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2<512>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                   // both CTAs' barriers and TMEM exist before any cross-CTA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_trigger();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (both CTAs; completion counted on the leader)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t wphase = 0;
+      int it = 0;
+      const uint32_t lead_x_full = map_to_rank(x_full, 0);
+      for (int t = gid; t < tiles; t += ngroups, ++it) {
+        mbar_wait(x_empty, (it & 1) ^ 1);
+        mbar_wait(xpanel_free, (it & 1) ^ 1);
+        if (rank == 0) mbar_arrive_expect_tx(x_full, 2 * M2_X_BYTES);
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(s_x + kb * 16384, &tmX, lead_x_full, kb * 64, (t * NCTA + (int)rank) * 128);
+        for (int s = 0; s <= nch; ++s) {
+          for (int which = 0; which < 2; ++which) {
+            const bool is_w1 = which == 0;
+            const int c = is_w1 ? s : s - 1;
+            if (is_w1 ? (s >= nch) : (s < 1)) continue;
+            for (int kb = 0; kb < 4; ++kb) {
+              mbar_wait(&w_empty[stage], wphase ^ 1);
+              if (rank == 0) mbar_arrive_expect_tx(&w_full[stage], 2 * W_SLOT);
+              const int c0 = is_w1 ? kb * 64 : c * M2_NC + kb * 64;
+              const int c1 = is_w1 ? c * M2_NC + (int)rank * 128 : (int)rank * 128;       // this CTA's half of the rows
+              tma_load_2d_pair(s_w + stage * W_SLOT, is_w1 ? &tmW1 : &tmW2, map_to_rank(&w_full[stage], 0), c0, c1);
+              if (++stage == NST) { stage = 0; wphase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      if (rank == 0) {
+        // ===================================================== MMA issuer (leader CTA): M = 256 over the pair
+        constexpr uint32_t idesc1 = make_idesc(UMMA_FMT_BF16, 256, M2_NC, 0, 0);
+        constexpr uint32_t idesc2 = make_idesc_ab(UMMA_FMT_F16, UMMA_FMT_F16, 256, M2_H);
+        const uint64_t xdesc0 = make_smem_desc(smem_u32(s_x), 16, 1024, UMMA_LAYOUT_SW128);
+        const uint64_t adesc0 = make_smem_desc(smem_u32(s_a), 16, 1024, UMMA_LAYOUT_SW128);
+        const uint64_t wdesc0 = make_smem_desc(smem_u32(s_w), 16, 1024, UMMA_LAYOUT_SW128);
+        int stage = 0;
+        uint32_t wphase = 0;
+        int it = 0;
+        uint32_t g1 = 0, g2 = 0;
+        for (int t = gid; t < tiles; t += ngroups, ++it) {
+          mbar_wait(x_full, it & 1);
+          for (int s = 0; s <= nch; ++s) {
+            if (s < nch) {
+              mbar_wait(acc1_empty, (g1 & 1) ^ 1);
+              mbar_wait_cluster(p_acc1_empty, (g1 & 1) ^ 1);
+              tc_fence_after();
+#pragma unroll
+              for (int kb = 0; kb < 4; ++kb) {
+                mbar_wait(&w_full[stage], wphase);
+                const uint64_t ad = xdesc0 + (uint64_t)(kb * 1024);
+                const uint64_t bd = wdesc0 + (uint64_t)(stage * (W_SLOT >> 4));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma2(tmem_base, ad + 2 * k, bd + 2 * k, idesc1, (kb | k) ? 1u : 0u);
+                umma2_commit(&w_empty[stage]);
+                if (++stage == NST) { stage = 0; wphase ^= 1; }
+              }
+              umma2_commit(acc1_full);
+              if (s == nch - 1) umma2_commit(x_empty);
+              ++g1;
+            }
+            if (s >= 1) {
+              const int c = s - 1;
+              if (c == 0) {
+                mbar_wait(acc2_empty, (it & 1) ^ 1);
+                mbar_wait_cluster(p_acc2_empty, (it & 1) ^ 1);
+              }
+              mbar_wait(a2_full, g2 & 1);
+              mbar_wait_cluster(p_a2_full, g2 & 1);
+              tc_fence_after();
+#pragma unroll
+              for (int kb = 0; kb < 4; ++kb) {
+                mbar_wait(&w_full[stage], wphase);
+                const uint64_t ad = adesc0 + (uint64_t)(kb * 1024);
+                const uint64_t bd = wdesc0 + (uint64_t)(stage * (W_SLOT >> 4));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma2(tmem_base + 256, ad + 2 * k, bd + 2 * k, idesc2, (c | kb | k) ? 1u : 0u);
+                umma2_commit(&w_empty[stage]);
+                if (++stage == NST) { stage = 0; wphase ^= 1; }
+              }
+              umma2_commit(a2_empty);
+              if (c == nch - 1) umma2_commit(acc2_full);
+              ++g2;
+            }
+          }
+        }
+      } else {
+        // ===================================================== relay (peer CTA): one remote arrive per local completion
+        const uint32_t r_acc1 = map_to_rank(p_acc1_empty, 0), r_a2 = map_to_rank(p_a2_full, 0), r_acc2 = map_to_rank(p_acc2_empty, 0);
+        uint32_t g = 0;
+        int it = 0;
+        for (int t = gid; t < tiles; t += ngroups, ++it) {
+          for (int c = 0; c < nch; ++c, ++g) {
+            mbar_wait(acc1_empty, g & 1);
+            mbar_arrive_cluster(r_acc1);
+            mbar_wait(a2_full, g & 1);
+            mbar_arrive_cluster(r_a2);
+          }
+          mbar_wait(acc2_empty, it & 1);
+          mbar_arrive_cluster(r_acc2);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+#include "tc_mlp2_epilogue.inc"
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                   // nobody leaves while the partner may still signal / read this CTA
+  if (warp == 1) tmem_dealloc2<512>(tmem_base);
+}
+
+template <int LN>
+static int launch_mlp2x(const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& ty,
+                        const CUtensorMap& tr, const CUtensorMap& tl, const Mlp2Args& a, cudaStream_t st) {
+  auto kern = tc_mlp2x_kernel<LN>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  V3_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    V3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM));
+    configured_dev = dev;
+  }
+  const int tiles = ceil_div(a.M, 256);
+  int groups = sm_count() / 2;
+  if (groups > tiles) groups = tiles;
+  V3_CUDA(launch_pdl(kern, dim3(groups * 2), dim3(M2_THREADS), (size_t)M2_SMEM, st, tx, tw1, tw2, ty, tr, tl, a));
+  V3_LAUNCH_CHECK();
+  return VIT3D_OK;
 }
 
 bool tc_mlp2_supported(int M, int H, int d) { return M > 0 && H == M2_H && d % M2_NC == 0 && d >= M2_NC; }
@@ -491,7 +501,8 @@ int tc_mlp2_fwd(const void* xn, const void* w1, const float* b1, const void* w2_
                 cudaStream_t st) {
   if (!tc_mlp2_supported(M, H, d)) V3_UNSUPPORTED("fused MLP: unsupported shape M=%d H=%d d=%d", M, H, d);
   if (ln_f32 && !ln_out) { set_error("fused MLP: fp32 LayerNorm output requested without a buffer"); return VIT3D_ERR_INVALID; }
-  const bool pair = M > 128 && tuning(VIT3D_TUNE_MLP_PAIR) != 0;
+  const int pair_mode = M > 128 ? tuning(VIT3D_TUNE_MLP_PAIR) : 0;       // 1: multicast pairs (cta_group::1), 2: cta_group::2
+  const bool pair = pair_mode != 0;
   CUtensorMap tx, tw1, tw2, ty, tr, tl;
   int rc = make_tmap_2d(&tx, xn, 2, M, H, H, 128, 64, 128);
   if (rc != VIT3D_OK) return rc;
@@ -511,6 +522,10 @@ int tc_mlp2_fwd(const void* xn, const void* w1, const float* b1, const void* w2_
   Mlp2Args a;
   a.b1 = b1; a.b2 = b2; a.gamma = gamma; a.beta = beta; a.eps = eps; a.M = M; a.d = d;
   const int mode = ln_f32 ? 2 : (ln_out ? 1 : 0);
+  if (pair_mode == 2) {
+    if (mode == 2) return launch_mlp2x<2>(tx, tw1, tw2, ty, tr, tl, a, st);
+    return mode ? launch_mlp2x<1>(tx, tw1, tw2, ty, tr, tl, a, st) : launch_mlp2x<0>(tx, tw1, tw2, ty, tr, tl, a, st);
+  }
   if (pair) {
     if (mode == 2) return launch_mlp2<true, 2>(tx, tw1, tw2, ty, tr, tl, a, st);
     return mode ? launch_mlp2<true, 1>(tx, tw1, tw2, ty, tr, tl, a, st) : launch_mlp2<true, 0>(tx, tw1, tw2, ty, tr, tl, a, st);

@@ -7,7 +7,7 @@ from vit3d_b200._lib import call, lib, ptr, stream
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--d", type=int, default=2048)
-ap.add_argument("--pair", type=int, default=1)
+ap.add_argument("--pair", type=int, default=1, help="0 one CTA per tile, 1 multicast pairs, 2 cta_group::2 pairs")
 ap.add_argument("--iters", type=int, default=3)
 a = ap.parse_args()
 dev = "cuda:0"
