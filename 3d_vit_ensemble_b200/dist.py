@@ -124,13 +124,20 @@ class GradReducer:
             return "embeddings"
         return "head+norm"
 
-    def prepare(self):
+    def prepare(self, defer: bool = False):
+        """Start a step: zero the arena, point every p.grad into it.  With bucket overlap EXACTLY ONE backward pass may
+        run between prepare() and finish(): a bucket is all-reduced as soon as its last gradient has been reported, so
+        a second backward (gradient accumulation, the reference's --gradient_accumulation_steps) would add into
+        gradients that are already reduced or in flight.  For accumulation pass defer=True: nothing is launched until
+        finish(), which then all-reduces the whole arena once."""
         self.flat.zero_()
         for n, p in self._named:
             p.grad = self.views[n]
         self._pending = {b: len(ps) for b, ps in self._bucket_params.items()}
         self._handles = []
         self._seen = set()
+        self._defer = bool(defer)
+        self._launched = set()
         # parameters whose gradient the kernels accumulate in place never reach autograd's hooks:
         # functional._grad_done reports them here instead
         from . import functional as F
@@ -146,11 +153,12 @@ class GradReducer:
         if b is None:
             return
         self._pending[b] -= 1
-        if self._pending[b] == 0 and self.overlap:
+        if self._pending[b] == 0 and self.overlap and not getattr(self, "_defer", False):
             self._launch(b)
 
     def _launch(self, b):
         _, ws = world()
+        self._launched.add(b)
         if ws <= 1:
             return
         s, e = self.ranges[b]
@@ -169,7 +177,7 @@ class GradReducer:
         _, ws = world()
         if ws <= 1:
             return
-        if not self.overlap:
+        if not self.overlap or getattr(self, "_defer", False):
             self._handles.append(dist.all_reduce(self.flat, group=self.group, async_op=True))
         else:
             for b, left in self._pending.items():
@@ -269,13 +277,19 @@ class ShardedEnsemble:
         self._streams = None
         params = list(ensemble.parameters()) if hasattr(ensemble, "parameters") else []
         self._cuda = bool(params) and params[0].is_cuda
+        self._graphed_all = None
         if graphs and self._cuda:
-            from .graphs import GraphedInference
+            from .graphs import GraphedInference, GraphedMembers
             self._graphed = [GraphedInference(t) for t in ensemble.transformers]
+            # batch-major sharding: every member runs on the same slice -> ONE graph with the members as parallel
+            # branches (concurrent=False keeps the members back to back, for A/B timing)
+            self._graphed_all = {c: GraphedMembers(ensemble, concurrent=c) for c in (True, False)}
         self.graphed = self._graphed is not None
 
     def graph_runners(self):
-        return list(self._graphed) if self._graphed is not None else []
+        if self._graphed is None:
+            return []
+        return list(self._graphed) + list(self._graphed_all.values())
 
     # ---- static plan per (batch size, world size)
     def _plan(self, B: int, device):
@@ -379,8 +393,22 @@ class ShardedEnsemble:
         if handle is not None:
             torch.cuda.current_stream(dev).wait_event(handle.event)
             staged = handle.views
-        buf = torch.zeros(pl["maxlen"], device=dev, dtype=torch.float32)
         conc = self.concurrent
+        m_all = len(self.ensemble.transformers)
+        same_slice = len(mine) == m_all and len({(b0, b1) for _, b0, b1 in mine}) == 1 and [j for j, _, _ in mine] == list(range(m_all))
+        if self._graphed_all is not None and same_slice:
+            # one graph launch: all members of this rank's slice as parallel branches
+            _, b0, b1 = mine[0]
+            if conc is None:
+                conc = (b1 - b0) <= self.CONCURRENT_MAX_SLICE
+            xs = staged[(b0, b1)] if staged is not None else x[b0:b1]
+            local = self._graphed_all[bool(conc)](xs)                    # (n, m)
+            buf = torch.zeros(pl["maxlen"], device=dev, dtype=torch.float32)
+            buf[:local.numel()] = local.t().reshape(-1)                  # member-major inside the rank's chunk (perm layout)
+            if handle is not None:
+                self._stage_sets[handle.key]["free"].record(torch.cuda.current_stream(dev))
+            return self._gather(buf, pl, B, ws, dev)
+        buf = torch.zeros(pl["maxlen"], device=dev, dtype=torch.float32)
         if conc is None:
             conc = self._cuda and len(mine) > 1 and max(b1 - b0 for _, b0, b1 in mine) <= self.CONCURRENT_MAX_SLICE
         if conc and self._streams is None:
@@ -405,6 +433,9 @@ class ShardedEnsemble:
             main.wait_stream(s)
         if handle is not None:
             self._stage_sets[handle.key]["free"].record(main)      # this staging set may be overwritten again
+        return self._gather(buf, pl, B, ws, dev)
+
+    def _gather(self, buf, pl, B, ws, dev):
         if ws > 1:
             gathered = torch.empty(ws * buf.numel(), device=dev, dtype=torch.float32)
             dist.all_gather_into_tensor(gathered, buf, group=self.group)

@@ -82,6 +82,83 @@ class GraphedInference:
         return self._graphs[key][1]
 
 
+class GraphedMembers:
+    """The member forwards of a TransformerEnsemble (modeling.py:354, `[t(x)[0] for t in transformers]`) replayed from
+    ONE CUDA graph in which every member is a parallel branch (forked streams inside the capture): one graph launch
+    per call, and the members overlap on the GPU when a batch is too small to fill it with one member.
+
+        g = GraphedMembers(ensemble)
+        logits = g(x)            # (B, n_members) fp32, static buffer
+    """
+
+    def __init__(self, ensemble, warmup: int = 2, concurrent: bool = True):
+        self.ensemble = ensemble
+        self.members = list(ensemble.transformers)
+        self.warmup = warmup
+        self.concurrent = concurrent
+        self._graphs = {}
+        self._params = [p for m in self.members for p in m.parameters()]
+        self._sig = None
+        self.launches_per_replay = 0
+        self.replays = 0
+        self.recaptures = 0
+
+    def _weights_signature(self):
+        return (tuple(p._version for p in self._params), tuple(p.data_ptr() for p in self._params),
+                F._STATE.get("epoch", 0), tuple(getattr(m, "precision", None) for m in self.members))
+
+    def _run(self, x, streams):
+        if x.dtype == torch.uint8:                  # N2: convert once for all members
+            x = F.u8_volumes_to_f32(x, self.members[0].input_mean)
+        main = torch.cuda.current_stream()
+        outs = []
+        if streams is None:
+            outs = [m(x)[0] for m in self.members]
+        else:
+            for m, s in zip(self.members, streams):
+                s.wait_stream(main)
+                with torch.cuda.stream(s):
+                    outs.append(m(x)[0])
+            for s in streams:
+                main.wait_stream(s)
+        return torch.cat([o.reshape(x.shape[0], -1).float() for o in outs], dim=1)
+
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor):
+        sig = self._weights_signature()
+        if sig != self._sig:
+            if self._graphs:
+                self._graphs = {}
+                self.recaptures += 1
+            self._sig = sig
+        key = (tuple(x.shape), x.dtype)
+        ent = self._graphs.get(key)
+        if ent is None:
+            for m in self.members:
+                m.eval()
+            static_x = x.clone()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(self.warmup):
+                    self._run(static_x, None)
+            torch.cuda.current_stream().wait_stream(s)
+            streams = [torch.cuda.Stream() for _ in self.members] if (self.concurrent and len(self.members) > 1) else None
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.lib().vit3d_launch_count()
+            with torch.cuda.graph(g):
+                out = self._run(static_x, streams)
+            self.launches_per_replay = _lib.lib().vit3d_launch_count() - n0
+            ent = (g, static_x, out)
+            self._graphs[key] = ent
+        g, static_x, out = ent
+        if x.data_ptr() != static_x.data_ptr():
+            static_x.copy_(x, non_blocking=True)
+        g.replay()
+        self.replays += 1
+        return out
+
+
 class GraphedTrainStep:
     """One captured training step: loss = model(x, y, pos_weight); loss.backward(); optimizer.step().
 

@@ -154,3 +154,96 @@ def load_training_state(path: str, model: torch.nn.Module, optimizer=None, sched
     if scheduler is not None and "scheduler" in state:
         scheduler.load_state_dict(state["scheduler"])
     return int(state.get("step", 0))
+
+
+# ----------------------------------------------------------------------------- CV / bootstrap sweep (replicas only)
+class _SweepJob:
+    """One (configuration, fold) training run of train_baseline_cv.py:269-278: SGD(lr 1e-4, momentum .9, wd 1e-2) under the
+    warm-up-cosine schedule (:111-119), `steps` optimizer steps at batch `batch`, validation every `eval_every` steps."""
+
+    def __init__(self, conf, fold, device, precision, batch, seed):
+        from .graphs import GraphedTrainStep
+        from .optim import FusedSGD
+        self.conf, self.fold = conf, fold
+        torch.manual_seed(seed)                                   # tools.set_seed(args) per fold (train_baseline_cv.py:272)
+        self.model = build_baseline(conf, precision=precision, vis=False).to(device)
+        self.model.train()
+        self.opt = FusedSGD(self.model.parameters(), lr=1e-4, momentum=0.9, weight_decay=1e-2)
+        self.step_fn = GraphedTrainStep(self.model, self.opt, warmup=1)
+        self.stream = torch.cuda.Stream(device=device)
+        self.steps_done = 0
+        self.best = -1.0
+        self.losses = []
+
+
+def warmup_cosine_lr(step: int, base_lr: float = 1e-4, warmup_steps: int = 1000, t_total: int = 100) -> float:
+    """utils/scheduler.py:46-63 (WarmupCosineSchedule) as a host scalar: with the scripts' defaults (warm-up 1000 steps,
+    100 steps in total) the learning rate never leaves the linear warm-up."""
+    import math
+    if step < warmup_steps:
+        return base_lr * float(step) / float(max(1.0, warmup_steps))
+    progress = float(step - warmup_steps) / float(max(1, t_total - warmup_steps))
+    return base_lr * max(0.0, 0.5 * (1.0 + math.cos(math.pi * 2.0 * 0.5 * progress)))
+
+
+def run_packed_sweep(jobs: Sequence[Tuple[int, int]], data, *, steps: int = 100, batch: int = 4, eval_every: int = 24,
+                     concurrent: int = 6, device="cuda", precision: str = "bf16", seed: int = 42) -> Dict[str, float]:
+    """The CV sweep of train_baseline_cv.py (18 configurations x 5 folds, BASELINE.json config 5) as independent jobs
+    packed on ONE GPU (one process per GPU takes its share of the job list from dist.pack_jobs: replicas only, no
+    collective).  A batch-4 step is 260 token rows - three 128-row tiles on a 148-SM GPU - so `concurrent` jobs are
+    kept in flight, each on its own stream, each step one CUDA-graph replay of the fused training step; the job
+    streams interleave on the GPU.
+
+    jobs: (configuration id, fold) pairs.  data(fold) -> (train_x (N,1,128,128,5), train_y (N,), val_x, val_y) host
+    tensors (pinned for speed).  Returns wall-clock numbers: jobs/s, optimizer steps/s, time spent building models
+    and capturing graphs, and per-job results (last loss, best validation balanced accuracy)."""
+    import time
+    from .dist import batch_pos_weight
+    dev = torch.device(device)
+    t0 = time.perf_counter()
+    pending = list(jobs)
+    active: List[_SweepJob] = []
+    done = []
+    setup_s = 0.0
+    total_steps = 0
+    cache = {}
+
+    def fold_data(fold):
+        if fold not in cache:
+            cache[fold] = data(fold)
+        return cache[fold]
+
+    while pending or active:
+        while pending and len(active) < concurrent:
+            conf, fold = pending.pop(0)
+            ts = time.perf_counter()
+            active.append(_SweepJob(conf, fold, dev, precision, batch, seed + fold))
+            setup_s += time.perf_counter() - ts
+        for job in list(active):
+            tx, ty, vx, vy = fold_data(job.fold)
+            n = tx.shape[0]
+            i0 = (job.steps_done * batch) % max(1, n - batch + 1)
+            xb, yb = tx[i0:i0 + batch], ty[i0:i0 + batch].float()
+            with torch.cuda.stream(job.stream):
+                job.step_fn.set_lr(warmup_cosine_lr(job.steps_done + 1))
+                loss = job.step_fn(xb.to(dev, non_blocking=True), yb.to(dev, non_blocking=True), batch_pos_weight(yb))
+            job.steps_done += 1
+            total_steps += 1
+            if job.steps_done % eval_every == 0 or job.steps_done == steps:
+                with torch.cuda.stream(job.stream):
+                    res = validate(job.model, vx, vy, batch_size=max(1, vx.shape[0]), graphs=False)
+                    job.model.train()
+                    job.best = max(job.best, float(res["balanced_accuracy"]))
+                    job.losses.append(float(loss))
+            if job.steps_done >= steps:
+                job.stream.synchronize()
+                done.append({"conf": job.conf, "fold": job.fold, "loss": job.losses[-1] if job.losses else float("nan"),
+                             "best_balanced_accuracy": job.best})
+                active.remove(job)
+                del job
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    F._STATE["step_dev"] = None
+    return {"jobs": len(done), "wall_s": wall, "jobs_per_s": len(done) / wall, "steps_per_s": total_steps / wall,
+            "setup_s": setup_s, "train_steps_per_s_excl_setup": total_steps / max(1e-9, wall - setup_s),
+            "concurrent": concurrent, "results": done}

@@ -188,3 +188,31 @@ def test_pos_weight_matches_sklearn_balanced():
         assert abs(float(D.batch_pos_weight(torch.tensor(y))) - want) < 1e-12, labels
         assert abs(float(D.global_pos_weight(torch.tensor(y))) - want) < 1e-12, labels
         assert abs(float(O.sklearn_pos_weight(torch.tensor(y))) - want) < 1e-12, labels
+
+
+def _accumulate_two_backwards(rank, world):
+    """gradient accumulation (two backward passes per step) with prepare(defer=True) equals the big batch."""
+    torch.manual_seed(0)
+    model = Toy()
+    ref = Toy()
+    ref.load_state_dict(model.state_dict())
+    x = torch.randn(8, 6)
+    y = (torch.arange(8) % 3 == 0).float()
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(ref(x).reshape(-1), y)
+    loss.backward()
+    xs, ys = x[rank::world], y[rank::world]
+    red = D.GradReducer(model, overlap=True)
+    red.prepare(defer=True)
+    half = xs.shape[0] // 2
+    for a, b in ((0, half), (half, xs.shape[0])):          # two micro-batches, each scaled to its share of the mean
+        l = torch.nn.functional.binary_cross_entropy_with_logits(model(xs[a:b]).reshape(-1), ys[a:b], reduction="sum") / xs.shape[0]
+        l.backward()
+    assert not red._launched                                # nothing was reduced before finish()
+    red.finish()
+    for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        torch.testing.assert_close(p.grad, q.grad, rtol=1e-5, atol=1e-6)
+    red.remove()
+
+
+def test_grad_reducer_deferred_mode_supports_gradient_accumulation():
+    spawn(_accumulate_two_backwards)
