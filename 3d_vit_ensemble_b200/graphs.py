@@ -193,12 +193,23 @@ class GraphedTrainStep:
         # taken before the capture) continues Adam's bias correction and the mask sequence instead of restarting them
         self.step_dev = torch.full((1,), int(getattr(optimizer, "_steps", 0)), device=dev, dtype=torch.int32)
         self.fused = False
+        # per-step scalars (class weight, learning rate) reach the device through a small ring of PINNED host slots:
+        # a copy from pageable memory would make the host wait for the stream (it serialises concurrent job streams),
+        # a fill kernel would be a framework kernel in the step
+        self._scalars = torch.empty(128, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.empty(128)
+        self._scalar_i = 0
         optimizer.lr_dev = self.lr_dev
         if hasattr(optimizer, "exp_avg"):
             optimizer.step_dev = self.step_dev
 
+    def _put_scalar(self, dst: torch.Tensor, value: float):
+        i = self._scalar_i
+        self._scalar_i = (i + 1) % self._scalars.numel()
+        self._scalars[i] = float(value)
+        dst.copy_(self._scalars[i:i + 1], non_blocking=True)
+
     def set_lr(self, lr: float):
-        self.lr_dev.copy_(torch.tensor([float(lr)], dtype=torch.float32))      # a copy, not a fill kernel
+        self._put_scalar(self.lr_dev, lr)
         self.opt.param_groups[0]["lr"] = float(lr)
 
     def _fwd_bwd(self):
@@ -264,7 +275,7 @@ class GraphedTrainStep:
         if y.data_ptr() != self.y.data_ptr():
             self.y.copy_(y, non_blocking=True)
         if self.use_pw:
-            self.pw_dev.copy_(torch.tensor([float(pos_weight)], dtype=torch.float32))    # a copy, not a fill kernel
+            self._put_scalar(self.pw_dev, float(pos_weight))
         self._graph.replay()
         self._after_replay()
         return self.loss

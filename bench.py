@@ -15,6 +15,8 @@ workloads that DO exchange data, reported under `workloads`:
     ensemble_infer   confs 5+9+11 + meta-classifier (models/modeling.py:353-356): (member, batch-slice) work list cut
                      into equal-FLOP chunks, one all-gather of the member logits, meta-head on every rank
     conf5_infer_tf32 the headline workload in the TF32 (1e-3 logit tolerance) mode
+    cv_sweep         a bounded sample of the 18 x 5 train_baseline_cv.py sweep as independent jobs packed on the GPUs
+                     (replicas only), jobs/s
 
 `value` = volumes/s with the batch resident in HBM; `e2e` = the same through the public module call with pinned HOST
 input, H2D copy and D2H read of the result inside the timed region (`e2e.variants.u8`: volumes cross PCIe as the
@@ -434,6 +436,47 @@ def ensemble_small_batch_probe(ctx, args):
     return out
 
 
+def cv_sweep_leg(ctx, args, jobs_per_gpu=6):
+    """BASELINE.json config 5 (the train_baseline_cv.py sweep: 18 configurations x 5 folds of 100 steps at batch 4,
+    validation every 24 steps on 18 volumes) on a bounded sample: `jobs_per_gpu` x world of the 90 jobs, dealt to the
+    ranks longest-first, several jobs in flight per GPU (workflow.run_packed_sweep).  Replicas only - no collective.
+    The whole 90-job sweep: tools/run_cv_sweep.py."""
+    import importlib.util
+    import torch
+    import vit3d_b200
+    from vit3d_b200 import workflow as W
+    from vit3d_b200.dist import pack_jobs
+    spec = importlib.util.spec_from_file_location("run_cv_sweep", os.path.join(ROOT, "tools", "run_cv_sweep.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    all_jobs = [(c, f) for c in range(1, 19) for f in range(5)]
+    pick = all_jobs[::max(1, len(all_jobs) // (jobs_per_gpu * ctx.world))][:jobs_per_gpu * ctx.world]
+    costs = []
+    for c, _ in pick:
+        cfg = vit3d_b200.north_star_config(c)
+        costs.append(cfg.transformer["num_layers"] * (4 * 256 + 2 * cfg.transformer["mlp_dim"]))
+    mine = [pick[i] for i in pack_jobs(costs, ctx.world)[ctx.rank]]
+    if ctx.dist is not None:
+        ctx.dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = W.run_packed_sweep(mine, mod.synth_fold, steps=100, batch=4, concurrent=6, device=str(ctx.dev))
+    wall = time.perf_counter() - t0
+    if ctx.dist is not None:
+        t = torch.tensor([wall], device=ctx.dev)
+        ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.MAX)
+        wall = float(t)
+    n = len(pick)
+    torch.cuda.empty_cache()
+    return {"jobs": n, "of": len(all_jobs), "wall_s": wall, "jobs_per_s": n / wall, "train_steps_per_s": n * 100 / wall,
+            "value": n * 100 * 4 / wall, "unit": UNIT, "concurrent_jobs_per_gpu": 6, "collective": None,
+            "rank0_setup_s": res["setup_s"], "rank0_train_steps_per_s_excl_setup": res["train_steps_per_s_excl_setup"],
+            "timing": "host wall clock around the whole sample (model construction, graph capture, training, validation), max over ranks",
+            "config": {"workload": "train_baseline_cv.py sweep sample: 100 steps at batch 4, validation every 24 steps on 18 volumes, "
+                                   "jobs = (configuration, fold) pairs spread over the 18 configurations",
+                       "jobs_per_gpu": jobs_per_gpu, "parallelism": f"{ctx.world} ranks: independent jobs packed longest-first, no collective"}}
+
+
 def sharded_e2e_run(sharded, x_host, res_host, nsteps):
     """End-to-end loop of the sharded ensemble: `stage` ships THIS rank's slice of the host batch on a copy stream, the
     copy of step s+1 overlaps the member forwards of step s, the result is read back before a step counts as done."""
@@ -505,7 +548,7 @@ def main():
     elif args.legs == "none":
         names = []
     else:
-        names = [s for s in args.legs.split(",") if s]
+        names = [s for s in args.legs.split(",") if s and s != "cv_sweep"]
     for nm in names:
         try:
             if nm == "conf5_infer_tf32":
@@ -522,6 +565,13 @@ def main():
             legs["ensemble_small_batch"] = ensemble_small_batch_probe(ctx, args)
         except Exception as e:
             legs["ensemble_small_batch"] = {"error": f"{type(e).__name__}: {e}"[:400]}
+    if args.legs == "auto" or "cv_sweep" in args.legs.split(","):
+        try:
+            legs["cv_sweep"] = cv_sweep_leg(ctx, args)
+        except Exception as e:
+            legs["cv_sweep"] = {"error": f"{type(e).__name__}: {e}"[:400]}
+            if ctx.dist is not None:
+                raise
 
     roof = cpu_base = None
     if rank == 0:
