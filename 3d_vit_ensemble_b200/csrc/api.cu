@@ -326,9 +326,17 @@ int vit3d_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int h
   V3_REQUIRE(qkv && ctx, "attn_fwd: null pointer");
   V3_REQUIRE(B >= 0 && S > 0 && heads > 0 && D > 0, "attn_fwd: bad shape");
   cudaStream_t st = as_stream(stream);
-  if (prec == VIT3D_PREC_BF16 && tc_attn_supported(S, heads, D)) return tc_attn_fwd(qkv, ctx, probs, B, S, heads, D, st);
+  if (prec == VIT3D_PREC_BF16 && tc_attn_supported(S, heads, D)) return tc_attn_fwd(qkv, ctx, probs, S, B, S, heads, D, st);
   return launch_attn_fwd_generic(qkv, act_f32(prec), ctx, probs, B, S, heads, D, prec == VIT3D_PREC_TF32, st);
 }
+int vit3d_attn_fwd_padded(const void* qkv, void* ctx, float* probs, int probs_ld, int B, int S, int heads, int D,
+                          vit3d_stream_t stream) {
+  V3_REQUIRE(qkv && ctx && probs, "attn_fwd_padded: null pointer");
+  V3_REQUIRE(B >= 0 && S > 0 && heads > 0 && D > 0 && probs_ld >= S, "attn_fwd_padded: bad shape");
+  if (!tc_attn_supported(S, heads, D)) V3_UNSUPPORTED("attn_fwd_padded: unsupported shape S=%d heads=%d D=%d", S, heads, D);
+  return tc_attn_fwd(qkv, ctx, probs, probs_ld, B, S, heads, D, as_stream(stream));
+}
+int vit3d_attn_padded_supported(int S, int heads, int D) { return tc_attn_supported(S, heads, D) ? 1 : 0; }
 int vit3d_attn_bwd(const void* dctx, const void* qkv, void* dqkv, int B, int S, int heads, int D, int prec,
                    vit3d_stream_t stream) {
   V3_REQUIRE(dctx && qkv && dqkv, "attn_bwd: null pointer");

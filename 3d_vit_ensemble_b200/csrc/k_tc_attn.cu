@@ -90,10 +90,14 @@ __device__ __forceinline__ void st_shared_u32_if(bool pred, uint32_t addr, uint3
 // The warps are only coupled through data: the producer warp refills a volume buffer when all compute warps
 // have released it (mbarrier with one arrival per warp), and every warp ships its own context tile, so a fast
 // warp walks on into the next volume instead of waiting at a block-wide barrier (15 % of the samples before).
-template <int D, int THREADS, bool VIS>
+// VIS: 0 = no probabilities; 1 = probabilities in the reference's packed layout (rows of 65 floats); 2 = rows padded to
+// `pld` floats with pld % 8 == 0 (288-byte rows at pld = 72): every row starts on a 32-byte sector, so each 8-byte
+// column pair a lane stores is sector-aligned - the packed layout's rows start at 4-byte phases, its 32-byte row
+// segments straddle sectors and the L1 -> L2 write traffic was 1.58x the payload (ncu, profiles/r01_attn_fwd_vis_*).
+template <int D, int THREADS, int VIS>
 __global__ void __launch_bounds__(THREADS + 32, 1)
 attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, float* __restrict__ probs,
-                   int B, float scale_log2e) {
+                   int B, float scale_log2e, int pld) {
   constexpr int HEADS = AT_A / D;
   constexpr int NW = THREADS / 32;    // compute warps
   constexpr int KSTEPS = D / 16;      // k-steps of the Q K^T product
@@ -212,7 +216,23 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
       // `full` is warp-uniform, so the stores below are predicated instructions, not divergent branches.
       const bool full = rt < 4;
       const bool w0 = full || g == 0, w1 = full;
-      if constexpr (VIS) {
+      if constexpr (VIS == 2) {
+#pragma unroll
+        for (int nt = 0; nt < 9; ++nt) {
+          s[nt][0] *= inv0; s[nt][1] *= inv0;
+          s[nt][2] *= inv1; s[nt][3] *= inv1;
+        }
+        float* p0 = probs + ((size_t)(b * HEADS + h) * AT_S + row0) * pld + 2 * t;
+        float* p1 = p0 + 8 * (size_t)pld;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          st_global_f2_if(w0, p0 + nt * 8, s[nt][0], s[nt][1]);
+          st_global_f2_if(w1, p1 + nt * 8, s[nt][2], s[nt][3]);
+        }
+        st_global_f1_if(tail && w0, p0 + 64, s[8][0]);
+        st_global_f1_if(tail && w1, p1 + 64, s[8][2]);
+      }
+      if constexpr (VIS == 1) {
         // The probabilities leave from the accumulator registers, normalised in place (the P V product below
         // then needs no rescaling).  What bounds this kernel with vis=True is the L1 store path and the issue
         // slots around it, so every store carries a PAIR of columns as one 8-byte word and the code is
@@ -274,7 +294,7 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
 #pragma unroll
       for (int dt = 0; dt < DT; ++dt) {
         const int col = h * D + dt * 8 + 2 * t;
-        const float c0 = VIS ? 1.f : inv0, c1 = VIS ? 1.f : inv1;      // VIS: P was normalised before the product
+        const float c0 = VIS != 0 ? 1.f : inv0, c1 = VIS != 0 ? 1.f : inv1;      // VIS: P was normalised before the product
         st_shared_u32_if(w0, sb + row0 * AT_PITCH + col * 2, pack_bf16(o[dt][0] * c0, o[dt][1] * c0));
         st_shared_u32_if(w1, sb + row1 * AT_PITCH + col * 2, pack_bf16(o[dt][2] * c1, o[dt][3] * c1));
       }
@@ -301,20 +321,21 @@ bool tc_attn_supported(int S, int heads, int D) {
   return S == AT_S && heads * D == AT_A && (D == 16 || D == 32 || D == 64);
 }
 
-template <int D, int THREADS, bool VIS>
-static int launch_attn_v(const void* qkv, void* ctx, float* probs, int B, cudaStream_t st) {
+template <int D, int THREADS, int VIS>
+static int launch_attn_v(const void* qkv, void* ctx, float* probs, int pld, int B, cudaStream_t st) {
   auto kern = attn_fwd_tc_kernel<D, THREADS, VIS>;
   V3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
   const int grid = B < sm_count() ? B : sm_count();
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)D);
   V3_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS + 32), (size_t)AT_SMEM, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
-                     reinterpret_cast<__nv_bfloat16*>(ctx), probs, B, scale_log2e));
+                     reinterpret_cast<__nv_bfloat16*>(ctx), probs, B, scale_log2e, pld));
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
 }
 template <int D, int THREADS>
-static int launch_attn(const void* qkv, void* ctx, float* probs, int B, cudaStream_t st) {
-  return probs ? launch_attn_v<D, THREADS, true>(qkv, ctx, probs, B, st) : launch_attn_v<D, THREADS, false>(qkv, ctx, probs, B, st);
+static int launch_attn(const void* qkv, void* ctx, float* probs, int pld, int B, cudaStream_t st) {
+  if (!probs) return launch_attn_v<D, THREADS, 0>(qkv, ctx, probs, pld, B, st);
+  return pld == AT_S ? launch_attn_v<D, THREADS, 1>(qkv, ctx, probs, pld, B, st) : launch_attn_v<D, THREADS, 2>(qkv, ctx, probs, pld, B, st);
 }
 // 0 = automatic.  20 warps make a volume of 8 heads exactly two rounds of (head, row-tile) tasks and are the
 // faster choice without the probabilities; with them (vis=True) the kernel is bound by its store path and 16
@@ -326,22 +347,26 @@ static int attn_threads(int D, bool vis) {
   return (D <= 32 && vis) ? 512 : 640;
 }
 
-int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int heads, int D, cudaStream_t st) {
+int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int probs_ld, int B, int S, int heads, int D, cudaStream_t st) {
   if (!tc_attn_supported(S, heads, D)) V3_UNSUPPORTED("tc attention: unsupported shape S=%d heads=%d D=%d", S, heads, D);
   if (B <= 0) return VIT3D_OK;
+  if (probs && probs_ld != S && (probs_ld < S || probs_ld % 8 || (reinterpret_cast<uintptr_t>(probs) & 31))) {
+    set_error("tc attention: padded probability rows need probs_ld %% 8 == 0, probs_ld >= S and a 32-byte aligned buffer");
+    return VIT3D_ERR_INVALID;
+  }
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(ctx) & 15) ||
       (reinterpret_cast<uintptr_t>(probs) & 7)) {
     set_error("tc attention: qkv/ctx must be 16-byte aligned, probs 8-byte aligned");
     return VIT3D_ERR_INVALID;
   }
   if (attn_threads(D, probs != nullptr) == 640) {
-    if (D == 16) return launch_attn<16, 640>(qkv, ctx, probs, B, st);
-    if (D == 32) return launch_attn<32, 640>(qkv, ctx, probs, B, st);
-    return launch_attn<64, 640>(qkv, ctx, probs, B, st);
+    if (D == 16) return launch_attn<16, 640>(qkv, ctx, probs, probs_ld, B, st);
+    if (D == 32) return launch_attn<32, 640>(qkv, ctx, probs, probs_ld, B, st);
+    return launch_attn<64, 640>(qkv, ctx, probs, probs_ld, B, st);
   }
-  if (D == 16) return launch_attn<16, 512>(qkv, ctx, probs, B, st);
-  if (D == 32) return launch_attn<32, 512>(qkv, ctx, probs, B, st);
-  return launch_attn<64, 512>(qkv, ctx, probs, B, st);
+  if (D == 16) return launch_attn<16, 512>(qkv, ctx, probs, probs_ld, B, st);
+  if (D == 32) return launch_attn<32, 512>(qkv, ctx, probs, probs_ld, B, st);
+  return launch_attn<64, 512>(qkv, ctx, probs, probs_ld, B, st);
 }
 
 // ============================================================================ backward

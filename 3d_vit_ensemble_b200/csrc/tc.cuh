@@ -57,7 +57,8 @@ int tc_mlp_bwd(const void* gy, const void* w2_t, const void* w1_t, const void* d
                int H, int d, cudaStream_t st);
 
 bool tc_attn_supported(int S, int heads, int D);
-int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int heads, int D, cudaStream_t st);
+// probs_ld: floats per probability row (S = the packed layout of the reference tensor; a multiple of 8 = padded rows)
+int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int probs_ld, int B, int S, int heads, int D, cudaStream_t st);
 // db_q / db_k / db_v (each [heads*D] fp32, all or none): += column sums of dq / dk / dv (the q, k, v bias gradients)
 int tc_attn_bwd(const void* dctx, const void* qkv, void* dqkv, float* db_q, float* db_k, float* db_v, int B, int S,
                 int heads, int D, cudaStream_t st);

@@ -476,8 +476,18 @@ class AttnCoreFn(torch.autograd.Function):
         ad = act_dtype(prec)
         qkv = _c(qkv.to(ad))
         out = torch.empty(B, S, A, device=qkv.device, dtype=ad)
-        probs = torch.empty(B, heads, S, S, device=qkv.device) if vis else None
-        call("vit3d_attn_fwd", ptr(qkv), ptr(out), ptr(probs), B, S, heads, D, PREC[prec], stream())
+        probs = None
+        pld = int(_STATE.get("probs_row_pad", 8))
+        if vis and prec == "bf16" and pld > 1 and _lib.lib().vit3d_attn_padded_supported(S, heads, D):
+            # rows padded to a multiple of 8 floats (72 for S = 65): sector-aligned stores; callers get the [..., :S] view -
+            # the shape and values of the reference's attention_probs (modeling.py:89-90), not contiguous
+            ld = (S + pld - 1) // pld * pld
+            store = torch.empty(B, heads, S, ld, device=qkv.device)
+            call("vit3d_attn_fwd_padded", ptr(qkv), ptr(out), ptr(store), ld, B, S, heads, D, stream())
+            probs = store[..., :S]
+        else:
+            probs = torch.empty(B, heads, S, S, device=qkv.device) if vis else None
+            call("vit3d_attn_fwd", ptr(qkv), ptr(out), ptr(probs), B, S, heads, D, PREC[prec], stream())
         ctx.save_for_backward(qkv)
         ctx.meta = (heads, D, prec)
         if probs is None:

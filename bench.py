@@ -673,11 +673,15 @@ def roofline_probe(args, cfg, B, dev, train=False):
         hbm = peaks["hbm_gbs"]
         qkv = (torch.randn(M, 3 * H, device=dev) * 0.5).to(torch.bfloat16)
         ctx = torch.empty(M, H, device=dev, dtype=torch.bfloat16)
-        probs = torch.empty(B, heads, 65, 65, device=dev) if args.vis else None
-        t = _time_launches(lambda: call("vit3d_attn_fwd", ptr(qkv), ptr(ctx), ptr(probs), B, 65, heads, H // heads,
-                                        PREC["bf16"], stream()))
-        nb = M * 4 * H * 2 + (B * heads * 65 * 65 * 4 if args.vis else 0)
-        others.append({"kernel": "attention forward (attn_fwd_tc_kernel, vis=%s)" % bool(args.vis), "bound": "hbm",
+        if args.vis:      # the layout the module path uses: probability rows padded to 72 floats (sector-aligned stores)
+            probs = torch.empty(B, heads, 65, 72, device=dev)
+            t = _time_launches(lambda: call("vit3d_attn_fwd_padded", ptr(qkv), ptr(ctx), ptr(probs), 72, B, 65, heads, H // heads,
+                                            stream()))
+        else:
+            t = _time_launches(lambda: call("vit3d_attn_fwd", ptr(qkv), ptr(ctx), None, B, 65, heads, H // heads,
+                                            PREC["bf16"], stream()))
+        nb = M * 4 * H * 2 + (B * heads * 65 * 65 * 4 if args.vis else 0)      # payload: the 65 valid floats of a row
+        others.append({"kernel": "attention forward (attn_fwd_tc_kernel, vis=%s, probability rows padded to 72 floats)" % bool(args.vis), "bound": "hbm",
                        "achieved": nb / (t * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": nb / (t * 1e-3) / 1e9 / hbm,
                        "ms_per_launch": t})
         wo = (torch.randn(H, H, device=dev) / 16).to(torch.bfloat16)

@@ -169,6 +169,14 @@ int vit3d_mlp_lnf_fwd(const void* xn, const void* w1_lp, const float* b1, const 
  * ctx [M, k*D] "act"; probs (optional, vis=True) fp32 [B,k,S,S]. */
 int vit3d_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int heads, int D, int prec,
                    vit3d_stream_t stream);
+/* Same in BF16 mode with PADDED probability rows: probs is [B,k,S,probs_ld] with probs_ld % 8 == 0 (72 for S = 65) and a
+ * 32-byte aligned base; only the first S floats of a row are written.  Every row then starts on a 32-byte sector and the
+ * column pairs a lane stores never straddle one (the packed rows of 65 floats start at 4-byte phases: 1.58x write
+ * amplification between L1 and L2).  The Python surface hands out `probs[..., :S]` - same shape and values as the
+ * reference's attention_probs tensor, non-contiguous. */
+int vit3d_attn_fwd_padded(const void* qkv, void* ctx, float* probs, int probs_ld, int B, int S, int heads, int D,
+                          vit3d_stream_t stream);
+int vit3d_attn_padded_supported(int S, int heads, int D);
 /* dqkv from dctx (probabilities are recomputed from qkv) */
 int vit3d_attn_bwd(const void* dctx, const void* qkv, void* dqkv, int B, int S, int heads, int D, int prec,
                    vit3d_stream_t stream);

@@ -66,3 +66,25 @@ def test_attention_backward_bf16(heads, B):
     assert np.isfinite(err) and err <= 0.03 * scale, (err, scale)
     rel = float((dqkv.double() - ref).norm() / ref.norm())
     assert rel < 0.01, rel
+
+
+@pytest.mark.parametrize("heads", [4, 8, 16])
+def test_padded_probability_rows_equal_packed_rows(heads):
+    """vit3d_attn_fwd_padded (rows of 72 floats, sector-aligned stores) writes the same probabilities and context as the
+    packed layout of the reference tensor; the padding floats are never touched."""
+    import vit3d_b200  # noqa: F401
+    from vit3d_b200._lib import PREC, call, ptr, stream
+    B, S, A = 150, 65, 256
+    D = A // heads
+    torch.manual_seed(heads)
+    qkv = (torch.randn(B, S, 3 * A, device=DEV) * 0.7).to(torch.bfloat16)
+    ctx0 = torch.empty(B, S, A, device=DEV, dtype=torch.bfloat16)
+    ctx1 = torch.empty_like(ctx0)
+    packed = torch.empty(B, heads, S, S, device=DEV)
+    padded = torch.full((B, heads, S, 72), -7.0, device=DEV)
+    call("vit3d_attn_fwd", ptr(qkv), ptr(ctx0), ptr(packed), B, S, heads, D, PREC["bf16"], stream())
+    call("vit3d_attn_fwd_padded", ptr(qkv), ptr(ctx1), ptr(padded), 72, B, S, heads, D, stream())
+    assert torch.equal(padded[..., :S], packed)
+    assert torch.equal(ctx0, ctx1)
+    assert bool((padded[..., S:] == -7.0).all())
+    assert abs(float(padded[..., :S].sum(-1).mean()) - 1.0) < 1e-5
