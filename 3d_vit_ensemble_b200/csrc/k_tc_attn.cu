@@ -224,13 +224,13 @@ attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
         }
         float* p0 = probs + ((size_t)(b * HEADS + h) * AT_S + row0) * pld + 2 * t;
         float* p1 = p0 + 8 * (size_t)pld;
+        // n-tile 8 = column 64 and the 7 padding floats (zeros): EVERY sector of a row is written completely - a row
+        // whose last sector carried 4 valid bytes made the L2 read-modify-write it (measured slower than the packed rows)
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < 9; ++nt) {
           st_global_f2_if(w0, p0 + nt * 8, s[nt][0], s[nt][1]);
           st_global_f2_if(w1, p1 + nt * 8, s[nt][2], s[nt][3]);
         }
-        st_global_f1_if(tail && w0, p0 + 64, s[8][0]);
-        st_global_f1_if(tail && w1, p1 + 64, s[8][2]);
       }
       if constexpr (VIS == 1) {
         // The probabilities leave from the accumulator registers, normalised in place (the P V product below
@@ -350,8 +350,8 @@ static int attn_threads(int D, bool vis) {
 int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int probs_ld, int B, int S, int heads, int D, cudaStream_t st) {
   if (!tc_attn_supported(S, heads, D)) V3_UNSUPPORTED("tc attention: unsupported shape S=%d heads=%d D=%d", S, heads, D);
   if (B <= 0) return VIT3D_OK;
-  if (probs && probs_ld != S && (probs_ld < S || probs_ld % 8 || (reinterpret_cast<uintptr_t>(probs) & 31))) {
-    set_error("tc attention: padded probability rows need probs_ld %% 8 == 0, probs_ld >= S and a 32-byte aligned buffer");
+  if (probs && probs_ld != S && (probs_ld != 72 || (reinterpret_cast<uintptr_t>(probs) & 31))) {
+    set_error("tc attention: padded probability rows are 72 floats (9 whole sectors) in a 32-byte aligned buffer");
     return VIT3D_ERR_INVALID;
   }
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(ctx) & 15) ||

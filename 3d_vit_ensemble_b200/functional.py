@@ -477,11 +477,10 @@ class AttnCoreFn(torch.autograd.Function):
         qkv = _c(qkv.to(ad))
         out = torch.empty(B, S, A, device=qkv.device, dtype=ad)
         probs = None
-        pld = int(_STATE.get("probs_row_pad", 8))
-        if vis and prec == "bf16" and pld > 1 and _lib.lib().vit3d_attn_padded_supported(S, heads, D):
-            # rows padded to a multiple of 8 floats (72 for S = 65): sector-aligned stores; callers get the [..., :S] view -
+        if vis and prec == "bf16" and _STATE.get("probs_padded", True) and _lib.lib().vit3d_attn_padded_supported(S, heads, D):
+            # rows padded to 72 floats (9 whole 32-byte sectors): sector-aligned stores; callers get the [..., :S] view -
             # the shape and values of the reference's attention_probs (modeling.py:89-90), not contiguous
-            ld = (S + pld - 1) // pld * pld
+            ld = 72
             store = torch.empty(B, heads, S, ld, device=qkv.device)
             call("vit3d_attn_fwd_padded", ptr(qkv), ptr(out), ptr(store), ld, B, S, heads, D, stream())
             probs = store[..., :S]

@@ -169,8 +169,8 @@ int vit3d_mlp_lnf_fwd(const void* xn, const void* w1_lp, const float* b1, const 
  * ctx [M, k*D] "act"; probs (optional, vis=True) fp32 [B,k,S,S]. */
 int vit3d_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int heads, int D, int prec,
                    vit3d_stream_t stream);
-/* Same in BF16 mode with PADDED probability rows: probs is [B,k,S,probs_ld] with probs_ld % 8 == 0 (72 for S = 65) and a
- * 32-byte aligned base; only the first S floats of a row are written.  Every row then starts on a 32-byte sector and the
+/* Same in BF16 mode with PADDED probability rows: probs is [B,k,S,probs_ld] with probs_ld = 72 (S = 65) and a 32-byte
+ * aligned base; the 7 padding floats of a row are written as zeros (whole sectors only).  Every row then starts on a 32-byte sector and the
  * column pairs a lane stores never straddle one (the packed rows of 65 floats start at 4-byte phases: 1.58x write
  * amplification between L1 and L2).  The Python surface hands out `probs[..., :S]` - same shape and values as the
  * reference's attention_probs tensor, non-contiguous. */
