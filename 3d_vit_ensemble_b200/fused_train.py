@@ -131,6 +131,11 @@ class TrainPlan:
         self.jobs_dev = host.to(self.device)
         self._ptrs = tuple(s.data_ptr() for s in self._job_src)
 
+    def side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def signature(self):
         return (tuple(s._version for s in self._job_src), F._STATE.get("epoch", 0))
 
@@ -209,6 +214,7 @@ def forward(model, x, labels, pos_weight, step: Optional[int] = None):
     bits0 = None
     bits1 = [None] * L
     bits2 = [None] * L
+    bits_ready = []          # per Block: event after which its two masks exist (side stream)
     scale = 1.0
     if training:
         scale = 1.0 / (1.0 - p)
@@ -226,8 +232,25 @@ def forward(model, x, labels, pos_weight, step: Optional[int] = None):
             if step is None:
                 step = F.next_dropout_step()
             seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
-            call("vit3d_dropout_bits", ptr(allbits), len(nel), (C.c_uint * len(nel))(*sites),
-                 (C.c_longlong * len(nel))(*nel), p, seed, step, ptr(step_dev), st)
+            # the embedding mask is needed at once; the masks of Block l (2 sites, M*(d+H) decisions: ALU-bound Philox,
+            # 30 registers, no shared memory) are drawn on a SIDE stream, one launch per Block, and co-reside with the
+            # forward's GEMM CTAs (one per SM, half of the issue slots idle) - the main stream waits for Block l's
+            # event just before fc1 of Block l.  Inside a CUDA graph these become a parallel branch.
+            call("vit3d_dropout_bits", ptr(allbits), 1, (C.c_uint * 1)(0), (C.c_longlong * 1)(nel[0]), p, seed, step,
+                 ptr(step_dev), st)
+            main = torch.cuda.current_stream(dev)
+            side = plan.side_stream()
+            side.wait_stream(main)
+            allbits.record_stream(side)
+            with torch.cuda.stream(side):
+                sst = stream()
+                for l in range(L):
+                    base = allbits[int(offs[1 + 2 * l]):]
+                    call("vit3d_dropout_bits", ptr(base), 2, (C.c_uint * 2)(1 + 2 * l, 2 + 2 * l),
+                         (C.c_longlong * 2)(nel[1 + 2 * l], nel[2 + 2 * l]), p, seed, step, ptr(step_dev), sst)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    bits_ready.append(ev)
         seg = [allbits[int(o0):int(o1)] for o0, o1 in zip(offs[:-1], offs[1:])]
         bits0 = seg[0]
         bits1 = seg[1::2]
@@ -266,6 +289,8 @@ def forward(model, x, labels, pos_weight, step: Optional[int] = None):
         call("vit3d_linear_res_train_fwd", ptr(ctx), ptr(sh["wo"]), ptr(a.out.bias), ptr(x0), ptr(x1), None, 1.0,
              ptr(blk.ffn_norm.weight), ptr(blk.ffn_norm.bias), float(blk.ffn_norm.eps), ptr(xn2), ptr(mean2), ptr(rstd2),
              M, H, H, st)
+        if bits_ready:
+            torch.cuda.current_stream(dev).wait_event(bits_ready[i])
         dact = torch.empty(M, d, device=dev, dtype=bf)       # gelu'(pre) * keep / (1-p): all the backward needs of fc1's output
         act = torch.empty(M, d, device=dev, dtype=bf)
         call("vit3d_fc1_train_fwd", ptr(xn2), ptr(sh["w1"]), ptr(f.fc1.bias), ptr(dact), ptr(act), ptr(bits1[i]), scale,
