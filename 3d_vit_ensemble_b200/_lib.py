@@ -97,6 +97,9 @@ SIGNATURES = {
     "vit3d_fc1_train_fwd": (_i, [_p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _p]),
     "vit3d_linear_res_train_fwd": (_i, [_p, _p, _p, _p, _p, _p, _f, _p, _p, _f, _p, _p, _p, _i, _i, _i, _p]),
     "vit3d_wgrad": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "vit3d_wgrad_ws_bytes": (_sz, [_i, _i, _i]),
+    "vit3d_wgrad_partial": (_i, [_p, _p, _p, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), _p]),
+    "vit3d_wgrad_reduce": (_i, [_p, _i, _p]),
     "vit3d_attn_bwd_bias": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
 }
 

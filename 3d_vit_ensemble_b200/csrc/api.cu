@@ -525,6 +525,22 @@ int vit3d_wgrad(const void* dy, const void* x, float* dw0, float* dw1, float* dw
   if (!tc_wgrad_supported(VIT3D_PREC_BF16, M, N, K)) V3_UNSUPPORTED("wgrad: unsupported shape M=%d N=%d K=%d", M, N, K);
   return tc_gemm_wgrad_seg(dy, x, dw0, dw1, dw2, seg_rows, N, K, M, as_stream(stream));
 }
+size_t vit3d_wgrad_ws_bytes(int M, int N, int K) {
+  int bn, splits, tiles;
+  tc_wgrad_plan(N, K, M, &bn, &splits, &tiles);
+  return (size_t)tiles * splits * 128 * bn * sizeof(float);
+}
+int vit3d_wgrad_partial(const void* dy, const void* x, float* ws, int M, int N, int K, int* bn, int* splits,
+                        vit3d_stream_t stream) {
+  V3_REQUIRE(dy && x && ws && M > 0 && N > 0 && K > 0, "wgrad_partial: bad argument");
+  if (!tc_wgrad_supported(VIT3D_PREC_BF16, M, N, K) || N % 128) V3_UNSUPPORTED("wgrad_partial: unsupported shape M=%d N=%d K=%d", M, N, K);
+  tc_wgrad_plan(N, K, M, bn, splits, nullptr);
+  return tc_gemm_wgrad_partial(dy, x, ws, N, K, M, as_stream(stream));
+}
+int vit3d_wgrad_reduce(const void* host_jobs, int njobs, vit3d_stream_t stream) {
+  V3_REQUIRE(host_jobs && njobs >= 0 && njobs <= VIT3D_MAX_WGRAD_JOBS, "wgrad_reduce: bad argument");
+  return launch_wgrad_reduce(host_jobs, njobs, as_stream(stream));
+}
 int vit3d_attn_bwd_bias(const void* dctx, const void* qkv, void* dqkv, float* db_q, float* db_k, float* db_v, int B, int S,
                         int heads, int D, vit3d_stream_t stream) {
   V3_REQUIRE(dctx && qkv && dqkv && db_q && db_k && db_v, "attn_bwd_bias: null pointer");

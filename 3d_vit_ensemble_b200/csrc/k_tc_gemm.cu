@@ -289,7 +289,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     smem_u32(bias_stage) + BN * 4 + part * CW * 2, lane, m_base, n_base, drop_row,
                                     ep.drop_scale, mw_default);
       } else {
-        epilogue_rows<CW, !TF32>(ep, &tmC, &tmPre, taddr, stage, lane, m_base, n_base, M, N);
+        if (ep.partial_ws != nullptr) {
+          TcEpilogue pe = ep;                       // this work item's dense partial tile
+          pe.out = ep.partial_ws + (size_t)ti.w * (TC_BLOCK_M * BN);
+          pe.atomic = 0;
+          pe.seg_rows = 0;
+          epilogue_rows<CW, !TF32>(pe, &tmC, &tmPre, taddr, stage, lane, q * 32, part * CW, TC_BLOCK_M, BN);
+        } else {
+          epilogue_rows<CW, !TF32>(ep, &tmC, &tmPre, taddr, stage, lane, m_base, n_base, M, N);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -454,6 +462,43 @@ int tc_gemm_wgrad(const void* A, const void* B, float* out, int Mo, int No, int 
 }
 
 // same, output rows [i*seg_rows, (i+1)*seg_rows) accumulated into out0 / out1 / out2 (seg_rows % 128 == 0; 0 = one buffer)
+// the tile width / split count tc_gemm_wgrad_seg uses for a product (also sizes the partial-tile workspace)
+void tc_wgrad_plan(int Mo, int No, int Kred, int* bn_out, int* splits_out, int* tiles_out) {
+  const int sms = sm_count();
+  int bn = 256;
+  if (No % 256) bn = 128;
+  if (No % 128) bn = 64;
+  const int tiles = ceil_div(Mo, TC_BLOCK_M) * ceil_div(No, bn);
+  const int nkb = ceil_div(Kred, 64);
+  int splits = sms / tiles;
+  if (splits > nkb) splits = nkb;
+  if (splits < 1) splits = 1;
+  for (;;) {
+    const int kp = ceil_div(nkb, splits), s2 = ceil_div(nkb, kp);
+    if (s2 == splits) break;
+    splits = s2;
+  }
+  if (bn_out) *bn_out = bn;
+  if (splits_out) *splits_out = splits;
+  if (tiles_out) *tiles_out = tiles;
+}
+
+// partial-tile variant: every work item stores its tile to `ws` (tiles * splits * 128 * bn floats), no atomics
+int tc_gemm_wgrad_partial(const void* A, const void* B, float* ws, int Mo, int No, int Kred, cudaStream_t st) {
+  int bn, splits, tiles;
+  tc_wgrad_plan(Mo, No, Kred, &bn, &splits, &tiles);
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d(&ta, A, 2, Kred, Mo, Mo, 64, 64, 128);
+  if (rc != VIT3D_OK) return rc;
+  rc = make_tmap_2d(&tb, B, 2, Kred, No, No, 64, 64, 128);
+  if (rc != VIT3D_OK) return rc;
+  TcEpilogue ep;
+  ep.out = ws; ep.out_f32 = 1; ep.partial_ws = ws;
+  if (bn == 256) return launch_tc<false, 256>(ta, tb, ta, ta, ep, Mo, No, Kred, splits, false, st, 0, 1);
+  if (bn == 128) return launch_tc<false, 128>(ta, tb, ta, ta, ep, Mo, No, Kred, splits, false, st, 0, 1);
+  return launch_tc<false, 64>(ta, tb, ta, ta, ep, Mo, No, Kred, splits, false, st, 0, 1);
+}
+
 int tc_gemm_wgrad_seg(const void* A, const void* B, float* out, float* out1, float* out2, int seg_rows, int Mo, int No,
                       int Kred, cudaStream_t st) {
   const int sms = sm_count();

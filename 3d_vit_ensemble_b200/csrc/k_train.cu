@@ -339,6 +339,77 @@ int launch_head_bwd(const float* dlogit, const float* enc, const float* w, float
   return VIT3D_OK;
 }
 
+// ============================================================================ weight-gradient partial tiles -> gradients
+// One launch per training step: for every weight-gradient GEMM of the step, sum the split-K slices of each output tile
+// (vit3d_wgrad_partial stored them densely, slice-minor) and ADD the sum to the parameter gradient(s).
+struct WgradJob {
+  const float* ws;       // [tiles][splits][128][bn]
+  float* dst[3];         // rows [i*seg_rows, (i+1)*seg_rows) of the product go to dst[i] (seg_rows = 0: all to dst[0])
+  int seg_rows, rows, cols, bn, splits, tiles_n;
+  int block0;            // first block of this job in the launch
+  int pad;
+};
+static_assert(sizeof(WgradJob) == VIT3D_WGRAD_JOB_BYTES, "WgradJob layout is part of the C ABI");
+struct WgradJobs {
+  int n;
+  int pad;
+  WgradJob j[VIT3D_MAX_WGRAD_JOBS];
+};
+
+constexpr int WR_F4_PER_BLOCK = 1024;     // float4 per block: 256 threads x 4
+
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ WgradJobs jobs) {
+  int k = 0;
+  while (k + 1 < jobs.n && (int)blockIdx.x >= jobs.j[k + 1].block0) ++k;
+  const WgradJob& jb = jobs.j[k];
+  const int tile_f4 = 128 * jb.bn / 4;
+  const long long total = (long long)(jb.rows / 128) * jb.tiles_n * tile_f4;       // float4 of the whole output
+  const long long base = (long long)((int)blockIdx.x - jb.block0) * WR_F4_PER_BLOCK;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const long long e = base + u * 256 + threadIdx.x;
+    if (e >= total) break;
+    const int tile = (int)(e / tile_f4), r = (int)(e % tile_f4);
+    const float4* src = reinterpret_cast<const float4*>(jb.ws) + ((long long)tile * jb.splits) * tile_f4 + r;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < jb.splits; ++s) {
+      const float4 v = __ldg(src + (long long)s * tile_f4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const int tm = tile / jb.tiles_n, tn = tile % jb.tiles_n;
+    const int row = tm * 128 + (r * 4) / jb.bn, col = tn * jb.bn + (r * 4) % jb.bn;
+    float* d = jb.dst[0];
+    int lrow = row;
+    if (jb.seg_rows > 0) {
+      const int seg = row / jb.seg_rows;
+      d = jb.dst[seg];
+      lrow = row - seg * jb.seg_rows;
+    }
+    float4* o = reinterpret_cast<float4*>(d + (long long)lrow * jb.cols + col);
+    float4 cur = *o;
+    cur.x += acc.x; cur.y += acc.y; cur.z += acc.z; cur.w += acc.w;
+    *o = cur;
+  }
+}
+
+int launch_wgrad_reduce(const void* host_jobs, int njobs, cudaStream_t st) {
+  if (njobs <= 0) return VIT3D_OK;
+  WgradJobs jobs;
+  memset(&jobs, 0, sizeof(jobs));
+  jobs.n = njobs;
+  memcpy(jobs.j, host_jobs, sizeof(WgradJob) * njobs);
+  int blocks = 0;
+  for (int i = 0; i < njobs; ++i) {
+    WgradJob& j = jobs.j[i];
+    j.block0 = blocks;
+    const long long total = (long long)(j.rows / 128) * j.tiles_n * (128 * j.bn / 4);
+    blocks += (int)((total + WR_F4_PER_BLOCK - 1) / WR_F4_PER_BLOCK);
+  }
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(jobs);
+  V3_LAUNCH_CHECK();
+  return VIT3D_OK;
+}
+
 // ============================================================================ weight shadows
 // kinds: 0 bf16 copy, 1 bf16 transposed copy, 2 fp16 copy, 3 fp32 copy rounded to TF32, 4 fp32 copy
 struct ShadowJob {

@@ -75,6 +75,7 @@ int launch_ln256_bwd(const float* dy, const float* x, const float* mean, const f
 int launch_mul_colsum_bwd(const void* da, const void* dact, void* dh, float* db, int M, int d, cudaStream_t st);
 int launch_head_bwd(const float* dlogit, const float* enc, const float* w, float* denc, float* dw, float* db, int B, int S,
                     cudaStream_t st);
+int launch_wgrad_reduce(const void* host_jobs, int njobs, cudaStream_t st);
 int launch_refresh_shadows(const void* jobs, int njobs, int total_tiles, unsigned* step_dev, cudaStream_t st);
 
 }  // namespace vit3d

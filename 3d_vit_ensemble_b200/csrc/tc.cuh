@@ -38,6 +38,8 @@ int tc_linear_fwd(const TcLinear& t, cudaStream_t st);
 // dW[N,K] += dY[M,N]^T X[M,K]  (bf16 operands, fp32 atomics)
 bool tc_wgrad_supported(int prec, int M, int N, int K);
 int tc_gemm_wgrad(const void* dy, const void* x, float* dw, int N, int K, int M, cudaStream_t st);
+void tc_wgrad_plan(int N, int K, int M, int* bn, int* splits, int* tiles);
+int tc_gemm_wgrad_partial(const void* dy, const void* x, float* ws, int N, int K, int M, cudaStream_t st);
 int tc_gemm_wgrad_seg(const void* dy, const void* x, float* dw0, float* dw1, float* dw2, int seg_rows, int N, int K, int M,
                       cudaStream_t st);
 

@@ -36,6 +36,10 @@ struct TcEpilogue {
   // go to out / out_seg[0] / out_seg[1] (the packed q|k|v weight gradient lands in three parameters' .grad)
   float* out_seg[2] = {nullptr, nullptr};
   int seg_rows = 0;
+  // split-K weight gradients WITHOUT atomics: work item w stores its 128 x BN fp32 tile densely at partial_ws + w*128*BN
+  // (plain 16-byte stores); vit3d_wgrad_reduce sums the slices of a tile afterwards.  (Measured: not faster than the
+  // atomics for the training step - the extra HBM traffic outweighs them; kept as an option.)
+  float* partial_ws = nullptr;
 };
 
 

@@ -14,7 +14,8 @@ What the per-operator path (functional.py) pays and this one does not:
   * q, k, v as one packed projection without torch.cat: packed shadows, and the packed weight gradient lands in
     the three parameters' gradients directly (vit3d_wgrad with row segments).
 
-Per encoder Block: 5 launches forward, 10 backward.  Reference line numbers: models/modeling.py.
+Per encoder Block: 5 launches forward (+1 mask launch on a side stream), 10 backward; one launch per step sums the
+weight-gradient partial tiles.  Reference line numbers: models/modeling.py.
 """
 from __future__ import annotations
 
@@ -32,6 +33,52 @@ _BF16 = PREC["bf16"]
 _JOB_DTYPE = np.dtype([("src", "<u8"), ("dst", "<u8"), ("rows", "<i4"), ("cols", "<i4"), ("ld", "<i4"), ("kind", "<i4"),
                        ("tile0", "<i4"), ("tiles_c", "<i4")])
 K_BF16, K_BF16_T, K_F16, K_TF32, K_F32 = 0, 1, 2, 3, 4
+
+
+class _WgradJob(C.Structure):
+    """include/vit3d.h: record of vit3d_wgrad_reduce (VIT3D_WGRAD_JOB_BYTES = 64)."""
+    _fields_ = [("ws", C.c_void_p), ("dst", C.c_void_p * 3), ("seg_rows", C.c_int), ("rows", C.c_int), ("cols", C.c_int),
+                ("bn", C.c_int), ("splits", C.c_int), ("tiles_n", C.c_int), ("block0", C.c_int), ("pad", C.c_int)]
+
+
+class _Wgrads:
+    """The weight-gradient GEMMs of one backward pass.  Default: split-K work items accumulate into the gradients with
+    fp32 vector atomics.  `functional._STATE["wgrad_partial"] = True`: every work item stores its partial tile into one
+    workspace (plain stores) and ONE reduce launch at the end adds them to the gradients - built on the estimate
+    that the atomics of 148 partial tiles cost ~20 us per GEMM; MEASURED slower (conf 18, batch 256: 4.52 ms per step
+    against 4.28 ms): the 1.2 GB of extra HBM traffic costs more than the atomics, which the L2 absorbs."""
+
+    def __init__(self, M, shapes, dev):
+        self.M = M
+        self.partial = F._STATE.get("wgrad_partial", False) and all(N % 128 == 0 for N, _ in shapes)
+        self.jobs = (_WgradJob * max(1, len(shapes)))()
+        self.n = 0
+        self.off = 0
+        self.ws = None
+        if self.partial:
+            L = _lib.lib()
+            total = sum(L.vit3d_wgrad_ws_bytes(M, N, K) for N, K in shapes)
+            self.ws = torch.empty(total // 4, device=dev, dtype=torch.float32)
+
+    def __call__(self, dy, x, dsts, seg_rows, N, K, st):
+        if not self.partial:
+            d = list(dsts) + [None] * (3 - len(dsts))
+            call("vit3d_wgrad", ptr(dy), ptr(x), d[0], d[1], d[2], seg_rows, self.M, N, K, st)
+            return
+        bn, sp = C.c_int(0), C.c_int(0)
+        wp = self.ws.data_ptr() + self.off
+        call("vit3d_wgrad_partial", ptr(dy), ptr(x), wp, self.M, N, K, C.byref(bn), C.byref(sp), st)
+        j = self.jobs[self.n]
+        j.ws = wp
+        for i in range(3):
+            j.dst[i] = dsts[i] if i < len(dsts) else None
+        j.seg_rows, j.rows, j.cols, j.bn, j.splits, j.tiles_n = seg_rows, N, K, bn.value, sp.value, K // bn.value
+        self.n += 1
+        self.off += _lib.lib().vit3d_wgrad_ws_bytes(self.M, N, K)
+
+    def finish(self, st):
+        if self.partial and self.n:
+            call("vit3d_wgrad_reduce", C.cast(self.jobs, C.c_void_p), self.n, st)
 
 
 def supported(model, x) -> bool:
@@ -373,6 +420,7 @@ def backward(model, saved, dloss: Optional[torch.Tensor] = None):
     dqkv = torch.empty(M, 3 * H, device=dev, dtype=bf)
     dxn = denc                                            # fp32 [M,H] scratch for the dgrad outputs
     fused_mlp = F._STATE.get("fused_mlp_bwd", True) and bool(_lib.lib().vit3d_mlp_bwd_supported(M, H, d))
+    wg = _Wgrads(M, [s_ for _ in range(L) for s_ in ((H, d), (d, H), (H, H), (3 * H, H))], dev)
     last = enc.layer[L - 1]
     call("vit3d_ln256_bwd", ptr(denc), ptr(saved["x_last"]), ptr(saved["mean_f"]), ptr(saved["rstd_f"]), ptr(en.weight), None,
          ptr(bits2[L - 1]), scale, 0, ptr(g), ptr(gb), G(en.weight), G(en.bias), G(last.ffn.fc2.bias), M, st)
@@ -384,29 +432,29 @@ def backward(model, saved, dloss: Optional[torch.Tensor] = None):
         sh = plan.layers[i]
         r = saved["layers"][i]
         # ---- Mlp backward (modeling.py:118-124): fc2, Dropout + GELU, fc1
-        call("vit3d_wgrad", ptr(gb), ptr(r["act"]), G(f.fc2.weight), None, None, 0, M, H, d, st)
+        wg(gb, r["act"], [G(f.fc2.weight)], 0, H, d, st)
         if fused_mlp:
             # dgrad(fc2) -> GELU' x mask -> dgrad(fc1) in one kernel: `da` stays on chip, dh is written once
             call("vit3d_mlp_bwd", ptr(gb), ptr(sh["w2_t"]), ptr(sh["w1_t"]), ptr(r["dact"]), ptr(dwide), ptr(dxn),
                  G(f.fc1.bias), M, H, d, st)
-            call("vit3d_wgrad", ptr(dwide), ptr(r["xn2"]), G(f.fc1.weight), None, None, 0, M, d, H, st)
+            wg(dwide, r["xn2"], [G(f.fc1.weight)], 0, d, H, st)
         else:
             call("vit3d_linear_fwd", ptr(gb), H, 0, ptr(sh["w2_t"]), ptr(sh["w2_t"]), None, None, ptr(dwide), 0, None, 0, M, d,
                  H, _BF16, st)
             call("vit3d_mul_colsum_bwd", ptr(dwide), ptr(r["dact"]), ptr(dwide), G(f.fc1.bias), M, d, st)
-            call("vit3d_wgrad", ptr(dwide), ptr(r["xn2"]), G(f.fc1.weight), None, None, 0, M, d, H, st)
+            wg(dwide, r["xn2"], [G(f.fc1.weight)], 0, d, H, st)
             call("vit3d_linear_fwd", ptr(dwide), d, 0, ptr(sh["w1_t"]), ptr(sh["w1_t"]), None, None, ptr(dxn), 1, None, 0, M, H,
                  d, _BF16, st)
         # ---- ffn_norm backward + skip gradient; bf16 copy and column sums for the out-projection
         call("vit3d_ln256_bwd", ptr(dxn), ptr(r["x1"]), ptr(r["mean2"]), ptr(r["rstd2"]), ptr(blk.ffn_norm.weight), ptr(g),
              None, 1.0, 0, ptr(g1), ptr(g1b), G(blk.ffn_norm.weight), G(blk.ffn_norm.bias), G(a.out.bias), M, st)
         # ---- Attention backward (modeling.py:78-99)
-        call("vit3d_wgrad", ptr(g1b), ptr(r["ctx"]), G(a.out.weight), None, None, 0, M, H, H, st)
+        wg(g1b, r["ctx"], [G(a.out.weight)], 0, H, H, st)
         call("vit3d_linear_fwd", ptr(g1b), H, 0, ptr(sh["wo_t"]), ptr(sh["wo_t"]), None, None, ptr(dctx), 0, None, 0, M, H, H,
              _BF16, st)
         call("vit3d_attn_bwd_bias", ptr(dctx), ptr(r["qkv"]), ptr(dqkv), G(a.query.bias), G(a.key.bias), G(a.value.bias),
              B, S, heads, D, st)
-        call("vit3d_wgrad", ptr(dqkv), ptr(r["xn1"]), G(a.query.weight), G(a.key.weight), G(a.value.weight), H, M, 3 * H, H, st)
+        wg(dqkv, r["xn1"], [G(a.query.weight), G(a.key.weight), G(a.value.weight)], H, 3 * H, H, st)
         call("vit3d_linear_fwd", ptr(dqkv), 3 * H, 0, ptr(sh["wqkv_t"]), ptr(sh["wqkv_t"]), None, None, ptr(dxn), 1, None, 0,
              M, H, 3 * H, _BF16, st)
         # ---- attention_norm backward + skip gradient; below it: the previous Block's fc2 Dropout, or the embedding Dropout
@@ -418,8 +466,14 @@ def backward(model, saved, dloss: Optional[torch.Tensor] = None):
         else:
             call("vit3d_ln256_bwd", ptr(dxn), ptr(r["x0"]), ptr(r["mean1"]), ptr(r["rstd1"]), ptr(an.weight), ptr(g1),
                  ptr(bits0), scale, 1, ptr(g), None, G(an.weight), G(an.bias), None, M, st)
-        for p_ in blk.parameters():
-            F._grad_done(p_)
+        if not wg.partial:
+            for p_ in blk.parameters():
+                F._grad_done(p_)
+    wg.finish(st)                      # one launch: partial tiles of all 4 L weight-gradient GEMMs -> the gradients
+    if wg.partial:
+        for blk in reversed(list(enc.layer)):
+            for p_ in blk.parameters():
+                F._grad_done(p_)
     # ---- Embeddings backward (modeling.py:162-174): g = dL/d(tokens) with the embedding Dropout already undone
     x = saved["x"]
     w = emb.patch_embeddings.weight

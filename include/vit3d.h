@@ -322,6 +322,19 @@ int vit3d_linear_res_train_fwd(const void* x, const void* w_lp, const float* bia
  * product accumulate into dw0 / dw1 / dw2 (the packed q|k|v projection: three parameters). */
 int vit3d_wgrad(const void* dy, const void* x, float* dw0, float* dw1, float* dw2, int seg_rows, int M, int N, int K,
                 vit3d_stream_t stream);
+/* The same product WITHOUT atomics, in two steps.  vit3d_wgrad_partial: every (output tile, reduction slice) work item
+ * stores its 128 x bn fp32 tile densely into `ws` (vit3d_wgrad_ws_bytes(M, N, K) bytes; tile-major, slice-minor) and
+ * reports the tile width / slice count it used.  vit3d_wgrad_reduce: ONE launch for all weight-gradient GEMMs of a
+ * training step sums the slices of every tile and ADDS the result to the gradient buffers.  `host_jobs` is a HOST
+ * array of njobs (<= VIT3D_MAX_WGRAD_JOBS) records of VIT3D_WGRAD_JOB_BYTES bytes:
+ *   { const float* ws; float* dst[3]; int seg_rows, rows (= N), cols (= K), bn, splits, tiles_n (= K / bn), block0, pad; }
+ * (block0 is filled in by the library).  N % 128 == 0. */
+#define VIT3D_MAX_WGRAD_JOBS 48
+#define VIT3D_WGRAD_JOB_BYTES 64
+size_t vit3d_wgrad_ws_bytes(int M, int N, int K);
+int vit3d_wgrad_partial(const void* dy, const void* x, float* ws, int M, int N, int K, int* bn, int* splits,
+                        vit3d_stream_t stream);
+int vit3d_wgrad_reduce(const void* host_jobs, int njobs, vit3d_stream_t stream);
 /* vit3d_attn_bwd (BF16 mode) that also accumulates the q / k / v bias gradients (column sums of dqkv) */
 int vit3d_attn_bwd_bias(const void* dctx, const void* qkv, void* dqkv, float* db_q, float* db_k, float* db_v, int B, int S,
                         int heads, int D, vit3d_stream_t stream);
