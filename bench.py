@@ -620,7 +620,7 @@ def _time_launches(fn, iters=10, warm=3):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures under profiles/
 # (valid only for the captured shape: conf 5, batch 1024, bf16; None otherwise)
-NCU_TRAFFIC = {"mlp_ln": (162.7e6, "profiles/r01_fused_mlp_ln_ncu_full_raw.csv"),
+NCU_TRAFFIC = {"mlp_ln": (162.2e6, "profiles/r02_fused_mlp_fwd_ncu_full_raw.csv"),
                "fc1_gelu": (257.2e6, "profiles/r01_per_kernel_probe_conf5_b1024.log")}
 
 
