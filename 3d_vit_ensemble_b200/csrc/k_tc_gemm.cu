@@ -102,8 +102,9 @@ template <int BN, bool WIDE> struct TcLayout {
 template <bool TF32, int BN, int EPI = EPI_GENERIC, bool WIDE = false>
 __global__ void __launch_bounds__(tc_threads(BN), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmPre, TcEpilogue ep, int M,
-               int N, int K, int tiles_m, int tiles_n, int splits, int stationary, int patch_blocks, int mn_major) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmPre,
+               const __grid_constant__ CUtensorMap tmX, TcEpilogue ep, int M, int N, int K, int tiles_m, int tiles_n,
+               int splits, int stationary, int patch_blocks, int mn_major) {
   using Cfg = TcCfg<BN>;
   using Lay = TcLayout<BN, WIDE>;
   constexpr int BLOCK_K = TF32 ? 32 : 64;   // 128 bytes of K per stage row
@@ -122,8 +123,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAXST + 5);
 
   const bool stat = stationary != 0;
-  const int STAGES = stat ? Lay::STAT_STAGES : Lay::STREAM_STAGES;
-  const int stage_bytes = stat ? Cfg::A_BYTES : Cfg::STAGE_BYTES;
+  const bool tall = mn_major == 2;      // 256 x BN weight-gradient tile: A stage doubles, both TMEM buffers form ONE accumulator
+  const int STAGES = stat ? Lay::STAT_STAGES : (tall ? Lay::OPER_BYTES / (Cfg::STAGE_BYTES + Cfg::A_BYTES) : Lay::STREAM_STAGES);
+  const int stage_bytes = stat ? Cfg::A_BYTES : (tall ? Cfg::STAGE_BYTES + Cfg::A_BYTES : Cfg::STAGE_BYTES);
   uint8_t* ring = stat ? smem + TC_SLAB_BYTES : smem;
 
   // warp index through a shuffle: warp-uniform for the compiler, so the role branches are uniform control flow
@@ -183,12 +185,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else if (mn_major) {
             // both operands MN-major (weight gradients: dW = dY^T X reduces over the token rows): a stage
             // holds 64 reduction rows; each 64-column block is one {64 cols x 64 rows} box = 8 KB
-#pragma unroll
-            for (int j = 0; j < TC_BLOCK_M / 64; ++j)
-              tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], ti.tm * TC_BLOCK_M + 64 * j, kb * 64);
+            // (mn_major == 2: the tile spans 256 output rows = two accumulators sharing the B operand)
+            const int a_blocks = mn_major == 2 ? 2 * TC_BLOCK_M / 64 : TC_BLOCK_M / 64;
+            for (int j = 0; j < a_blocks; ++j)
+              tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], ti.tm * (a_blocks * 64) + 64 * j, kb * 64);
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sa + Cfg::A_BYTES + j * 8192, &tmB, &full_bar[stage], ti.tn * BN + 64 * j, kb * 64);
+              tma_load_2d(sa + a_blocks * 8192 + j * 8192, &tmB, &full_bar[stage], ti.tn * BN + 64 * j, kb * 64);
           } else {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, ti.tm * TC_BLOCK_M);
             if (!stat) tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, ti.tn * BN);
@@ -224,8 +227,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       bool slab_ready = !stat;
       for (; ti.next(); ++it) {
         const int kb0 = ti.split * kb_per, kb1 = min(nkb, kb0 + kb_per);
-        const int buf = it & 1;
-        mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+        const int buf = tall ? 0 : (it & 1);
+        mbar_wait(&tmem_empty[buf], (tall ? (it & 1) : ((it >> 1) & 1)) ^ 1);
         if (!slab_ready) { mbar_wait(slab_full, 0); slab_ready = true; }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
@@ -234,10 +237,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           const uint64_t ad = ring_desc + (uint64_t)((stage * stage_bytes) >> 4);
-          const uint64_t bd = stat ? slab_desc + (uint64_t)((kb * Cfg::B_BYTES) >> 4) : ad + (uint64_t)(Cfg::A_BYTES >> 4);
+          const uint64_t bd = stat ? slab_desc + (uint64_t)((kb * Cfg::B_BYTES) >> 4)
+                                   : ad + (uint64_t)(((tall ? 2 : 1) * Cfg::A_BYTES) >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k)     // 4 x 32 bytes of K per stage
             umma<TF32>(d_tmem, ad + k * kstep, bd + k * kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          if (tall) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // rows 128..255 of the tile: second accumulator, same B k-block
+              umma<TF32>(d_tmem + BN, ad + (uint64_t)(Cfg::A_BYTES >> 4) + k * kstep, bd + k * kstep, idesc,
+                         (kb > kb0 || k > 0) ? 1u : 0u);
+          }
           umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -274,6 +284,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           cur_tn = ti.tn;
         }
       }
+      if (tall) {
+        // weight-gradient tile of 256 rows: accumulator h holds rows [128 h, 128 h + 128)
+        if constexpr (EPI < 0) {
+          mbar_wait(&tmem_full[0], it & 1);
+          tc_fence_after();
+          const int n_base = ti.tn * BN + part * CW;
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * BN + part * CW;
+            const int m_base = ti.tm * (2 * TC_BLOCK_M) + h * TC_BLOCK_M + q * 32;
+            const int seg = ep.seg_rows > 0 ? m_base / ep.seg_rows : 0;
+            const CUtensorMap* tr = seg == 0 ? &tmC : (seg == 1 ? &tmPre : &tmX);
+            epilogue_reduce_f32<CW>(tr, taddr, stage, lane, m_base - seg * ep.seg_rows, n_base, N);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[0]);
+        }
+        continue;
+      }
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + part * CW;
@@ -289,7 +319,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     smem_u32(bias_stage) + BN * 4 + part * CW * 2, lane, m_base, n_base, drop_row,
                                     ep.drop_scale, mw_default);
       } else {
-        if (ep.partial_ws != nullptr) {
+        if (ep.atomic == 2) {
+          // weight gradients: boxes added into the output by the TMA unit; one tensor map per output segment
+          const int seg = ep.seg_rows > 0 ? m_base / ep.seg_rows : 0;
+          const CUtensorMap* tr = seg == 0 ? &tmC : (seg == 1 ? &tmPre : &tmX);
+          epilogue_reduce_f32<CW>(tr, taddr, stage, lane, m_base - seg * ep.seg_rows, n_base, N);
+        } else if (ep.partial_ws != nullptr) {
           TcEpilogue pe = ep;                       // this work item's dense partial tile
           pe.out = ep.partial_ws + (size_t)ti.w * (TC_BLOCK_M * BN);
           pe.atomic = 0;
@@ -365,7 +400,7 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long ro
 template <bool TF32, int BN, int EPI = EPI_GENERIC, bool WIDE = false>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
                      const TcEpilogue& ep, int M, int N, int K, int splits, bool stationary, cudaStream_t st,
-                     int patch_blocks = 0, int mn_major = 0) {
+                     int patch_blocks = 0, int mn_major = 0, const CUtensorMap* tx = nullptr) {
   using Cfg = TcCfg<BN>;
   using Lay = TcLayout<BN, WIDE>;
   auto kern = tc_gemm_kernel<TF32, BN, EPI, WIDE>;
@@ -376,7 +411,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     V3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay::SMEM_BYTES));
     configured_dev = dev;
   }
-  const int tiles_m = ceil_div(M, TC_BLOCK_M), tiles_n = ceil_div(N, BN);
+  const int tiles_m = ceil_div(M, mn_major == 2 ? 2 * TC_BLOCK_M : TC_BLOCK_M), tiles_n = ceil_div(N, BN);
   const int total = tiles_m * tiles_n * splits;
   const int sms = sm_count();
   int grid = total < sms ? total : sms;
@@ -385,7 +420,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     if (cpn > tiles_m) cpn = tiles_m;
     grid = cpn * tiles_n;
   }
-  V3_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), (size_t)Lay::SMEM_BYTES, st, ta, tb, tc, tp, ep, M, N, K, tiles_m,
+  V3_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), (size_t)Lay::SMEM_BYTES, st, ta, tb, tc, tp, tx ? *tx : tp, ep, M, N, K, tiles_m,
                      tiles_n, splits, stationary ? 1 : 0, patch_blocks, mn_major));
   V3_LAUNCH_CHECK();
   return VIT3D_OK;
@@ -505,11 +540,19 @@ int tc_gemm_wgrad_seg(const void* A, const void* B, float* out, float* out1, flo
   int bn = 256;
   if (No % 256) bn = 128;
   if (No % 128) bn = 64;
-  const int tiles = ceil_div(Mo, TC_BLOCK_M) * ceil_div(No, bn);
+  int tiles = ceil_div(Mo, TC_BLOCK_M) * ceil_div(No, bn);
   const int nkb = ceil_div(Kred, 64);
-  // Every work item ends in a 128 x bn tile of fp32 atomics into the SAME few output tiles; the L2 retires about
-  // one fp32 atomic per slice and clock (~0.2 T/s chip-wide), so the atomic volume - work items x tile size -
-  // is what the small products (out-projection: 2 output tiles) pay for.  One work item per SM, not two.
+  // Tall tiles (256 x 256, two accumulators sharing the B k-block): 64 KB of operands per 1024 MMA cycles instead
+  // of 48 KB per 512 - the streamed products are bound by operand delivery (~40 B/clk/SM), so the large products
+  // (fc1 / fc2: 12 tall tiles) take them; small outputs keep 128-row tiles (less reduce volume per work item).
+  const bool red = tuning(VIT3D_TUNE_WGRAD_RED) != 0 && No % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                   (!out1 || (reinterpret_cast<uintptr_t>(out1) & 15) == 0) && (!out2 || (reinterpret_cast<uintptr_t>(out2) & 15) == 0);
+  const int tall_tiles = (Mo / 256) * ceil_div(No, 256);
+  const bool tall = red && tuning(VIT3D_TUNE_WGRAD_RED) == 2 && bn == 256 && Mo % 256 == 0 && (seg_rows == 0 || seg_rows % 256 == 0) &&
+                    tall_tiles >= 8 && tall_tiles <= sms && nkb / (sms / tall_tiles) >= 8;
+  if (tall) tiles = tall_tiles;
+  // Every work item ends in a tile of fp32 adds into the SAME few output tiles, so the reduce volume - work items x
+  // tile size - is what the small products (out-projection: 2 output tiles) pay for.  One work item per SM, not two.
   int splits = sms / tiles;              // floor: 24 tiles x 6 slices = 144 items are one wave, 24 x 7 = 168 would be two
   if (splits > nkb) splits = nkb;
   if (splits < 1) splits = 1;
@@ -534,9 +577,26 @@ int tc_gemm_wgrad_seg(const void* A, const void* B, float* out, float* out1, flo
     }
     ep.seg_rows = seg_rows; ep.out_seg[0] = out1; ep.out_seg[1] = out2;
   }
-  if (bn == 256) return launch_tc<false, 256>(ta, tb, ta, ta, ep, Mo, No, Kred, splits, false, st, 0, 1);
-  if (bn == 128) return launch_tc<false, 128>(ta, tb, ta, ta, ep, Mo, No, Kred, splits, false, st, 0, 1);
-  return launch_tc<false, 64>(ta, tb, ta, ta, ep, Mo, No, Kred, splits, false, st, 0, 1);
+  CUtensorMap tc = ta, tp = ta, tx = ta;
+  if (red) {
+    // partial tiles leave as [32 x 16] fp32 boxes the TMA unit adds into the output (one map per segment)
+    const int rows0 = seg_rows > 0 ? (Mo < seg_rows ? Mo : seg_rows) : Mo;
+    rc = make_tmap_2d(&tc, out, 4, rows0, No, No, 32, 16, 64);
+    if (rc != VIT3D_OK) return rc;
+    if (seg_rows > 0 && Mo > seg_rows) {
+      rc = make_tmap_2d(&tp, out1, 4, Mo - seg_rows < seg_rows ? Mo - seg_rows : seg_rows, No, No, 32, 16, 64);
+      if (rc != VIT3D_OK) return rc;
+    }
+    if (seg_rows > 0 && Mo > 2 * seg_rows) {
+      rc = make_tmap_2d(&tx, out2, 4, Mo - 2 * seg_rows, No, No, 32, 16, 64);
+      if (rc != VIT3D_OK) return rc;
+    }
+    ep.atomic = 2;
+  }
+  if (tall) return launch_tc<false, 256>(ta, tb, tc, tp, ep, Mo, No, Kred, splits, false, st, 0, 2, &tx);
+  if (bn == 256) return launch_tc<false, 256>(ta, tb, tc, tp, ep, Mo, No, Kred, splits, false, st, 0, 1, &tx);
+  if (bn == 128) return launch_tc<false, 128>(ta, tb, tc, tp, ep, Mo, No, Kred, splits, false, st, 0, 1, &tx);
+  return launch_tc<false, 64>(ta, tb, tc, tp, ep, Mo, No, Kred, splits, false, st, 0, 1, &tx);
 }
 
 bool tc_wgrad_supported(int prec, int M, int N, int K) {

@@ -20,7 +20,7 @@ struct TcEpilogue {
   int out_f32 = 1;
   int act = 0;
   int row_group = 0;                // >0: out row = m + m / row_group + 1
-  int atomic = 0;                   // accumulate with fp32 atomics (split-K)
+  int atomic = 0;                   // accumulate (split-K): 1 = fp32 vector atomics, 2 = TMA reduce-add boxes (tmC / tmPre / tmX per segment)
   int vols_per_tile = 0;            // patch-embedding mode: volumes per 128-row tile
   int round_tf32 = 0;               // fp32 output is the operand of a TF32 GEMM: round to nearest tf32
   int l2_ahead = 0;                 // producer: tiles of A to prefetch into L2 ahead of the shared-memory ring
@@ -156,9 +156,43 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem
                "r"(smem_src), "r"(c0), "r"(c1)
                : "memory");
 }
+// fp32 reduce-add of a staged box into global memory, executed by the TMA unit at the L2 (split-K weight gradients:
+// no REDG instructions through the SM's load/store path, which retires ~1 element per clock and SM)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// split-K weight-gradient epilogue: the warp's 32 x CW fp32 slice leaves as [32 x 16] boxes (SWIZZLE_64B staging)
+// that the TMA unit adds into `tm` at (row0, n_base + c); rows / columns past the map's extent are clipped.
+template <int CW>
+__device__ __forceinline__ void epilogue_reduce_f32(const CUtensorMap* tm, uint32_t taddr, uint32_t stage, int lane,
+                                                    int row0, int n_base, int N) {
+  const uint32_t my_row = stage + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll 1
+  for (int c = 0; c < CW; c += 16) {
+    if (n_base + c >= N) break;
+    uint32_t r[16];
+    tmem_ld_32x32b_x16(taddr + c, r);
+    if (lane == 0) bulk_store_wait_read();      // the previous box has left the staging tile
+    __syncwarp();
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st_shared_v4(my_row + ((j ^ sw) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_reduce_add_2d(tm, stage, n_base + c, row0);
+      bulk_store_commit();
+    }
+  }
+}
 
 template <int CW, bool FAST_GELU>
 __device__ __forceinline__ void epilogue_rows(const TcEpilogue& ep, const CUtensorMap* tmC, const CUtensorMap* tmPre,

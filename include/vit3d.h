@@ -69,9 +69,12 @@ unsigned long long vit3d_launch_count(void);
  *                            write-saturated HBM is not an L2 miss).  Env VIT3D_L2_AHEAD.
  *   VIT3D_TUNE_MLP_PAIR      0 (default): one CTA per 128-row tile of the fused MLP; 1: clusters of two CTAs that
  *                            share every weight k-block by TMA multicast (half the L2 reads; measured equal -
- *                            the kernel is bound by its GELU / final epilogue, not by L2).  Env VIT3D_MLP_PAIR. */
+ *                            the kernel is bound by its GELU / final epilogue, not by L2).  Env VIT3D_MLP_PAIR.
+ *   VIT3D_TUNE_WGRAD_RED     1 (default): split-K weight-gradient tiles are added into the gradient buffer by the
+ *                            TMA unit (cp.reduce.async.bulk.tensor, fp32 add at the L2); 0: red.global.add.v4.f32
+ *                            from the epilogue warps (~1 element per clock and SM).  Env VIT3D_WGRAD_RED. */
 enum { VIT3D_TUNE_EPI_PANEL = 0, VIT3D_TUNE_ATTN_THREADS = 1, VIT3D_TUNE_EPI_LEAN = 2, VIT3D_TUNE_STORE_WIDE = 3,
-       VIT3D_TUNE_L2_AHEAD = 4, VIT3D_TUNE_MLP_PAIR = 5, VIT3D_TUNE_COUNT = 6 };
+       VIT3D_TUNE_L2_AHEAD = 4, VIT3D_TUNE_MLP_PAIR = 5, VIT3D_TUNE_WGRAD_RED = 6, VIT3D_TUNE_COUNT = 7 };
 int vit3d_set_tuning(int key, int value);
 int vit3d_get_tuning(int key);
 /* bytes per "act" element for a precision mode */

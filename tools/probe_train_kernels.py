@@ -24,7 +24,11 @@ def main():
     ap.add_argument("--d", type=int, default=3072)
     ap.add_argument("--heads", type=int, default=16)
     ap.add_argument("--only", default="")
+    ap.add_argument("--tune", default="", help="comma list of key=value tuning switches (include/vit3d.h VIT3D_TUNE_*)")
     args = ap.parse_args()
+    for kv in [t for t in args.tune.split(",") if t]:
+        k, v = kv.split("=")
+        vit3d_b200._lib.lib().vit3d_set_tuning(int(k), int(v))
     dev = torch.device("cuda:0")
     B, S, H, d, heads = args.batch, 65, 256, args.d, args.heads
     M = B * S
@@ -85,6 +89,10 @@ def main():
         bytes_=M * d * 2 + M * H * (4 + 4 + 2), flops=2 * M * d * H)
     reg("wgrad fc2 [H,d]", lambda: call("vit3d_wgrad", ptr(gy), ptr(wide), ptr(dwB), None, None, 0, M, H, d, st),
         bytes_=M * d * 2 + M * H * 2, flops=2 * M * d * H)
+    ws = torch.empty(vit3d_b200._lib.lib().vit3d_wgrad_ws_bytes(M, H, d) // 4, device=dev)
+    bn_, sp_ = C.c_int(0), C.c_int(0)
+    reg("wgrad fc2 partial tiles (no reduce)", lambda: call("vit3d_wgrad_partial", ptr(gy), ptr(wide), ptr(ws), M, H, d, C.byref(bn_),
+                                                            C.byref(sp_), st), bytes_=M * d * 2 + M * H * 2, flops=2 * M * d * H)
     reg("mlp_bwd fused (dgrad fc2, x dact, dgrad fc1)", lambda: call("vit3d_mlp_bwd", ptr(gy), ptr(w2_t), ptr(w1_t), ptr(pre), ptr(wide2),
                                                                     ptr(out32), ptr(db1), M, H, d, st),
         bytes_=2 * M * d * 2 + M * H * 6, flops=4 * M * d * H)
