@@ -659,6 +659,360 @@ attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16* 
   if (warp == 0) bulk_wait0();
 }
 
+// ---------------------------------------------------------------------------- backward, unit kernel
+// Same math as attn_bwd_tc_kernel, re-cut for the SM: a work unit is (volume, group of 4 heads), a CTA is 4 warps
+// and ONE WARP OWNS ONE HEAD for both passes (its row statistics never leave the warp, no CTA barrier between the
+// passes).  The unit's q | k | v | dO column blocks arrive as 65-row x 128-byte boxes (TMA, SWIZZLE_128B: 4 * NB
+// tensor copies instead of 130 per-row bulk copies, ~46 cycles of TMA service each), dQ / dK / dV leave the same
+// way.  ~50 KB of shared memory and 128 registers per thread: four CTAs per SM at D = 16, so one CTA's loads and
+// stores hide behind the other three's math, and a batch of 256 volumes is 1024 units over 592 CTA slots
+// (7 units on the busiest SM = 1.75 volumes, where one-volume-per-CTA needs 2).
+constexpr int AU_TILE = 72 * 128;          // one column block: 65 rows (padded to a multiple of 8) of 128 bytes
+template <int D> struct AuCfg {
+  static constexpr int UC = 4 * D;                    // columns of a unit (4 heads)
+  static constexpr int NB = UC / 64;                  // 128-byte column blocks per matrix
+  static constexpr int MAT = NB * AU_TILE;
+  static constexpr int STATS = 4 * 240 * 4;           // (max, 1/sum, delta) x 80 rows per warp
+  static constexpr int SMEM = 5 * MAT + STATS + 64 + 1024;
+  static constexpr int CTAS = D == 16 ? 4 : (D == 32 ? 2 : 1);
+  static constexpr int NC = (3 * UC + 127) / 128;     // bias-gradient columns per thread
+};
+// byte address of (row, byte column colb) inside a matrix of swizzled column blocks
+__device__ __forceinline__ uint32_t au_addr(uint32_t base, int row, int colb) {
+  return base + (colb >> 7) * AU_TILE + row * 128 + ((((colb >> 4) ^ row) & 7) << 4) + (colb & 15);
+}
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void au_store_box(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+template <int D>
+__global__ void __launch_bounds__(128, AuCfg<D>::CTAS)
+attn_bwd_unit_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmDo,
+                     const __grid_constant__ CUtensorMap tmDqkv, float* __restrict__ db_q, float* __restrict__ db_k,
+                     float* __restrict__ db_v, int units, int groups, float scale, float scale_log2e) {
+  using Cfg = AuCfg<D>;
+  constexpr int KSTEPS = D / 16;
+  constexpr int NT = 10;
+  constexpr int DT = D / 8;
+  constexpr int MAT = Cfg::MAT, NB = Cfg::NB, UC = Cfg::UC;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sq = smem_u32(smem), sk = sq + MAT, sv = sk + MAT, sdo = sv + MAT, sdq = sdo + MAT;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  float* st = reinterpret_cast<float*>(smem + 5 * MAT) + warp * 240;       // [0,80): max c + log2 sum, [80,160): delta
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 5 * MAT + Cfg::STATS);
+  const int g = lane >> 2, t = lane & 3;
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQkv);
+    prefetch_tmap(&tmDo);
+    prefetch_tmap(&tmDqkv);
+    mbar_init(full, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_trigger();
+  pdl_wait();
+  const int hq = blockIdx.x % groups;      // the grid is a multiple of `groups`: a CTA keeps its head group
+  const int c0 = hq * UC;
+  const int hc = warp * D * 2;             // byte column of this warp's head inside the unit
+  float bs[Cfg::NC];
+#pragma unroll
+  for (int i = 0; i < Cfg::NC; ++i) bs[i] = 0.f;
+
+  int it = 0;
+  for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+    const int row_g = (u / groups) * AT_S;
+    if (threadIdx.x == 0) {
+      bulk_wait_read0();                   // the previous unit's stores have finished reading shared memory
+      mbar_arrive_expect_tx(full, 4 * NB * AT_S * 128);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        tma_load_2d(smem + j * AU_TILE, &tmQkv, full, c0 + 64 * j, row_g);
+        tma_load_2d(smem + MAT + j * AU_TILE, &tmQkv, full, AT_A + c0 + 64 * j, row_g);
+        tma_load_2d(smem + 2 * MAT + j * AU_TILE, &tmQkv, full, 2 * AT_A + c0 + 64 * j, row_g);
+        tma_load_2d(smem + 3 * MAT + j * AU_TILE, &tmDo, full, c0 + 64 * j, row_g);
+      }
+    }
+    mbar_wait(full, it & 1);
+
+    // ------------------------------------------------------------------ pass 1: query tiles of this warp's head
+#pragma unroll 1
+    for (int rt = 0; rt < 5; ++rt) {
+      const int r0 = rt * 16;
+      uint32_t qa[KSTEPS][4], da[KSTEPS][4];
+      {
+        const int row = min(r0 + (lane & 7) + ((lane >> 3) & 1) * 8, AT_S - 1);
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          ldsm_x4(au_addr(sq, row, hc + ks * 32 + (lane >> 4) * 16), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+          ldsm_x4(au_addr(sdo, row, hc + ks * 32 + (lane >> 4) * 16), da[ks][0], da[ks][1], da[ks][2], da[ks][3]);
+        }
+      }
+      float s[NT][4], dp[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+        if (nt < 9) {
+          const int key = min(nt * 8 + (lane & 7), AT_S - 1);
+#pragma unroll
+          for (int ks = 0; ks < KSTEPS; ++ks) {
+            uint32_t b0, b1;
+            ldsm_x2(au_addr(sk, key, hc + ks * 32 + ((lane >> 3) & 1) * 16), b0, b1);
+            mma_bf16(s[nt], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
+            ldsm_x2(au_addr(sv, key, hc + ks * 32 + ((lane >> 3) & 1) * 16), b0, b1);
+            mma_bf16(dp[nt], da[ks][0], da[ks][1], da[ks][2], da[ks][3], b0, b1);
+          }
+        }
+      }
+      // softmax statistics over the 65 valid keys: columns 0..63 (nt < 8) are always valid, nt = 8 holds only
+      // key 64 (quad lane 0, first element), nt = 9 is padding for the K = 80 reduction of dQ = dS K
+      const bool tail = t == 0;
+      float mx0 = tail ? s[8][0] : -INFINITY, mx1 = tail ? s[8][2] : -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mc0 = mx0 * scale_log2e, mc1 = mx1 * scale_log2e;
+      // e = exp(s - max) (unnormalised P), sum = rowsum(e), dl = rowsum(e dP): one FFMA + MUFU + FADD + FFMA per element
+      float sum0 = 0.f, sum1 = 0.f, dl0 = 0.f, dl1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = ex2_approx(fmaf(s[nt][0], scale_log2e, -mc0));
+        s[nt][1] = ex2_approx(fmaf(s[nt][1], scale_log2e, -mc0));
+        s[nt][2] = ex2_approx(fmaf(s[nt][2], scale_log2e, -mc1));
+        s[nt][3] = ex2_approx(fmaf(s[nt][3], scale_log2e, -mc1));
+        sum0 += s[nt][0] + s[nt][1];
+        sum1 += s[nt][2] + s[nt][3];
+        dl0 = fmaf(s[nt][0], dp[nt][0], fmaf(s[nt][1], dp[nt][1], dl0));
+        dl1 = fmaf(s[nt][2], dp[nt][2], fmaf(s[nt][3], dp[nt][3], dl1));
+      }
+      s[8][0] = tail ? ex2_approx(fmaf(s[8][0], scale_log2e, -mc0)) : 0.f;
+      s[8][2] = tail ? ex2_approx(fmaf(s[8][2], scale_log2e, -mc1)) : 0.f;
+      s[8][1] = s[8][3] = 0.f;
+      sum0 += s[8][0]; sum1 += s[8][2];
+      dl0 = fmaf(s[8][0], dp[8][0], dl0);
+      dl1 = fmaf(s[8][2], dp[8][2], dl1);
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+      dl0 += __shfl_xor_sync(0xffffffffu, dl0, 1);
+      dl0 += __shfl_xor_sync(0xffffffffu, dl0, 2);
+      dl1 += __shfl_xor_sync(0xffffffffu, dl1, 1);
+      dl1 += __shfl_xor_sync(0xffffffffu, dl1, 2);
+      const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+      dl0 *= inv0; dl1 *= inv1;                        // delta = rowsum(P dP)
+      const int row0 = r0 + g, row1 = r0 + g + 8;
+      if (tail) {
+        // pass 2 rebuilds P = exp2(s c - (max c + log2 sum)) with one FFMA + MUFU per element
+        st[row0] = mc0 + __log2f(sum0); st[80 + row0] = dl0;
+        st[row1] = mc1 + __log2f(sum1); st[80 + row1] = dl1;
+      }
+      // dS / (scale / sum) = e (dP - delta); the per-row factor scale / sum is applied to the dQ tile instead
+#pragma unroll
+      for (int nt = 0; nt < 9; ++nt) {
+        s[nt][0] *= dp[nt][0] - dl0; s[nt][1] *= dp[nt][1] - dl0;
+        s[nt][2] *= dp[nt][2] - dl1; s[nt][3] *= dp[nt][3] - dl1;
+      }
+      s[9][0] = s[9][1] = s[9][2] = s[9][3] = 0.f;
+      const float ks0 = inv0 * scale, ks1 = inv1 * scale;
+      float o[DT][4];
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) {
+        const uint32_t a0 = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+        const uint32_t a1 = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+        const uint32_t a2 = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        const uint32_t a3 = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        const int key = min(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, AT_S - 1);
+#pragma unroll
+        for (int dt = 0; dt < DT; ++dt) {
+          uint32_t b0, b1;
+          ldsm_x2_t(au_addr(sk, key, hc + dt * 16), b0, b1);                          // K rows, transposed
+          mma_bf16(o[dt], a0, a1, a2, a3, b0, b1);
+        }
+      }
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) {
+        const int colb = hc + (dt * 8 + 2 * t) * 2;
+        if (row0 < AT_S) st_shared_u32(au_addr(sdq, row0, colb), pack_bf16(o[dt][0] * ks0, o[dt][1] * ks0));
+        if (row1 < AT_S) st_shared_u32(au_addr(sdq, row1, colb), pack_bf16(o[dt][2] * ks1, o[dt][3] * ks1));
+      }
+    }
+    __syncwarp();
+
+    // ------------------------------------------------------------------ pass 2: key tiles of the same head
+#pragma unroll 1
+    for (int kt = 0; kt < 5; ++kt) {
+      const int k0 = kt * 16;
+      uint32_t ka[KSTEPS][4], va[KSTEPS][4];
+      {
+        const int row = min(k0 + (lane & 7) + ((lane >> 3) & 1) * 8, AT_S - 1);
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          ldsm_x4(au_addr(sk, row, hc + ks * 32 + (lane >> 4) * 16), ka[ks][0], ka[ks][1], ka[ks][2], ka[ks][3]);
+          ldsm_x4(au_addr(sv, row, hc + ks * 32 + (lane >> 4) * 16), va[ks][0], va[ks][1], va[ks][2], va[ks][3]);
+        }
+      }
+      float s[NT][4], dp[NT][4];     // rows = keys (g, g+8), columns = queries
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+        if (nt < 9) {
+          const int qrow = min(nt * 8 + (lane & 7), AT_S - 1);
+#pragma unroll
+          for (int ks = 0; ks < KSTEPS; ++ks) {
+            uint32_t b0, b1;
+            ldsm_x2(au_addr(sq, qrow, hc + ks * 32 + ((lane >> 3) & 1) * 16), b0, b1);      // Q rows
+            mma_bf16(s[nt], ka[ks][0], ka[ks][1], ka[ks][2], ka[ks][3], b0, b1);
+            ldsm_x2(au_addr(sdo, qrow, hc + ks * 32 + ((lane >> 3) & 1) * 16), b0, b1);     // dO rows
+            mma_bf16(dp[nt], va[ks][0], va[ks][1], va[ks][2], va[ks][3], b0, b1);
+          }
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {                 // query columns 0..63: always valid
+        const int c = nt * 8 + 2 * t;
+        const float2 ml = *reinterpret_cast<const float2*>(st + c), dl = *reinterpret_cast<const float2*>(st + 80 + c);
+        s[nt][0] = ex2_approx(fmaf(s[nt][0], scale_log2e, -ml.x));       // P^T
+        s[nt][1] = ex2_approx(fmaf(s[nt][1], scale_log2e, -ml.y));
+        s[nt][2] = ex2_approx(fmaf(s[nt][2], scale_log2e, -ml.x));
+        s[nt][3] = ex2_approx(fmaf(s[nt][3], scale_log2e, -ml.y));
+        dp[nt][0] = s[nt][0] * (dp[nt][0] - dl.x); dp[nt][1] = s[nt][1] * (dp[nt][1] - dl.y);   // dS^T / scale
+        dp[nt][2] = s[nt][2] * (dp[nt][2] - dl.x); dp[nt][3] = s[nt][3] * (dp[nt][3] - dl.y);
+      }
+      {                                                // query 64 (quad lane 0, first element); the rest is padding
+        const bool tail = t == 0;
+        const float ml = st[64], dl = st[80 + 64];
+        s[8][0] = tail ? ex2_approx(fmaf(s[8][0], scale_log2e, -ml)) : 0.f;
+        s[8][2] = tail ? ex2_approx(fmaf(s[8][2], scale_log2e, -ml)) : 0.f;
+        s[8][1] = s[8][3] = 0.f;
+        dp[8][0] = s[8][0] * (dp[8][0] - dl); dp[8][2] = s[8][2] * (dp[8][2] - dl);
+        dp[8][1] = dp[8][3] = 0.f;
+        s[9][0] = s[9][1] = s[9][2] = s[9][3] = 0.f;
+        dp[9][0] = dp[9][1] = dp[9][2] = dp[9][3] = 0.f;
+      }
+      float ov[DT][4], ok[DT][4];
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) {
+        ov[dt][0] = ov[dt][1] = ov[dt][2] = ov[dt][3] = 0.f;
+        ok[dt][0] = ok[dt][1] = ok[dt][2] = ok[dt][3] = 0.f;
+      }
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) {
+        const uint32_t p0 = pack_bf16(s[2 * kk][0], s[2 * kk][1]), p1 = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+        const uint32_t p2 = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]), p3 = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        const uint32_t e0 = pack_bf16(dp[2 * kk][0], dp[2 * kk][1]), e1 = pack_bf16(dp[2 * kk][2], dp[2 * kk][3]);
+        const uint32_t e2 = pack_bf16(dp[2 * kk + 1][0], dp[2 * kk + 1][1]), e3 = pack_bf16(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
+        const int qrow = min(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, AT_S - 1);
+#pragma unroll
+        for (int dt = 0; dt < DT; ++dt) {
+          uint32_t b0, b1;
+          ldsm_x2_t(au_addr(sdo, qrow, hc + dt * 16), b0, b1);              // dO rows, transposed
+          mma_bf16(ov[dt], p0, p1, p2, p3, b0, b1);
+          ldsm_x2_t(au_addr(sq, qrow, hc + dt * 16), b0, b1);               // Q rows, transposed
+          mma_bf16(ok[dt], e0, e1, e2, e3, b0, b1);
+        }
+      }
+      __syncwarp();
+      const int row0 = k0 + g, row1 = k0 + g + 8;
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) {
+        const int colb = hc + (dt * 8 + 2 * t) * 2;
+        if (row0 < AT_S) {
+          st_shared_u32(au_addr(sk, row0, colb), pack_bf16(ok[dt][0] * scale, ok[dt][1] * scale));
+          st_shared_u32(au_addr(sv, row0, colb), pack_bf16(ov[dt][0], ov[dt][1]));
+        }
+        if (row1 < AT_S) {
+          st_shared_u32(au_addr(sk, row1, colb), pack_bf16(ok[dt][2] * scale, ok[dt][3] * scale));
+          st_shared_u32(au_addr(sv, row1, colb), pack_bf16(ov[dt][2], ov[dt][3]));
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        au_store_box(&tmDqkv, sdq + j * AU_TILE, c0 + 64 * j, row_g);                   // dQ
+        au_store_box(&tmDqkv, sk + j * AU_TILE, AT_A + c0 + 64 * j, row_g);             // dK
+        au_store_box(&tmDqkv, sv + j * AU_TILE, 2 * AT_A + c0 + 64 * j, row_g);         // dV
+      }
+      bulk_commit();
+    }
+    if (db_q) {
+      // q / k / v bias gradients: column sums of the unit's dQ | dK | dV images, kept in registers across units
+#pragma unroll
+      for (int i = 0; i < Cfg::NC; ++i) {
+        const int c = (int)threadIdx.x + 128 * i;
+        if (c < 3 * UC) {
+          const int m = c / UC, col = c - m * UC;
+          const uint32_t base = m == 0 ? sdq : (m == 1 ? sk : sv);
+          float a = 0.f;
+#pragma unroll 5
+          for (int r = 0; r < AT_S; ++r)
+            a += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(smem + (au_addr(base, r, col * 2) - sq)));
+          bs[i] += a;
+        }
+      }
+    }
+    __syncthreads();         // every warp is done with the images before the next unit's loads overwrite them
+  }
+  if (db_q && (int)blockIdx.x < units) {
+#pragma unroll
+    for (int i = 0; i < Cfg::NC; ++i) {
+      const int c = (int)threadIdx.x + 128 * i;
+      if (c < 3 * UC) {
+        const int m = c / UC, col = c - m * UC;
+        atomicAdd((m == 0 ? db_q : (m == 1 ? db_k : db_v)) + c0 + col, bs[i]);
+      }
+    }
+  }
+  if (threadIdx.x == 0) bulk_wait0();
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long long rows, long long cols, long long ld_elems,
+                 int box_rows, int box_cols, int swizzle_bytes);
+
+template <int D>
+static int launch_attn_bwd_unit(const void* dctx, const void* qkv, void* dqkv, float* db_q, float* db_k, float* db_v, int B,
+                                cudaStream_t st) {
+  using Cfg = AuCfg<D>;
+  auto kern = attn_bwd_unit_kernel<D>;
+  V3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  CUtensorMap tq, td, to;
+  int rc = make_tmap_2d(&tq, qkv, 2, (long long)B * AT_S, 3 * AT_A, 3 * AT_A, AT_S, 64, 128);
+  if (rc != VIT3D_OK) return rc;
+  rc = make_tmap_2d(&td, dctx, 2, (long long)B * AT_S, AT_A, AT_A, AT_S, 64, 128);
+  if (rc != VIT3D_OK) return rc;
+  rc = make_tmap_2d(&to, dqkv, 2, (long long)B * AT_S, 3 * AT_A, 3 * AT_A, AT_S, 64, 128);
+  if (rc != VIT3D_OK) return rc;
+  const int groups = AT_A / Cfg::UC;                // head groups (units) per volume
+  const int units = B * groups;
+  int grid = sm_count() * Cfg::CTAS;
+  if (grid > units) grid = units;
+  grid -= grid % groups;
+  const float scale = 1.0f / sqrtf((float)D);
+  V3_CUDA(launch_pdl(kern, dim3(grid), dim3(128), (size_t)Cfg::SMEM, st, tq, td, to, db_q, db_k, db_v, units, groups, scale,
+                     1.4426950408889634f * scale));
+  V3_LAUNCH_CHECK();
+  return VIT3D_OK;
+}
+
 template <int D>
 static int launch_attn_bwd(const void* dctx, const void* qkv, void* dqkv, float* db_q, float* db_k, float* db_v, int B,
                            cudaStream_t st) {
@@ -685,6 +1039,11 @@ int tc_attn_bwd(const void* dctx, const void* qkv, void* dqkv, float* db_q, floa
   if ((db_q != nullptr) != (db_k != nullptr) || (db_q != nullptr) != (db_v != nullptr)) {
     set_error("tc attention bwd: pass all three bias-gradient buffers or none");
     return VIT3D_ERR_INVALID;
+  }
+  if (tuning(VIT3D_TUNE_ATTN_BWD) != 0) {
+    if (D == 16) return launch_attn_bwd_unit<16>(dctx, qkv, dqkv, db_q, db_k, db_v, B, st);
+    if (D == 32) return launch_attn_bwd_unit<32>(dctx, qkv, dqkv, db_q, db_k, db_v, B, st);
+    return launch_attn_bwd_unit<64>(dctx, qkv, dqkv, db_q, db_k, db_v, B, st);
   }
   if (D == 16) return launch_attn_bwd<16>(dctx, qkv, dqkv, db_q, db_k, db_v, B, st);
   if (D == 32) return launch_attn_bwd<32>(dctx, qkv, dqkv, db_q, db_k, db_v, B, st);

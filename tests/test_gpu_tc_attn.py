@@ -46,17 +46,30 @@ def test_attention_bf16(heads, B, vis, threads):
         assert float((probs.sum(-1) - 1).abs().max()) < 1e-5
 
 
+@pytest.mark.parametrize("kern", [1, 0])
 @pytest.mark.parametrize("heads", [4, 8, 16])
-@pytest.mark.parametrize("B", [1, 3, 149, 300])
-def test_attention_backward_bf16(heads, B):
-    """mma.sync attention backward (probabilities recomputed) vs fp64 autograd on the same bf16 inputs."""
+@pytest.mark.parametrize("B", [1, 3, 149, 700])
+def test_attention_backward_bf16(heads, B, kern):
+    """mma.sync attention backward (probabilities recomputed) vs fp64 autograd on the same bf16 inputs: the unit kernel
+    (kern=1: (volume, 4-head) units, TMA boxes) and the one-volume-per-CTA kernel (kern=0), with the q | k | v bias
+    gradients (column sums of dqkv) accumulated onto existing values."""
+    from vit3d_b200._lib import lib
     torch.manual_seed(B * 17 + heads)
     S, A = 65, 256
     qkv = (torch.randn(B, S, 3 * A, device=DEV) * 1.2).to(torch.bfloat16)
     dctx = torch.randn(B, S, A, device=DEV).to(torch.bfloat16)
     dqkv = torch.full((B, S, 3 * A), float("nan"), device=DEV, dtype=torch.bfloat16)
-    call("vit3d_attn_bwd", ptr(dctx), ptr(qkv), ptr(dqkv), B, S, heads, A // heads, PREC["bf16"], stream())
-    torch.cuda.synchronize()
+    db = [torch.full((A,), 0.5, device=DEV) for _ in range(3)]
+    lib().vit3d_set_tuning(7, kern)
+    try:
+        call("vit3d_attn_bwd_bias", ptr(dctx), ptr(qkv), ptr(dqkv), ptr(db[0]), ptr(db[1]), ptr(db[2]), B, S, heads, A // heads, stream())
+        torch.cuda.synchronize()
+        plain = torch.full((B, S, 3 * A), float("nan"), device=DEV, dtype=torch.bfloat16)
+        call("vit3d_attn_bwd", ptr(dctx), ptr(qkv), ptr(plain), B, S, heads, A // heads, PREC["bf16"], stream())
+        torch.cuda.synchronize()
+    finally:
+        lib().vit3d_set_tuning(7, 1)
+    assert torch.equal(plain, dqkv)
     q64 = qkv.double().requires_grad_(True)
     ctx, _ = ref_attention(q64, heads)
     ctx.backward(dctx.double())
@@ -66,6 +79,9 @@ def test_attention_backward_bf16(heads, B):
     assert np.isfinite(err) and err <= 0.03 * scale, (err, scale)
     rel = float((dqkv.double() - ref).norm() / ref.norm())
     assert rel < 0.01, rel
+    got_b = torch.cat(db).double() - 0.5
+    ref_b = dqkv.double().sum((0, 1))
+    assert float((got_b - ref_b).abs().max()) <= 2e-3 * float(ref_b.abs().max()) + 1e-3 * B ** 0.5
 
 
 @pytest.mark.parametrize("heads", [4, 8, 16])
