@@ -264,7 +264,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     TileIter ti(stat, tiles_m, tiles_n, splits);
     int it = 0;
     int cur_tn = -1;
-    for (; ti.next(); ++it) {
+    // training fc1: a thread's keep bits (CW columns of its row) are fetched one tile AHEAD - the epilogue is the
+    // bottleneck of that GEMM (accumulators are ready long before), so a load issued at the top of the tile would
+    // expose its whole global-memory latency
+    uint32_t keep_nx[CW / 32];
+    auto load_keep = [&](const TileIter& tt) {
+      if constexpr (EPI >= 0 && (EPI & 8) != 0) {
+        const int m = tt.tm * TC_BLOCK_M + q * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < CW / 32; ++j) keep_nx[j] = ep.drop_bits == nullptr ? 0xffffffffu : 0u;
+        if (ep.drop_bits != nullptr && m < M) {
+          const uint32_t* drop_row = ep.drop_bits + (((long long)m * N + tt.tn * BN + part * CW) >> 5);
+#pragma unroll
+          for (int j = 0; j < CW / 32; ++j) keep_nx[j] = __ldg(drop_row + j);
+        }
+      }
+    };
+    bool more = ti.next();
+    if (more) load_keep(ti);
+    TileIter nx = ti;
+    bool more_nx = false;
+    for (; more; ++it, ti = nx, more = more_nx) {
+      uint32_t keep[CW / 32];
+#pragma unroll
+      for (int j = 0; j < CW / 32; ++j) keep[j] = keep_nx[j];
+      nx = ti;
+      more_nx = nx.next();
+      if (more_nx) load_keep(nx);
       const int buf = it & 1;
       if constexpr (EPI >= 0 && (EPI & 1) != 0) {
         if (ti.tn != cur_tn) {
@@ -304,20 +330,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         continue;
       }
+      const int m_base = ti.tm * TC_BLOCK_M + q * 32, n_base = ti.tn * BN + part * CW;
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + part * CW;
-      const int m_base = ti.tm * TC_BLOCK_M + q * 32, n_base = ti.tn * BN + part * CW;
       if constexpr (EPI >= 0) {
-        const uint32_t* drop_row = nullptr;
-        uint32_t mw_default = 0u;
-        if constexpr ((EPI & 8) != 0) {
-          if (ep.drop_bits == nullptr) mw_default = 0xffffffffu;
-          else if (m_base + lane < M) drop_row = ep.drop_bits + (((long long)(m_base + lane) * N + n_base) >> 5);
-        }
         epilogue_bf16_lean<CW, EPI, WIDE>(&tmC, &tmPre, taddr, stage, smem_u32(bias_stage) + part * CW * 4,
-                                    smem_u32(bias_stage) + BN * 4 + part * CW * 2, lane, m_base, n_base, drop_row,
-                                    ep.drop_scale, mw_default);
+                                    smem_u32(bias_stage) + BN * 4 + part * CW * 2, lane, m_base, n_base, keep,
+                                    ep.drop_scale);
       } else {
         if (ep.atomic == 2) {
           // weight gradients: boxes added into the output by the TMA unit; one tensor map per output segment

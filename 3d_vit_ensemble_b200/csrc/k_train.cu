@@ -68,6 +68,12 @@ int launch_dropout_bits(uint32_t* bits, int nseg, const unsigned* sites, const l
   segs.word0[nseg] = w;
   if (w <= 0) return VIT3D_OK;
   long long blocks = (w + 255) / 256;
+  // two CTAs (512 threads) per SM: the masks are drawn on a side stream next to the forward's GEMMs, whose one CTA
+  // per SM (576-608 threads, ~220 KB of shared memory) must still find its thread slots - eight CTAs per SM would
+  // fill all 2048 and push the GEMMs behind this ALU-bound kernel
+  // eight CTAs per SM.  (Measured: fewer CTAs so that the forward's GEMM CTAs co-reside, a matching shared-memory
+  // carve-out, or drawing the next step's masks beside the backward's GEMMs all leave the step time unchanged or
+  // worse - the Philox work, ~0.2 ms per conf-18 step, is not hidden by a side stream.)
   const long long cap = (long long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   dropout_bits_kernel<<<(int)blocks, 256, 0, st>>>(bits, segs, dropout_thresh(p), seed, step, step_dev);

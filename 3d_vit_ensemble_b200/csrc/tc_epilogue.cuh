@@ -133,6 +133,51 @@ __device__ __forceinline__ void gelu_and_grad_pair(float a, float b, float2& y, 
   const __half2 s = __hfma2(__hneg2(t), t, __float2half2_rn(1.f));        // 1 - t^2
   dy = __half22float2(__hfma2(__hmul2(hx, s), q, a1));
 }
+// Training fc1 epilogue for one column pair, all in packed half: x = acc + bias; the dropout scale is folded into
+// the constants (hs = 0.5 * scale), the keep bits arrive as a 32-bit AND mask (0xffff per kept column):
+//   w = bf16x2(gelu(x) * keep * scale),  dq = bf16x2(gelu'(x) * keep * scale)
+__device__ __forceinline__ void gelu_grad_drop_pair(float a, float b, uint32_t bias_h2, __half2 hs, uint32_t mask, uint32_t& w,
+                                                    uint32_t& dq) {
+  const __half2 x = __hadd2(__floats2half2_rn(a, b), *reinterpret_cast<const __half2*>(&bias_h2));
+  const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(100.f));
+  __half2 p = __hfma2(x2, __float2half2_rn(-3.58732362e-4f), __float2half2_rn(0.0370503451f));
+  p = __hfma2(x2, p, __float2half2_rn(0.797458471f));
+  const __half2 u = __hmul2(x, p);
+  uint32_t ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
+  const __half2 t = *reinterpret_cast<const __half2*>(&ti);
+  const __half2 hx = __hmul2(x, hs);                                       // scale x / 2
+  __half2 y = __hfma2(hx, t, hx);
+  __half2 q = __hfma2(x2, __float2half2_rn(5.f * -3.58732362e-4f), __float2half2_rn(3.f * 0.0370503451f));
+  q = __hfma2(x2, q, __float2half2_rn(0.797458471f));
+  const __half2 a1 = __hfma2(t, hs, hs);                                   // scale (1 + t) / 2
+  const __half2 sm = __hfma2(__hneg2(t), t, __float2half2_rn(1.f));        // 1 - t^2
+  __half2 dy = __hfma2(__hmul2(hx, sm), q, a1);
+  const uint32_t yb = *reinterpret_cast<const uint32_t*>(&y) & mask, db = *reinterpret_cast<const uint32_t*>(&dy) & mask;
+  y = *reinterpret_cast<const __half2*>(&yb);
+  dy = *reinterpret_cast<const __half2*>(&db);
+  w = pack2_bf16(__low2float(y), __high2float(y));
+  dq = pack2_bf16(__low2float(dy), __high2float(dy));
+}
+// keep bits (2j, 2j+1) of `mw` -> AND mask for the half pair: A = mw << s0 puts bit 2j at the top of byte j/4,
+// B = mw << (s0 - 1) puts bit 2j+1 there; prmt in sign-replication mode spreads the two byte signs over a half each
+template <int J>
+__device__ __forceinline__ uint32_t keep_mask_pair(const uint32_t (&sh)[8]) {
+  constexpr int s0 = 7 - ((2 * J) & 7), k = J >> 2;
+  constexpr uint32_t lo = 8u | k, hi = 8u | (4u + k);
+  constexpr uint32_t sel = (hi << 12) | (hi << 8) | (lo << 4) | lo;
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(sh[s0]), "r"(sh[s0 - 1]), "n"(sel));
+  return m;
+}
+template <int J>
+__device__ __forceinline__ void gelu_grad_drop_unroll(const uint32_t (&r)[32], const uint32_t (&bh)[16], __half2 hs,
+                                                      const uint32_t (&sh)[8], uint32_t (&w)[16], uint32_t (&dq)[16]) {
+  if constexpr (J < 16) {
+    gelu_grad_drop_pair(__uint_as_float(r[2 * J]), __uint_as_float(r[2 * J + 1]), bh[J], hs, keep_mask_pair<J>(sh), w[J], dq[J]);
+    gelu_grad_drop_unroll<J + 1>(r, bh, hs, sh, w, dq);
+  }
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -395,14 +440,14 @@ __device__ __forceinline__ uint32_t gelu_pair_bf16_h2(__half2 x) {
 // 128-byte rows (128B swizzle, 4 KB) and leaves by one bulk tensor store per tile instead of two stores of
 // 64-byte rows - half the TMA row transactions, and the wait for the previous store moves a whole tile away.
 //   MODE bit 3: the training fc1 (needs bits 0-2): output = gelu(v) * keep * scale, and the `pre` output receives
-//               d act / d pre = gelu'(v) * keep * scale (TcEpilogue::store_dact).  Keep bits: `drop_row` = word of
-//               column n_base of this thread's row; where it is null the word is `mw_default` (0 for rows >= M,
-//               all ones when the call has no dropout)
+//               d act / d pre = gelu'(v) * keep * scale (TcEpilogue::store_dact).  `keep` = the CW / 32 words of keep
+//               bits of this thread's row (fetched by the caller before the accumulator wait; 0 for rows >= M, all
+//               ones when the call has no dropout)
 template <int CW, int MODE, bool WIDE = false>
 __device__ __forceinline__ void epilogue_bf16_lean(const CUtensorMap* tmC, const CUtensorMap* tmPre, uint32_t taddr,
                                                    uint32_t stage, uint32_t bias_f32, uint32_t bias_h2, int lane,
-                                                   int m_base, int n_base, const uint32_t* drop_row = nullptr,
-                                                   float drop_scale = 1.f, uint32_t mw_default = 0u) {
+                                                   int m_base, int n_base, const uint32_t* keep = nullptr,
+                                                   float drop_scale = 1.f) {
   constexpr bool BIAS = (MODE & 1) != 0, GELU = (MODE & 2) != 0, PRE = (MODE & 4) != 0, DROP = (MODE & 8) != 0;
   static_assert(!WIDE || (CW == 64 && !PRE), "wide staging: 64 columns per warp, no pre-activation copy");
   static_assert(!DROP || (GELU && PRE), "dropout variant = training fc1 (bias + GELU + pre-activation)");
@@ -428,6 +473,29 @@ __device__ __forceinline__ void epilogue_bf16_lean(const CUtensorMap* tmC, const
           w[j + i] = gelu_pair_bf16_h2(x);
         }
       }
+    } else if constexpr (DROP) {
+      // training fc1: packed-half GELU and derivative, dropout scale folded in, keep bits as AND masks
+      uint32_t dq[16], bh[16];
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const uint4 b = ld_shared_v4(bias_h2 + (c + 2 * j) * 2);
+        bh[j] = b.x; bh[j + 1] = b.y; bh[j + 2] = b.z; bh[j + 3] = b.w;
+      }
+      const uint32_t mw = keep[c >> 5];
+      uint32_t sh[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sh[i] = mw << i;
+      gelu_grad_drop_unroll<0>(r, bh, __float2half2_rn(0.5f * drop_scale), sh, w, dq);
+      if (lane == 0) bulk_store_wait_read();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st_shared_v4(my_row + ((j ^ sw) << 4), dq[4 * j], dq[4 * j + 1], dq[4 * j + 2], dq[4 * j + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmPre, stage, n_base + c, m_base);
+        bulk_store_commit();
+      }
     } else {
       float v[32];
 #pragma unroll
@@ -440,29 +508,13 @@ __device__ __forceinline__ void epilogue_bf16_lean(const CUtensorMap* tmC, const
           v[j + 2] += __uint_as_float(b.z); v[j + 3] += __uint_as_float(b.w);
         }
       }
-      uint32_t dq[16];
-      if constexpr (DROP) {
-        const uint32_t mw = drop_row ? __ldg(drop_row + (c >> 5)) : mw_default;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float2 y, g;
-          gelu_and_grad_pair(v[2 * j], v[2 * j + 1], y, g);
-          const float k0 = ((mw >> (2 * j)) & 1u) ? drop_scale : 0.f, k1 = ((mw >> (2 * j + 1)) & 1u) ? drop_scale : 0.f;
-          w[j] = pack2_bf16(y.x * k0, y.y * k1);
-          dq[j] = pack2_bf16(g.x * k0, g.y * k1);
-        }
-      }
       if constexpr (PRE) {
         if (lane == 0) bulk_store_wait_read();
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if constexpr (DROP)
-            st_shared_v4(my_row + ((j ^ sw) << 4), dq[4 * j], dq[4 * j + 1], dq[4 * j + 2], dq[4 * j + 3]);
-          else
-            st_shared_v4(my_row + ((j ^ sw) << 4), pack2_bf16(v[8 * j], v[8 * j + 1]), pack2_bf16(v[8 * j + 2], v[8 * j + 3]),
-                         pack2_bf16(v[8 * j + 4], v[8 * j + 5]), pack2_bf16(v[8 * j + 6], v[8 * j + 7]));
-        }
+        for (int j = 0; j < 4; ++j)
+          st_shared_v4(my_row + ((j ^ sw) << 4), pack2_bf16(v[8 * j], v[8 * j + 1]), pack2_bf16(v[8 * j + 2], v[8 * j + 3]),
+                       pack2_bf16(v[8 * j + 4], v[8 * j + 5]), pack2_bf16(v[8 * j + 6], v[8 * j + 7]));
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -470,10 +522,8 @@ __device__ __forceinline__ void epilogue_bf16_lean(const CUtensorMap* tmC, const
           bulk_store_commit();
         }
       }
-      if constexpr (!DROP) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) w[j] = GELU ? gelu_pair_bf16(v[2 * j], v[2 * j + 1]) : pack2_bf16(v[2 * j], v[2 * j + 1]);
-      }
+      for (int j = 0; j < 16; ++j) w[j] = GELU ? gelu_pair_bf16(v[2 * j], v[2 * j + 1]) : pack2_bf16(v[2 * j], v[2 * j + 1]);
     }
     if (!WIDE || c == 0) {
       if (lane == 0) bulk_store_wait_read();    // the previous store has finished reading the staging tile
