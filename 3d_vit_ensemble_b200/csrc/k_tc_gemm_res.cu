@@ -21,6 +21,8 @@
 //     (tcgen05.st), the four column slices of a row exchange (sum, sum of squares) through their panel
 //     buffers, then every thread re-reads its slice from TMEM, normalises it and the bf16 panel leaves by
 //     one more bulk tensor store.  No register array of row values, no second pass over HBM.
+#include <stdlib.h>
+
 #include "ptx.cuh"
 #include "tc.cuh"
 #include "tc_epilogue.cuh"
@@ -45,13 +47,18 @@ struct ResEpilogue {
   float* rstd = nullptr;           // [M] optional (LN)
   float eps = 1e-6f;
   int l2_ahead = 0;                // tiles of A prefetched into L2 ahead of the operand ring
+  int k_ahead = 0;                 // k-blocks of the current tile's A prefetched into L2 beyond the ring (deep K)
   const uint32_t* drop_bits = nullptr;   // keep bits over [M,N] (MODE bit 3): (A B^T + bias) * keep * drop_scale + residual
   float drop_scale = 1.f;
 };
 
 // MODE bit 0: bias, bit 1: residual, bit 2: fused LayerNorm output, bit 3: Dropout before the residual add (training)
-template <int MODE>
-__global__ void __launch_bounds__(RS_THREADS, 1)
+// CL = 2: clusters of two CTAs that stay independent (own row tile, own tensor core, own barriers) except for the B
+// operand: the [256 x 64] weight k-block is fetched ONCE per cluster - each CTA loads half of its rows and multicasts
+// them into both CTAs' ring slots.  A streamed 128 x 256 tile needs 48 KB of operands per 512 MMA cycles (96 B/clk,
+// above what the L2 delivers to one SM); sharing B makes it 32 KB.  Needs tiles_n == 1 and an even tile count.
+template <int MODE, int CL = 1>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(RS_THREADS, 1)
 tc_gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmRes,
                    const __grid_constant__ CUtensorMap tmLn, ResEpilogue ep, int M, int N, int K, int tiles_m,
@@ -80,7 +87,7 @@ tc_gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     prefetch_tmap(&tmY);
     for (int s = 0; s < RS_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);      // the commit of every CTA of the cluster frees the slot
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
@@ -94,6 +101,8 @@ tc_gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
+  if constexpr (CL > 1) cluster_sync_all();       // every CTA's barriers exist before any multicast signal
   pdl_trigger();
   pdl_wait();
 
@@ -109,11 +118,23 @@ tc_gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           uint8_t* sa = smem + stage * RS_STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], RS_STAGE_BYTES);
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * 64, tm * RS_BM);
-          tma_load_2d(sa + RS_A_BYTES, &tmB, &full_bar[stage], kb * 64, tn * RS_BN);
+          if constexpr (CL > 1)     // this CTA's share of the B rows, into the same slot of every CTA of the cluster
+            tma_load_2d_mcast(sa + RS_A_BYTES + (int)rank * (RS_B_BYTES / CL), &tmB, &full_bar[stage], kb * 64,
+                              tn * RS_BN + (int)rank * (RS_BN / CL), (uint16_t)((1u << CL) - 1u));
+          else
+            tma_load_2d(sa + RS_A_BYTES, &tmB, &full_bar[stage], kb * 64, tn * RS_BN);
           // the same k-block of the A tile this CTA handles `l2_ahead` tiles from now -> L2
           if (ep.l2_ahead > 0) {
             const int wa = w + (nkb <= 8 ? ep.l2_ahead : 1) * (int)gridDim.x;
             if (wa < total) tma_prefetch_2d(&tmA, kb * 64, (wa / tiles_n) * RS_BM);
+          }
+          // deep reductions: the three-slot ring covers ~1.5 k cycles of a ~3 k cycle HBM read - keep `k_ahead` more
+          // k-blocks of this tile's A rows on their way into L2, so that the ring's own loads are L2 hits
+          if (ep.k_ahead > 0) {
+            if (kb == 0)
+              for (int j = RS_STAGES; j < RS_STAGES + ep.k_ahead && j < nkb; ++j) tma_prefetch_2d(&tmA, j * 64, tm * RS_BM);
+            else if (kb + RS_STAGES + ep.k_ahead - 1 < nkb)
+              tma_prefetch_2d(&tmA, (kb + RS_STAGES + ep.k_ahead - 1) * 64, tm * RS_BM);
           }
           if (++stage == RS_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -141,7 +162,8 @@ tc_gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint64_t bd = ad + (uint64_t)(RS_A_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma<false>(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
+          if constexpr (CL > 1) umma_commit_mcast(&empty_bar[stage], (uint16_t)((1u << CL) - 1u));
+          else umma_commit(&empty_bar[stage]);
           if (++stage == RS_STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[buf]);
@@ -326,6 +348,7 @@ tc_gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();       // nobody leaves while a partner may still multicast into this CTA
   if (warp == 1) tmem_dealloc<2 * RS_BN>(tmem_base);
 }
 
@@ -334,10 +357,10 @@ bool tc_res_supported(int M, int N, int K, bool ln) {
   return !ln || N == RS_BN;
 }
 
-template <int MODE>
+template <int MODE, int CL = 1>
 static int launch_res(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const CUtensorMap& tr,
                       const CUtensorMap& tl, const ResEpilogue& ep, int M, int N, int K, cudaStream_t st) {
-  auto kern = tc_gemm_res_kernel<MODE>;
+  auto kern = tc_gemm_res_kernel<MODE, CL>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   V3_CUDA(cudaGetDevice(&dev));
@@ -348,7 +371,8 @@ static int launch_res(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   const int tiles_m = ceil_div(M, RS_BM), tiles_n = N / RS_BN;
   const int total = tiles_m * tiles_n;
   const int sms = sm_count();
-  const int grid = total < sms ? total : sms;
+  int grid = total < sms ? total : sms;
+  grid -= grid % CL;       // whole clusters; res_pair_ok() made sure every CTA of a cluster walks equally many tiles
   V3_CUDA(launch_pdl(kern, dim3(grid), dim3(RS_THREADS), (size_t)RS_SMEM_BYTES, st, ta, tb, ty, tr, tl, ep, M, N, K, tiles_m,
                      tiles_n));
   V3_LAUNCH_CHECK();
@@ -363,7 +387,12 @@ int tc_gemm_res(const TcLinear& t, cudaStream_t st) {
   CUtensorMap ta, tb, ty, tr, tl;
   int rc = make_tmap_2d(&ta, t.x, 2, t.M, t.K, t.K, RS_BM, 64, 128);
   if (rc != VIT3D_OK) return rc;
-  rc = make_tmap_2d(&tb, t.w, 2, t.N, t.K, t.K, RS_BN, 64, 128);
+  // CTA pairs sharing the weight k-blocks by multicast: one n-tile, an even number of row tiles, a deep reduction
+  // (K = 256 products are bound by their output traffic, not by operand delivery)
+  const int tiles_total = ceil_div(t.M, RS_BM) * (t.N / RS_BN);
+  const bool pair = tuning(VIT3D_TUNE_RES_PAIR) != 0 && t.N == RS_BN && tiles_total % 2 == 0 && t.K >= 1024 &&
+                    (tiles_total <= sm_count() || (sm_count() % 2 == 0 && tiles_total % sm_count() % 2 == 0));
+  rc = make_tmap_2d(&tb, t.w, 2, t.N, t.K, t.K, pair ? RS_BN / 2 : RS_BN, 64, 128);
   if (rc != VIT3D_OK) return rc;
   rc = make_tmap_2d(&ty, t.y, 4, t.M, t.N, t.N, 32, 32, 128);
   if (rc != VIT3D_OK) return rc;
@@ -379,12 +408,14 @@ int tc_gemm_res(const TcLinear& t, cudaStream_t st) {
   }
   ResEpilogue ep;
   ep.l2_ahead = tuning(VIT3D_TUNE_L2_AHEAD);
+  { static const int ka = [] { const char* e = getenv("VIT3D_EXP_K_AHEAD"); return e ? atoi(e) : 0; }(); ep.k_ahead = t.K >= 1024 ? ka : 0; }
   ep.bias = t.bias; ep.gamma = t.ln_gamma; ep.beta = t.ln_beta; ep.mean = t.ln_mean; ep.rstd = t.ln_rstd; ep.eps = t.ln_eps;
   ep.drop_bits = t.drop_bits; ep.drop_scale = t.drop_scale;
   const int mode = (t.bias ? 1 : 0) | (t.residual ? 2 : 0) | (ln ? 4 : 0);
   if (t.drop_bits) {
     // training fc2: Dropout between the Linear and the residual add (modeling.py:123, :196)
     if (!t.bias || !t.residual) { set_error("tc_gemm_res: the dropout variant needs bias and residual"); return VIT3D_ERR_UNSUPPORTED; }
+    if (ln && pair) return launch_res<15, 2>(ta, tb, ty, tr, tl, ep, t.M, t.N, t.K, st);
     return ln ? launch_res<15>(ta, tb, ty, tr, tl, ep, t.M, t.N, t.K, st) : launch_res<11>(ta, tb, ty, tr, tl, ep, t.M, t.N, t.K, st);
   }
   switch (mode) {
@@ -395,7 +426,8 @@ int tc_gemm_res(const TcLinear& t, cudaStream_t st) {
     case 4: return launch_res<4>(ta, tb, ty, tr, tl, ep, t.M, t.N, t.K, st);
     case 5: return launch_res<5>(ta, tb, ty, tr, tl, ep, t.M, t.N, t.K, st);
     case 6: return launch_res<6>(ta, tb, ty, tr, tl, ep, t.M, t.N, t.K, st);
-    default: return launch_res<7>(ta, tb, ty, tr, tl, ep, t.M, t.N, t.K, st);
+    default: return pair ? launch_res<7, 2>(ta, tb, ty, tr, tl, ep, t.M, t.N, t.K, st)
+                         : launch_res<7>(ta, tb, ty, tr, tl, ep, t.M, t.N, t.K, st);
   }
 }
 

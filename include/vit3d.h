@@ -74,11 +74,14 @@ unsigned long long vit3d_launch_count(void);
  *                            TMA unit (cp.reduce.async.bulk.tensor, fp32 add at the L2); 0: red.global.add.v4.f32
  *                            from the epilogue warps (~1 element per clock and SM); 2: as 1 with 256-row tiles for the large
  *                            products (measured equal).  Env VIT3D_WGRAD_RED.
+ *   VIT3D_TUNE_RES_PAIR      1 (default): deep-K Linear + residual + LayerNorm products (fc2) run on clusters of two
+ *                            CTAs that share every weight k-block by TMA multicast; 0: independent CTAs.  Env
+ *                            VIT3D_RES_PAIR.
  *   VIT3D_TUNE_ATTN_BWD      1 (default): attention backward in (volume, 4-head) units, 4-warp CTAs, TMA boxes; 0: one
  *                            16-warp CTA per volume with per-row bulk copies.  Env VIT3D_ATTN_BWD. */
 enum { VIT3D_TUNE_EPI_PANEL = 0, VIT3D_TUNE_ATTN_THREADS = 1, VIT3D_TUNE_EPI_LEAN = 2, VIT3D_TUNE_STORE_WIDE = 3,
        VIT3D_TUNE_L2_AHEAD = 4, VIT3D_TUNE_MLP_PAIR = 5, VIT3D_TUNE_WGRAD_RED = 6, VIT3D_TUNE_ATTN_BWD = 7,
-       VIT3D_TUNE_COUNT = 8 };
+       VIT3D_TUNE_RES_PAIR = 8, VIT3D_TUNE_COUNT = 9 };
 int vit3d_set_tuning(int key, int value);
 int vit3d_get_tuning(int key);
 /* bytes per "act" element for a precision mode */

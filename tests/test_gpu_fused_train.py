@@ -225,6 +225,47 @@ def _gelu_fit(x):
     return 0.5 * x * (1 + t), 0.5 * (1 + t) + 0.5 * x * (1 - t * t) * (c0 + 3 * c1 * x2 + 5 * c2 * x2 * x2)
 
 
+@pytest.mark.parametrize("pair", [1, 0])
+@pytest.mark.parametrize("M,K,drop", [(16640, 3072, True), (256, 1024, False), (19500 + 76, 2048, True), (130, 3072, True), (1000, 256, True)])
+def test_linear_residual_dropout_layernorm_training_forward(M, K, drop, pair):
+    """vit3d_linear_res_train_fwd: y = residual + Dropout(x w^T + b), ln_out = LayerNorm(y) (+ mean / rstd), against fp32
+    torch on the same bf16 operands - as independent CTAs (pair=0) and as clusters of two CTAs sharing the weight
+    k-blocks by TMA multicast (pair=1; taken for even tile counts with K >= 1024: 130 tiles at conf-18 batch 256,
+    153 -> no, 154 tiles = several per CTA on 148 SMs; the other shapes fall back to single CTAs)."""
+    H = 256
+    gen = torch.Generator(device=DEV).manual_seed(M + K)
+    st = torch.cuda.current_stream().cuda_stream
+    x = (torch.randn(M, K, device=DEV, generator=gen) * 0.5).bfloat16()
+    w = (torch.randn(H, K, device=DEV, generator=gen) / K ** 0.5).bfloat16()
+    b = torch.randn(H, device=DEV, generator=gen) * 0.1
+    res = torch.randn(M, H, device=DEV, generator=gen)
+    gamma = 1 + 0.1 * torch.randn(H, device=DEV, generator=gen)
+    beta = 0.1 * torch.randn(H, device=DEV, generator=gen)
+    keep, bits, scale = torch.ones(M, H, device=DEV), None, 1.0
+    if drop:
+        keep = (torch.rand(M, H, device=DEV, generator=gen) > 0.1).float()
+        bits = fused_train._pack_mask_bits(keep, DEV)
+        scale = 1.0 / 0.9
+    y = torch.empty(M, H, device=DEV)
+    ln = torch.empty(M, H, device=DEV, dtype=torch.bfloat16)
+    mean, rstd = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    _lib.lib().vit3d_set_tuning(8, pair)
+    try:
+        _lib.call("vit3d_linear_res_train_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), res.data_ptr(), y.data_ptr(),
+                  None if bits is None else bits.data_ptr(), scale, gamma.data_ptr(), beta.data_ptr(), 1e-6, ln.data_ptr(),
+                  mean.data_ptr(), rstd.data_ptr(), M, H, K, st)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().vit3d_set_tuning(8, 1)
+    ref = res + (x.float() @ w.float().t() + b) * keep * scale
+    assert float((y - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+    mu, var = ref.mean(-1), ref.var(-1, unbiased=False)
+    assert float((mean - mu).abs().max()) < 2e-3
+    assert float((rstd - (var + 1e-6).rsqrt()).abs().max()) < 2e-3 * float((var + 1e-6).rsqrt().max())
+    ref_ln = torch.nn.functional.layer_norm(ref, (H,), gamma, beta, 1e-6)
+    assert float((ln.float() - ref_ln).abs().max()) < 0.03 * float(ref_ln.abs().max())
+
+
 @pytest.mark.parametrize("M,d,drop", [(130, 256, True), (1000, 512, False), (19500, 512, True), (65, 3072, True)])
 def test_fc1_train_forward_and_fused_mlp_backward_kernels(M, d, drop):
     """vit3d_fc1_train_fwd (act = Dropout(gelu(.)), dact = gelu'(.) x keep / (1-p)) and vit3d_mlp_bwd (dgrad fc2 -> x dact

@@ -6,6 +6,7 @@ import pytest
 import torch
 
 import vit3d_b200
+import vit3d_b200.models.modeling  # noqa: F401  (the reference-named module the workflow resolves lazily)
 from oracle import vit3d_oracle as O
 from vit3d_b200 import workflow as W
 
