@@ -53,7 +53,7 @@ static void tuning_defaults() {
     set(VIT3D_TUNE_MLP_PAIR, env("VIT3D_MLP_PAIR", 0));
     set(VIT3D_TUNE_WGRAD_RED, env("VIT3D_WGRAD_RED", 1));
     set(VIT3D_TUNE_ATTN_BWD, env("VIT3D_ATTN_BWD", 1));
-    set(VIT3D_TUNE_RES_PAIR, env("VIT3D_RES_PAIR", 1));
+    set(VIT3D_TUNE_RES_PAIR, env("VIT3D_RES_PAIR", 0));
     set(VIT3D_TUNE_ATTN_THREADS, env("VIT3D_ATTN_THREADS", 0));
   });
 }

@@ -21,8 +21,6 @@
 //     (tcgen05.st), the four column slices of a row exchange (sum, sum of squares) through their panel
 //     buffers, then every thread re-reads its slice from TMEM, normalises it and the bf16 panel leaves by
 //     one more bulk tensor store.  No register array of row values, no second pass over HBM.
-#include <stdlib.h>
-
 #include "ptx.cuh"
 #include "tc.cuh"
 #include "tc_epilogue.cuh"
@@ -47,7 +45,6 @@ struct ResEpilogue {
   float* rstd = nullptr;           // [M] optional (LN)
   float eps = 1e-6f;
   int l2_ahead = 0;                // tiles of A prefetched into L2 ahead of the operand ring
-  int k_ahead = 0;                 // k-blocks of the current tile's A prefetched into L2 beyond the ring (deep K)
   const uint32_t* drop_bits = nullptr;   // keep bits over [M,N] (MODE bit 3): (A B^T + bias) * keep * drop_scale + residual
   float drop_scale = 1.f;
 };
@@ -127,14 +124,6 @@ tc_gemm_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (ep.l2_ahead > 0) {
             const int wa = w + (nkb <= 8 ? ep.l2_ahead : 1) * (int)gridDim.x;
             if (wa < total) tma_prefetch_2d(&tmA, kb * 64, (wa / tiles_n) * RS_BM);
-          }
-          // deep reductions: the three-slot ring covers ~1.5 k cycles of a ~3 k cycle HBM read - keep `k_ahead` more
-          // k-blocks of this tile's A rows on their way into L2, so that the ring's own loads are L2 hits
-          if (ep.k_ahead > 0) {
-            if (kb == 0)
-              for (int j = RS_STAGES; j < RS_STAGES + ep.k_ahead && j < nkb; ++j) tma_prefetch_2d(&tmA, j * 64, tm * RS_BM);
-            else if (kb + RS_STAGES + ep.k_ahead - 1 < nkb)
-              tma_prefetch_2d(&tmA, (kb + RS_STAGES + ep.k_ahead - 1) * 64, tm * RS_BM);
           }
           if (++stage == RS_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -388,7 +377,10 @@ int tc_gemm_res(const TcLinear& t, cudaStream_t st) {
   int rc = make_tmap_2d(&ta, t.x, 2, t.M, t.K, t.K, RS_BM, 64, 128);
   if (rc != VIT3D_OK) return rc;
   // CTA pairs sharing the weight k-blocks by multicast: one n-tile, an even number of row tiles, a deep reduction
-  // (K = 256 products are bound by their output traffic, not by operand delivery)
+  // (K = 256 products are bound by their output traffic, not by operand delivery).  Measured at conf 18 / batch 256
+  // (fc2: M = 16640, K = 3072, one tile per CTA): 39.6 us paired vs 39.7 us single - the product is not bound by L2
+  // operand delivery; an in-tile L2 look-ahead of 4-16 k-blocks made it 2-3 us SLOWER.  ncu: the tensor pipe is
+  // busy 41 % of the CTA's life, the LayerNorm epilogue of the CTA's only tile (~9 us) is fully exposed.
   const int tiles_total = ceil_div(t.M, RS_BM) * (t.N / RS_BN);
   const bool pair = tuning(VIT3D_TUNE_RES_PAIR) != 0 && t.N == RS_BN && tiles_total % 2 == 0 && t.K >= 1024 &&
                     (tiles_total <= sm_count() || (sm_count() % 2 == 0 && tiles_total % sm_count() % 2 == 0));
@@ -408,7 +400,6 @@ int tc_gemm_res(const TcLinear& t, cudaStream_t st) {
   }
   ResEpilogue ep;
   ep.l2_ahead = tuning(VIT3D_TUNE_L2_AHEAD);
-  { static const int ka = [] { const char* e = getenv("VIT3D_EXP_K_AHEAD"); return e ? atoi(e) : 0; }(); ep.k_ahead = t.K >= 1024 ? ka : 0; }
   ep.bias = t.bias; ep.gamma = t.ln_gamma; ep.beta = t.ln_beta; ep.mean = t.ln_mean; ep.rstd = t.ln_rstd; ep.eps = t.ln_eps;
   ep.drop_bits = t.drop_bits; ep.drop_scale = t.drop_scale;
   const int mode = (t.bias ? 1 : 0) | (t.residual ? 2 : 0) | (ln ? 4 : 0);

@@ -36,8 +36,6 @@
 //   warp 0: TMA producer   warp 1: TMEM allocator + MMA issuer   warps 2..17: epilogue   warp 18: dh store
 #include <cuda_fp16.h>
 
-#include <stdlib.h>
-
 #include "ptx.cuh"
 #include "tc.cuh"
 #include "tc_epilogue.cuh"
@@ -60,7 +58,6 @@ static_assert(MB_SMEM <= 232448, "over the 227 KB shared-memory limit");
 struct MlpBwdArgs {
   float* db1 = nullptr;             // [d] (null: skip)
   int M = 0, d = 0;
-  int ahead = 0;                    // chunks of dact kept on their way into L2 beyond the two shared-memory buffers
 };
 
 __global__ void __launch_bounds__(MB_THREADS, 1)
@@ -230,13 +227,6 @@ tc_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         mbar_arrive_expect_tx(&dact_full[b], MB_D_BYTES);
         for (int kb = 0; kb < 2; ++kb)
           tma_load_2d(s_d + b * MB_D_BYTES + kb * 16384, &tmDact, &dact_full[b], c * MB_NC + kb * 64, t * 128);
-        // two 32 KB buffers cover ~2 k cycles of a ~3 k cycle HBM read: later chunks of the tile are requested into L2
-        // now, so that their shared-memory loads are L2 hits
-        if (args.ahead > 0) {
-          const int c0 = c == 0 ? 2 : c + args.ahead + 1, c1 = c + args.ahead + 2;
-          for (int cc = c0; cc < c1 && cc < nch; ++cc)
-            for (int kb = 0; kb < 2; ++kb) tma_prefetch_2d(&tmDact, cc * MB_NC + kb * 64, t * 128);
-        }
       };
       if (total > 0) load_dact(0);
       if (total > 1) load_dact(1);
@@ -392,7 +382,6 @@ int tc_mlp_bwd(const void* gy, const void* w2_t, const void* w1_t, const void* d
   if (rc != VIT3D_OK) return rc;
   MlpBwdArgs a;
   a.db1 = db1; a.M = M; a.d = d;
-  { static const int ah = [] { const char* e = getenv("VIT3D_EXP_DACT_AHEAD"); return e ? atoi(e) : 0; }(); a.ahead = ah; }
   auto kern = tc_mlp_bwd_kernel;
   static thread_local int configured_dev = -1;
   int dev = 0;

@@ -74,9 +74,9 @@ unsigned long long vit3d_launch_count(void);
  *                            TMA unit (cp.reduce.async.bulk.tensor, fp32 add at the L2); 0: red.global.add.v4.f32
  *                            from the epilogue warps (~1 element per clock and SM); 2: as 1 with 256-row tiles for the large
  *                            products (measured equal).  Env VIT3D_WGRAD_RED.
- *   VIT3D_TUNE_RES_PAIR      1 (default): deep-K Linear + residual + LayerNorm products (fc2) run on clusters of two
- *                            CTAs that share every weight k-block by TMA multicast; 0: independent CTAs.  Env
- *                            VIT3D_RES_PAIR.
+ *   VIT3D_TUNE_RES_PAIR      0 (default): independent CTAs; 1: deep-K Linear + residual + LayerNorm products (fc2) run
+ *                            on clusters of two CTAs that share every weight k-block by TMA multicast (measured
+ *                            equal: not bound by L2 operand delivery).  Env VIT3D_RES_PAIR.
  *   VIT3D_TUNE_ATTN_BWD      1 (default): attention backward in (volume, 4-head) units, 4-warp CTAs, TMA boxes; 0: one
  *                            16-warp CTA per volume with per-row bulk copies.  Env VIT3D_ATTN_BWD. */
 enum { VIT3D_TUNE_EPI_PANEL = 0, VIT3D_TUNE_ATTN_THREADS = 1, VIT3D_TUNE_EPI_LEAN = 2, VIT3D_TUNE_STORE_WIDE = 3,
