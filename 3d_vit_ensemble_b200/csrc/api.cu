@@ -54,6 +54,8 @@ static void tuning_defaults() {
     set(VIT3D_TUNE_WGRAD_RED, env("VIT3D_WGRAD_RED", 1));
     set(VIT3D_TUNE_ATTN_BWD, env("VIT3D_ATTN_BWD", 1));
     set(VIT3D_TUNE_RES_PAIR, env("VIT3D_RES_PAIR", 0));
+    set(VIT3D_TUNE_ATTN_TF32, env("VIT3D_ATTN_TF32", 1));
+    set(VIT3D_TUNE_F32_BOX, env("VIT3D_F32_BOX", 0));
     set(VIT3D_TUNE_ATTN_THREADS, env("VIT3D_ATTN_THREADS", 0));
   });
 }
@@ -330,6 +332,8 @@ int vit3d_attn_fwd(const void* qkv, void* ctx, float* probs, int B, int S, int h
   V3_REQUIRE(B >= 0 && S > 0 && heads > 0 && D > 0, "attn_fwd: bad shape");
   cudaStream_t st = as_stream(stream);
   if (prec == VIT3D_PREC_BF16 && tc_attn_supported(S, heads, D)) return tc_attn_fwd(qkv, ctx, probs, S, B, S, heads, D, st);
+  if (prec == VIT3D_PREC_TF32 && tc_attn_supported(S, heads, D) && tuning(VIT3D_TUNE_ATTN_TF32) != 0)
+    return tc_attn_fwd_tf32(reinterpret_cast<const float*>(qkv), reinterpret_cast<float*>(ctx), probs, S, B, S, heads, D, 1, st);
   return launch_attn_fwd_generic(qkv, act_f32(prec), ctx, probs, B, S, heads, D, prec == VIT3D_PREC_TF32, st);
 }
 int vit3d_attn_fwd_padded(const void* qkv, void* ctx, float* probs, int probs_ld, int B, int S, int heads, int D,

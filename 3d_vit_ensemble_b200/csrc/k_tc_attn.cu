@@ -1013,6 +1013,294 @@ static int launch_attn_bwd_unit(const void* dctx, const void* qkv, void* dqkv, f
   return VIT3D_OK;
 }
 
+
+// ---------------------------------------------------------------------------- forward, TF32 mode (fp32 activations)
+// The 1e-3 accuracy mode keeps q | k | v, the probabilities and the context in fp32; its attention ran on a generic
+// SIMT kernel (one block per head, 4.5 ms per layer at batch 1024 - 79 % of the TF32-mode step).  Same unit design as
+// the backward kernel above: a CTA of 4 warps takes (volume, 4 heads), the unit's q | k | v column blocks arrive as
+// 65-row x 128-byte boxes (32 floats = one head of D = 32), one warp owns one head.  Products on mma.sync.m16n8k8
+// (tf32 in, fp32 accumulate): Q K^T as a 3xTF32 split product (fp32-grade scores), P V with P and V rounded to tf32
+// (round to nearest, cvt.rna - the tensor core would truncate).  softmax in fp32, probabilities (packed or padded
+// rows) leave from the accumulator registers, the context tile overwrites the Q tile and leaves as TMA boxes.
+template <int D> struct AfCfg {
+  static constexpr int UC = 4 * D;                    // floats per unit row and matrix (4 heads)
+  static constexpr int NB = UC / 32;                  // 128-byte column blocks per matrix
+  static constexpr int MAT = NB * AU_TILE;
+  static constexpr int SMEM = 3 * MAT + 64 + 1024;
+  static constexpr int CTAS = D == 16 ? 4 : (D == 32 ? 2 : 1);
+};
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// VIS: 0 = no probabilities, 1 = packed rows of 65 floats, 2 = rows padded to `pld` floats (pld % 8 == 0)
+template <int D, int VIS>
+__global__ void __launch_bounds__(128, AfCfg<D>::CTAS)
+attn_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmCtx,
+                     float* __restrict__ probs, int units, int groups, float scale_log2e, int pld, int round_out) {
+  using Cfg = AfCfg<D>;
+  constexpr int HEADS = AT_A / D;
+  constexpr int KSTEPS = D / 8;
+  constexpr int NT = 9;
+  constexpr int DT = D / 8;
+  constexpr int MAT = Cfg::MAT, NB = Cfg::NB, UC = Cfg::UC;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sq = smem_u32(smem), sk = sq + MAT, sv = sk + MAT;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 3 * MAT);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQkv);
+    prefetch_tmap(&tmCtx);
+    mbar_init(full, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_trigger();
+  pdl_wait();
+  const int hq = blockIdx.x % groups;      // the grid is a multiple of `groups`: a CTA keeps its head group
+  const int c0 = hq * UC;                  // first float column of the unit inside q (and k, v, ctx)
+  const int hc = warp * D * 4;             // byte column of this warp's head inside the unit
+  const int h = hq * 4 + warp;             // head index
+
+  int it = 0;
+  for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+    const int b = u / groups;
+    const int row_g = b * AT_S;
+    if (threadIdx.x == 0) {
+      bulk_wait_read0();                   // the previous unit's context boxes have left shared memory
+      mbar_arrive_expect_tx(full, 3 * NB * AT_S * 128);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        tma_load_2d(smem + j * AU_TILE, &tmQkv, full, c0 + 32 * j, row_g);
+        tma_load_2d(smem + MAT + j * AU_TILE, &tmQkv, full, AT_A + c0 + 32 * j, row_g);
+        tma_load_2d(smem + 2 * MAT + j * AU_TILE, &tmQkv, full, 2 * AT_A + c0 + 32 * j, row_g);
+      }
+    }
+    mbar_wait(full, it & 1);
+    // round V to tf32 in place, once (every V element feeds five query tiles); Q and K stay fp32 - their products are
+    // split below
+    for (int i = threadIdx.x; i < NB * AT_S * 8; i += 128) {
+      const int tile = 2 * NB + i / (AT_S * 8), rem = i % (AT_S * 8);
+      float4* p4 = reinterpret_cast<float4*>(smem + tile * AU_TILE + rem * 16);
+      float4 v = *p4;
+      v.x = __uint_as_float(to_tf32(v.x)); v.y = __uint_as_float(to_tf32(v.y));
+      v.z = __uint_as_float(to_tf32(v.z)); v.w = __uint_as_float(to_tf32(v.w));
+      *p4 = v;
+    }
+    __syncthreads();
+
+#pragma unroll 1
+    for (int rt = 0; rt < 5; ++rt) {
+      const int r0 = rt * 16;
+      // S = Q K^T as a 3xTF32 product (x = hi + lo, hi = tf32(x), lo = tf32(x - hi); q_lo k_hi + q_hi k_lo + q_hi k_hi):
+      // the scores go through exp, where a plain tf32 product (2^-11 relative on both operands) costs ~1e-2 relative
+      // on the probabilities of sharp rows.  The arithmetic is tiny next to the memory traffic.
+      uint32_t qh[KSTEPS][4], ql[KSTEPS][4];
+      {
+        const int row = min(r0 + (lane & 7) + ((lane >> 3) & 1) * 8, AT_S - 1);
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          uint32_t f[4];
+          ldsm_x4(au_addr(sq, row, hc + ks * 32 + (lane >> 4) * 16), f[0], f[1], f[2], f[3]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            qh[ks][i] = to_tf32(__uint_as_float(f[i]));
+            ql[ks][i] = to_tf32(__uint_as_float(f[i]) - __uint_as_float(qh[ks][i]));
+          }
+        }
+      }
+      float s[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        const int key = min(nt * 8 + (lane & 7), AT_S - 1);
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          uint32_t f0, f1;
+          ldsm_x2(au_addr(sk, key, hc + ks * 32 + ((lane >> 3) & 1) * 16), f0, f1);
+          const uint32_t h0 = to_tf32(__uint_as_float(f0)), h1 = to_tf32(__uint_as_float(f1));
+          const uint32_t l0 = to_tf32(__uint_as_float(f0) - __uint_as_float(h0)), l1 = to_tf32(__uint_as_float(f1) - __uint_as_float(h1));
+          mma_tf32(s[nt], ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3], h0, h1);
+          mma_tf32(s[nt], qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], l0, l1);
+          mma_tf32(s[nt], qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], h0, h1);
+        }
+      }
+      // softmax over the 65 valid keys: n-tiles 0..7 are valid in every lane, key 64 is element [0] / [2] of n-tile 8
+      // in the lanes with t == 0
+      const bool tail = t == 0;
+      float mx0 = tail ? s[8][0] : -INFINITY, mx1 = tail ? s[8][2] : -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float m0 = mx0 * scale_log2e, m1 = mx1 * scale_log2e;
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = exp2f(fmaf(s[nt][0], scale_log2e, -m0));
+        s[nt][1] = exp2f(fmaf(s[nt][1], scale_log2e, -m0));
+        s[nt][2] = exp2f(fmaf(s[nt][2], scale_log2e, -m1));
+        s[nt][3] = exp2f(fmaf(s[nt][3], scale_log2e, -m1));
+        sum0 += s[nt][0] + s[nt][1];
+        sum1 += s[nt][2] + s[nt][3];
+      }
+      s[8][0] = tail ? exp2f(fmaf(s[8][0], scale_log2e, -m0)) : 0.f;
+      s[8][2] = tail ? exp2f(fmaf(s[8][2], scale_log2e, -m1)) : 0.f;
+      s[8][1] = s[8][3] = 0.f;
+      sum0 += s[8][0];
+      sum1 += s[8][2];
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+      const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] *= inv0; s[nt][1] *= inv0;
+        s[nt][2] *= inv1; s[nt][3] *= inv1;
+      }
+      const int row0 = r0 + g, row1 = r0 + g + 8;
+      const bool fullt = rt < 4;
+      const bool w0 = fullt || g == 0, w1 = fullt;
+      if constexpr (VIS == 2) {
+        float* p0 = probs + ((size_t)(b * HEADS + h) * AT_S + row0) * pld + 2 * t;
+        float* p1 = p0 + 8 * (size_t)pld;
+#pragma unroll
+        for (int nt = 0; nt < 9; ++nt) {
+          st_global_f2_if(w0, p0 + nt * 8, s[nt][0], s[nt][1]);
+          st_global_f2_if(w1, p1 + nt * 8, s[nt][2], s[nt][3]);
+        }
+      }
+      if constexpr (VIS == 1) {
+        // packed rows of 65 floats start at alternating 8-byte phases: see attn_fwd_tc_kernel
+        const int bh = b * HEADS + h;
+        const bool odd = ((bh + row0) & 1) != 0;
+        float* p0 = probs + ((size_t)bh * AT_S + row0) * AT_S + 2 * t + (odd ? 1 : 0);
+        float* p1 = p0 + 8 * AT_S;
+        const int src = (lane & ~3) | ((t + 1) & 3);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const float n0 = __shfl_sync(0xffffffffu, tail ? s[nt + 1][0] : s[nt][0], src);
+          const float n1 = __shfl_sync(0xffffffffu, tail ? s[nt + 1][2] : s[nt][2], src);
+          const float2 v0 = make_float2(odd ? s[nt][1] : s[nt][0], odd ? n0 : s[nt][1]);
+          const float2 v1 = make_float2(odd ? s[nt][3] : s[nt][2], odd ? n1 : s[nt][3]);
+          st_global_f2_if(w0, p0 + nt * 8, v0.x, v0.y);
+          st_global_f2_if(w1, p1 + nt * 8, v1.x, v1.y);
+        }
+        const int off = odd ? -1 : 64;
+        st_global_f1_if(tail && w0, p0 + off, odd ? s[0][0] : s[8][0]);
+        st_global_f1_if(tail && w1, p1 + off, odd ? s[0][2] : s[8][2]);
+      }
+      // O = P V.  An accumulator tile holds columns (2t, 2t+1) where the A fragment wants (t, t+4): the reduction runs
+      // over keys in the order (2t | 2t+1) - k-slot t is key 8 kk + 2t, slot t+4 is key 8 kk + 2t + 1 - and V is read
+      // in the same order
+      float o[DT][4];
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < NT; ++kk) {
+        const uint32_t a0 = to_tf32(s[kk][0]), a1 = to_tf32(s[kk][2]), a2 = to_tf32(s[kk][1]), a3 = to_tf32(s[kk][3]);
+        const int key0 = min(kk * 8 + 2 * t, AT_S - 1), key1 = min(kk * 8 + 2 * t + 1, AT_S - 1);
+#pragma unroll
+        for (int dt = 0; dt < DT; ++dt) {
+          const uint32_t b0 = ld_shared_u32(au_addr(sv, key0, hc + (dt * 8 + g) * 4));
+          const uint32_t b1 = ld_shared_u32(au_addr(sv, key1, hc + (dt * 8 + g) * 4));
+          mma_tf32(o[dt], a0, a1, a2, a3, b0, b1);
+        }
+      }
+      // the context tile overwrites the Q tile it came from (only this warp reads that head's columns)
+      __syncwarp();
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) {
+        const int colb = hc + (dt * 8 + 2 * t) * 4;
+        float x0 = o[dt][0], x1 = o[dt][1], x2 = o[dt][2], x3 = o[dt][3];
+        if (round_out) {
+          x0 = __uint_as_float(to_tf32(x0)); x1 = __uint_as_float(to_tf32(x1));
+          x2 = __uint_as_float(to_tf32(x2)); x3 = __uint_as_float(to_tf32(x3));
+        }
+        if (w0) { st_shared_u32(au_addr(sq, row0, colb), __float_as_uint(x0)); st_shared_u32(au_addr(sq, row0, colb + 4), __float_as_uint(x1)); }
+        if (w1) { st_shared_u32(au_addr(sq, row1, colb), __float_as_uint(x2)); st_shared_u32(au_addr(sq, row1, colb + 4), __float_as_uint(x3)); }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) au_store_box(&tmCtx, sq + j * AU_TILE, c0 + 32 * j, row_g);
+      bulk_commit();
+    }
+  }
+  if (threadIdx.x == 0) bulk_wait0();
+}
+
+template <int D, int VIS>
+static int launch_attn_tf32_v(const CUtensorMap& tq, const CUtensorMap& tc, float* probs, int pld, int B, int round_out,
+                              cudaStream_t st) {
+  using Cfg = AfCfg<D>;
+  auto kern = attn_fwd_tf32_kernel<D, VIS>;
+  V3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  const int groups = AT_A / Cfg::UC;
+  const int units = B * groups;
+  int grid = sm_count() * Cfg::CTAS;
+  if (grid > units) grid = units;
+  grid -= grid % groups;
+  const float scale_log2e = 1.4426950408889634f / sqrtf((float)D);
+  V3_CUDA(launch_pdl(kern, dim3(grid), dim3(128), (size_t)Cfg::SMEM, st, tq, tc, probs, units, groups, scale_log2e, pld, round_out));
+  V3_LAUNCH_CHECK();
+  return VIT3D_OK;
+}
+template <int D>
+static int launch_attn_tf32(const CUtensorMap& tq, const CUtensorMap& tc, float* probs, int pld, int B, int round_out,
+                            cudaStream_t st) {
+  if (!probs) return launch_attn_tf32_v<D, 0>(tq, tc, probs, pld, B, round_out, st);
+  if (pld == AT_S) return launch_attn_tf32_v<D, 1>(tq, tc, probs, pld, B, round_out, st);
+  return launch_attn_tf32_v<D, 2>(tq, tc, probs, pld, B, round_out, st);
+}
+
+// fp32 q | k | v [B*65, 768] -> fp32 context [B*65, 256] (+ fp32 probabilities, rows of probs_ld floats)
+int tc_attn_fwd_tf32(const float* qkv, float* ctx, float* probs, int probs_ld, int B, int S, int heads, int D, int round_out,
+                     cudaStream_t st) {
+  if (!tc_attn_supported(S, heads, D)) V3_UNSUPPORTED("tf32 attention: unsupported shape S=%d heads=%d D=%d", S, heads, D);
+  if (B <= 0) return VIT3D_OK;
+  if (probs && probs_ld != S && (probs_ld % 8 || probs_ld < S + 7 || (reinterpret_cast<uintptr_t>(probs) & 31))) {
+    set_error("tf32 attention: padded probability rows are a multiple of 8 floats >= 72 in a 32-byte aligned buffer");
+    return VIT3D_ERR_INVALID;
+  }
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(ctx) & 15) || (reinterpret_cast<uintptr_t>(probs) & 7)) {
+    set_error("tf32 attention: qkv/ctx must be 16-byte aligned, probs 8-byte aligned");
+    return VIT3D_ERR_INVALID;
+  }
+  CUtensorMap tq, tc;
+  int rc = make_tmap_2d(&tq, qkv, 4, (long long)B * AT_S, 3 * AT_A, 3 * AT_A, AT_S, 32, 128);
+  if (rc != VIT3D_OK) return rc;
+  rc = make_tmap_2d(&tc, ctx, 4, (long long)B * AT_S, AT_A, AT_A, AT_S, 32, 128);
+  if (rc != VIT3D_OK) return rc;
+  if (D == 16) return launch_attn_tf32<16>(tq, tc, probs, probs_ld, B, round_out, st);
+  if (D == 32) return launch_attn_tf32<32>(tq, tc, probs, probs_ld, B, round_out, st);
+  return launch_attn_tf32<64>(tq, tc, probs, probs_ld, B, round_out, st);
+}
+
 template <int D>
 static int launch_attn_bwd(const void* dctx, const void* qkv, void* dqkv, float* db_q, float* db_k, float* db_v, int B,
                            cudaStream_t st) {

@@ -470,6 +470,14 @@ int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const 
   if (rc != VIT3D_OK) return rc;
   tc = ta;
   tp = ta;
+  if (ep.out_f32 && !ep.atomic && ep.row_group == 0 && ep.seg_rows == 0 && !ep.partial_ws && N % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 && tuning(VIT3D_TUNE_F32_BOX) != 0) {
+    // fp32 outputs (TF32 mode, fp32 data gradients): [32 x 16] boxes through the TMA unit instead of 64-byte row
+    // segments from the epilogue warps' load/store path
+    rc = make_tmap_2d(&tc, ep.out, 4, M, N, N, 32, 16, 64);
+    if (rc != VIT3D_OK) return rc;
+    ep.f32_box = 1;
+  }
   if (!ep.out_f32) {   // bf16 outputs leave through bulk tensor stores
     if (ep.row_group > 0 || ep.atomic) { set_error("tc_gemm: bf16 output with row remap / atomics is not supported"); return VIT3D_ERR_INVALID; }
     rc = make_tmap_2d(&tc, ep.out, 2, M, N, N, 32, 32, 64);

@@ -61,6 +61,9 @@ int tc_mlp_bwd(const void* gy, const void* w2_t, const void* w1_t, const void* d
 bool tc_attn_supported(int S, int heads, int D);
 // probs_ld: floats per probability row (S = the packed layout of the reference tensor; a multiple of 8 = padded rows)
 int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int probs_ld, int B, int S, int heads, int D, cudaStream_t st);
+// TF32 mode: fp32 q | k | v and context, mma.sync tf32 (k_tc_attn.cu); round_out: context rounded to tf32
+int tc_attn_fwd_tf32(const float* qkv, float* ctx, float* probs, int probs_ld, int B, int S, int heads, int D, int round_out,
+                     cudaStream_t st);
 // db_q / db_k / db_v (each [heads*D] fp32, all or none): += column sums of dq / dk / dv (the q, k, v bias gradients)
 int tc_attn_bwd(const void* dctx, const void* qkv, void* dqkv, float* db_q, float* db_k, float* db_v, int B, int S,
                 int heads, int D, cudaStream_t st);

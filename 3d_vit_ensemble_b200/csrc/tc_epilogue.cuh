@@ -20,6 +20,7 @@ struct TcEpilogue {
   int out_f32 = 1;
   int act = 0;
   int row_group = 0;                // >0: out row = m + m / row_group + 1
+  int f32_box = 0;                  // fp32 output leaves as [32 x 16] TMA boxes through tmC (dense rows, no row remap / atomics)
   int atomic = 0;                   // accumulate (split-K): 1 = fp32 vector atomics, 2 = TMA reduce-add boxes (tmC / tmPre / tmX per segment)
   int vols_per_tile = 0;            // patch-embedding mode: volumes per 128-row tile
   int round_tf32 = 0;               // fp32 output is the operand of a TF32 GEMM: round to nearest tf32
@@ -271,6 +272,10 @@ __device__ __forceinline__ void epilogue_rows(const TcEpilogue& ep, const CUtens
         }
       }
       tmem_ld_wait();
+      if (ep.f32_box) {                 // the previous round's box has left the staging tile
+        if (lane == 0) bulk_store_wait_read();
+        __syncwarp();
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) st_shared_v4(my_row + ((j ^ sw) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
       __syncwarp();
@@ -300,9 +305,21 @@ __device__ __forceinline__ void epilogue_rows(const TcEpilogue& ep, const CUtens
               if (ep.act == VIT3D_ACT_GELU) { v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w); }
               v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w;
               if (ep.round_tf32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
-              *reinterpret_cast<float4*>(o) = v;
+              if (ep.f32_box)     // finished values go back to their staging slot; the [32 x 16] box leaves by one TMA store
+                st_shared_v4(stage + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4), __float_as_uint(v.x), __float_as_uint(v.y),
+                             __float_as_uint(v.z), __float_as_uint(v.w));
+              else
+                *reinterpret_cast<float4*>(o) = v;
             }
           }
+        }
+      }
+      if (ep.f32_box) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tmC, stage, n_base + c, m_base);
+          bulk_store_commit();
         }
       }
       __syncwarp();

@@ -46,6 +46,41 @@ def test_attention_bf16(heads, B, vis, threads):
         assert float((probs.sum(-1) - 1).abs().max()) < 1e-5
 
 
+@pytest.mark.parametrize("heads", [4, 8, 16])
+@pytest.mark.parametrize("B", [1, 3, 149, 700])
+@pytest.mark.parametrize("vis", [True, False])
+def test_attention_tf32_mode(heads, B, vis):
+    """TF32-mode attention (fp32 q | k | v, mma.sync tf32 in (volume, 4-head) units) against fp64 softmax attention, and
+    against the generic fp32 SIMT kernel it replaces: fp32-grade probabilities (3xTF32 scores), a context that differs
+    by the tf32 rounding of P and V."""
+    torch.manual_seed(B * 29 + heads)
+    S, A = 65, 256
+    qkv = torch.randn(B, S, 3 * A, device=DEV) * 1.5
+    out = {}
+    for kern in (1, 0):
+        ctx = torch.full((B, S, A), float("nan"), device=DEV)
+        probs = torch.full((B, heads, S, S), float("nan"), device=DEV) if vis else None
+        lib().vit3d_set_tuning(9, kern)
+        try:
+            call("vit3d_attn_fwd", ptr(qkv), ptr(ctx), ptr(probs), B, S, heads, A // heads, PREC["tf32"], stream())
+            torch.cuda.synchronize()
+        finally:
+            lib().vit3d_set_tuning(9, 1)
+        out[kern] = (ctx, probs)
+    rc, rp = ref_attention(qkv, heads)
+    ctx, probs = out[1]
+    err = float((ctx.double() - rc).abs().max())
+    scale = float(rc.abs().max())
+    assert np.isfinite(err) and err < 1.5e-3 * scale, (err, scale)   # P and V rounded to tf32 (2^-11 relative each)
+    rel = float((ctx.double() - rc).norm() / rc.norm())
+    assert rel < 5e-4, rel
+    assert float((ctx - out[0][0]).abs().max()) < 1.5e-3 * scale
+    if vis:
+        perr = float((probs.double() - rp).abs().max())
+        assert np.isfinite(perr) and perr < 2e-5, perr         # scores are a 3xTF32 product: fp32-grade probabilities
+        assert float((probs.sum(-1) - 1).abs().max()) < 1e-5
+
+
 @pytest.mark.parametrize("kern", [1, 0])
 @pytest.mark.parametrize("heads", [4, 8, 16])
 @pytest.mark.parametrize("B", [1, 3, 149, 700])
