@@ -123,7 +123,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * MAXST + 5);
 
   const bool stat = stationary != 0;
-  const bool tall = mn_major == 2;      // 256 x BN weight-gradient tile: A stage doubles, both TMEM buffers form ONE accumulator
+  const bool tall = (mn_major & 2) != 0;   // 256 x BN tile: the A stage doubles, both TMEM buffers form ONE accumulator pair
+  const bool mnm = (mn_major & 1) != 0;    // both operands MN-major (weight gradients)
   const int STAGES = stat ? Lay::STAT_STAGES : (tall ? Lay::OPER_BYTES / (Cfg::STAGE_BYTES + Cfg::A_BYTES) : Lay::STREAM_STAGES);
   const int stage_bytes = stat ? Cfg::A_BYTES : (tall ? Cfg::STAGE_BYTES + Cfg::A_BYTES : Cfg::STAGE_BYTES);
   uint8_t* ring = stat ? smem + TC_SLAB_BYTES : smem;
@@ -131,7 +132,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // warp index through a shuffle: warp-uniform for the compiler, so the role branches are uniform control flow
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   // patch mode passes the k-block count as K; MN-major stages hold 64 reduction rows
-  const int nkb = patch_blocks > 0 ? K : (mn_major ? (K + 63) / 64 : (K + BLOCK_K - 1) / BLOCK_K);
+  const int nkb = patch_blocks > 0 ? K : ((mn_major & 1) ? (K + 63) / 64 : (K + BLOCK_K - 1) / BLOCK_K);
   const int kb_per = (nkb + splits - 1) / splits;
 
   if (warp == 0 && lane == 0) {
@@ -168,6 +169,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       // L2 look-ahead (tiles): deep-K tiles last long, one tile ahead is enough; K = 256 tiles need ~4
       const int l2_ahead = (patch_blocks > 0 || mn_major || splits > 1) ? 0 : (nkb <= 8 ? ep.l2_ahead : min(ep.l2_ahead, 1));
+      const int a_bytes = tall ? 2 * Cfg::A_BYTES : Cfg::A_BYTES;
       while (ti.next()) {
         const int kb0 = ti.split * kb_per, kb1 = min(nkb, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -180,13 +182,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // patch row i = kb / patch_blocks, floats [32*(kb % patch_blocks), +32) of that row (zero-filled
             // past the row end in both operands).
             const int i = kb / patch_blocks, c0 = (kb % patch_blocks) * 32;
-            tma_load_5d(sa, &tmA, &full_bar[stage], c0, 0, i, 0, ti.tm * ep.vols_per_tile);
-            tma_load_3d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], c0, i, ti.tn * BN);
-          } else if (mn_major) {
+            if (tall) {       // 256 token rows: two boxes of 128 / P volumes each
+              tma_load_5d(sa, &tmA, &full_bar[stage], c0, 0, i, 0, 2 * ti.tm * ep.vols_per_tile);
+              tma_load_5d(sa + Cfg::A_BYTES, &tmA, &full_bar[stage], c0, 0, i, 0, (2 * ti.tm + 1) * ep.vols_per_tile);
+            } else {
+              tma_load_5d(sa, &tmA, &full_bar[stage], c0, 0, i, 0, ti.tm * ep.vols_per_tile);
+            }
+            tma_load_3d(sa + a_bytes, &tmB, &full_bar[stage], c0, i, ti.tn * BN);
+          } else if (mnm) {
             // both operands MN-major (weight gradients: dW = dY^T X reduces over the token rows): a stage
             // holds 64 reduction rows; each 64-column block is one {64 cols x 64 rows} box = 8 KB
             // (mn_major == 2: the tile spans 256 output rows = two accumulators sharing the B operand)
-            const int a_blocks = mn_major == 2 ? 2 * TC_BLOCK_M / 64 : TC_BLOCK_M / 64;
+            const int a_blocks = tall ? 2 * TC_BLOCK_M / 64 : TC_BLOCK_M / 64;
             for (int j = 0; j < a_blocks; ++j)
               tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], ti.tm * (a_blocks * 64) + 64 * j, kb * 64);
 #pragma unroll
@@ -211,13 +218,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // schedule - waits, tcgen05.mma, commits (an election + __syncwarp per k-block costs ~60 cycles per MMA:
     // tools/mma_pipe_bench.cu, k_tc_mlp2.cu)
     if (elect_one()) {
-      const uint32_t idesc = make_idesc(TF32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16, TC_BLOCK_M, BN, mn_major ? 1 : 0,
-                                        mn_major ? 1 : 0);
+      const uint32_t idesc = make_idesc(TF32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16, TC_BLOCK_M, BN, mnm ? 1 : 0, mnm ? 1 : 0);
       // K-major SW128: 8-row groups 1024 B apart, K advances 32 B inside the 128 B swizzle row.
       // MN-major SW128: 64-element MN blocks 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO),
       //                 one MMA (K = 16) consumes two K groups -> advance 2048 B.
-      const uint32_t lbo = mn_major ? 8192u : 16u;
-      const uint64_t kstep = mn_major ? (2048u >> 4) : (32u >> 4);       // descriptor address units of 16 B
+      const uint32_t lbo = mnm ? 8192u : 16u;
+      const uint64_t kstep = mnm ? (2048u >> 4) : (32u >> 4);            // descriptor address units of 16 B
       const uint64_t ring_desc = make_smem_desc(smem_u32(ring), lbo, 1024, UMMA_LAYOUT_SW128);
       const uint64_t slab_desc = make_smem_desc(smem_u32(smem), lbo, 1024, UMMA_LAYOUT_SW128);
       TileIter ti(stat, tiles_m, tiles_n, splits);
@@ -320,9 +326,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int h = 0; h < 2; ++h) {
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * BN + part * CW;
             const int m_base = ti.tm * (2 * TC_BLOCK_M) + h * TC_BLOCK_M + q * 32;
-            const int seg = ep.seg_rows > 0 ? m_base / ep.seg_rows : 0;
-            const CUtensorMap* tr = seg == 0 ? &tmC : (seg == 1 ? &tmPre : &tmX);
-            epilogue_reduce_f32<CW>(tr, taddr, stage, lane, m_base - seg * ep.seg_rows, n_base, N);
+            if (ep.atomic == 2) {
+              const int seg = ep.seg_rows > 0 ? m_base / ep.seg_rows : 0;
+              const CUtensorMap* tr = seg == 0 ? &tmC : (seg == 1 ? &tmPre : &tmX);
+              epilogue_reduce_f32<CW>(tr, taddr, stage, lane, m_base - seg * ep.seg_rows, n_base, N);
+            } else {
+              epilogue_rows<CW, !TF32>(ep, &tmC, &tmPre, taddr, stage, lane, m_base, n_base, M, N);
+            }
           }
           tc_fence_before();
           __syncwarp();
@@ -431,7 +441,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     V3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay::SMEM_BYTES));
     configured_dev = dev;
   }
-  const int tiles_m = ceil_div(M, mn_major == 2 ? 2 * TC_BLOCK_M : TC_BLOCK_M), tiles_n = ceil_div(N, BN);
+  const int tiles_m = ceil_div(M, (mn_major & 2) ? 2 * TC_BLOCK_M : TC_BLOCK_M), tiles_n = ceil_div(N, BN);
   const int total = tiles_m * tiles_n * splits;
   const int sms = sm_count();
   int grid = total < sms ? total : sms;
@@ -621,7 +631,7 @@ int tc_gemm_wgrad_seg(const void* A, const void* B, float* out, float* out1, flo
     }
     ep.atomic = 2;
   }
-  if (tall) return launch_tc<false, 256>(ta, tb, tc, tp, ep, Mo, No, Kred, splits, false, st, 0, 2, &tx);
+  if (tall) return launch_tc<false, 256>(ta, tb, tc, tp, ep, Mo, No, Kred, splits, false, st, 0, 3, &tx);
   if (bn == 256) return launch_tc<false, 256>(ta, tb, tc, tp, ep, Mo, No, Kred, splits, false, st, 0, 1, &tx);
   if (bn == 128) return launch_tc<false, 128>(ta, tb, tc, tp, ep, Mo, No, Kred, splits, false, st, 0, 1, &tx);
   return launch_tc<false, 64>(ta, tb, tc, tp, ep, Mo, No, Kred, splits, false, st, 0, 1, &tx);
@@ -724,6 +734,11 @@ int tc_patch_embed_fwd(const float* x, const float* w, const float* bias, const 
   }
   TcEpilogue ep;
   ep.bias = bias; ep.rowadd = pos; ep.row_group = P; ep.out = tokens; ep.out_f32 = 1; ep.vols_per_tile = vpt;
+  // 256-row tiles (two accumulators over one weight k-block): 64 KB stages of which 32 KB come from HBM, 1024 MMA
+  // cycles each - three stages in flight cover the ~3 k cycles of an HBM read, where four 48 KB stages of 512 cycles
+  // (16 KB from HBM) left the tensor pipe waiting two thirds of the time
+  if (bn == 256 && tuning(VIT3D_TUNE_PATCH_TALL) != 0 && M >= 4 * TC_BLOCK_M * sm_count() / 2)
+    return launch_tc<true, 256>(ta, tb, ta, ta, ep, M, N, nkb, 1, false, st, pblocks, 2);
   if (bn == 256) return launch_tc<true, 256>(ta, tb, ta, ta, ep, M, N, nkb, 1, false, st, pblocks);
   if (bn == 128) return launch_tc<true, 128>(ta, tb, ta, ta, ep, M, N, nkb, 1, false, st, pblocks);
   return launch_tc<true, 64>(ta, tb, ta, ta, ep, M, N, nkb, 1, false, st, pblocks);

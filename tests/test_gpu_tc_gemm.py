@@ -58,10 +58,13 @@ def test_tc_linear_matches_fp64(prec, shape, mode):
         assert errp <= tol, (errp, tol)
 
 
-@pytest.mark.parametrize("B", [1, 2, 3, 37, 597])
+@pytest.mark.parametrize("tall", [1, 0])
+@pytest.mark.parametrize("B", [1, 2, 3, 37, 597, 600])
 @pytest.mark.parametrize("H", [256, 64])
-def test_tc_patch_embedding_matches_oracle(B, H):
-    """TMA-im2col TF32 patch embedding (+bias, +position rows, cls rows) vs the fp64 oracle."""
+def test_tc_patch_embedding_matches_oracle(B, H, tall):
+    """TMA-im2col TF32 patch embedding (+bias, +position rows, cls rows) vs the fp64 oracle; batches of >= 592 volumes
+    take 256-row tiles (tall=1; 597 volumes leave the last tile's second half ragged)."""
+    lib().vit3d_set_tuning(11, tall)
     from oracle import vit3d_oracle as O
     from vit3d_b200.models.modeling import Embeddings
     cfg = vit3d_b200.get_config(16, 128, 1, H, 4)
@@ -72,8 +75,11 @@ def test_tc_patch_embedding_matches_oracle(B, H):
     emb.precision = "bf16"
     emb.to(DEV).eval()
     x = O.synth_volumes(B, seed=B)
-    with torch.no_grad():
-        got = emb(x.to(DEV)).cpu().double()
+    try:
+        with torch.no_grad():
+            got = emb(x.to(DEV)).cpu().double()
+    finally:
+        lib().vit3d_set_tuning(11, 1)
     ref = O.embeddings({k: v.double() for k, v in sd.items()}, cfg, x.double())
     scale = float(ref.abs().max())
     err = float((got - ref).abs().max())
