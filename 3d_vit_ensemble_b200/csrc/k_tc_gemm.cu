@@ -68,6 +68,20 @@ struct TileIter {
       w = (int)blockIdx.x - (int)gridDim.x;
     }
   }
+  // the tile after the current one, without advancing (false: this was the last one)
+  __device__ bool peek(int& tm2, int& tn2) const {
+    if (stat) {
+      tm2 = tm + cpn;
+      tn2 = tn;
+      return tm2 < tiles_m;
+    }
+    const int w2 = w + (int)gridDim.x;
+    if (w2 >= total) return false;
+    const int tile = w2 / splits;
+    tn2 = tile % tiles_n;
+    tm2 = tile / tiles_n;
+    return true;
+  }
   __device__ bool next() {
     if (stat) {
       tm += cpn;
@@ -273,31 +287,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // training fc1: a thread's keep bits (CW columns of its row) are fetched one tile AHEAD - the epilogue is the
     // bottleneck of that GEMM (accumulators are ready long before), so a load issued at the top of the tile would
     // expose its whole global-memory latency
+    constexpr bool KEEP = EPI >= 0 && (EPI & 8) != 0;
     uint32_t keep_nx[CW / 32];
-    auto load_keep = [&](const TileIter& tt) {
-      if constexpr (EPI >= 0 && (EPI & 8) != 0) {
-        const int m = tt.tm * TC_BLOCK_M + q * 32 + lane;
+    auto load_keep = [&](int tm2, int tn2) {
 #pragma unroll
-        for (int j = 0; j < CW / 32; ++j) keep_nx[j] = ep.drop_bits == nullptr ? 0xffffffffu : 0u;
-        if (ep.drop_bits != nullptr && m < M) {
-          const uint32_t* drop_row = ep.drop_bits + (((long long)m * N + tt.tn * BN + part * CW) >> 5);
+      for (int j = 0; j < CW / 32; ++j) keep_nx[j] = ep.drop_bits == nullptr ? 0xffffffffu : 0u;
+      const int m = tm2 * TC_BLOCK_M + q * 32 + lane;
+      if (ep.drop_bits != nullptr && m < M) {
+        const uint32_t* drop_row = ep.drop_bits + (((long long)m * N + tn2 * BN + part * CW) >> 5);
 #pragma unroll
-          for (int j = 0; j < CW / 32; ++j) keep_nx[j] = __ldg(drop_row + j);
-        }
+        for (int j = 0; j < CW / 32; ++j) keep_nx[j] = __ldg(drop_row + j);
       }
     };
-    bool more = ti.next();
-    if (more) load_keep(ti);
-    TileIter nx = ti;
-    bool more_nx = false;
-    for (; more; ++it, ti = nx, more = more_nx) {
+    for (; ti.next(); ++it) {
       uint32_t keep[CW / 32];
+      if constexpr (KEEP) {
+        if (it == 0) load_keep(ti.tm, ti.tn);
 #pragma unroll
-      for (int j = 0; j < CW / 32; ++j) keep[j] = keep_nx[j];
-      nx = ti;
-      more_nx = nx.next();
-      if (more_nx) load_keep(nx);
-      const int buf = it & 1;
+        for (int j = 0; j < CW / 32; ++j) keep[j] = keep_nx[j];
+        int tm2, tn2;
+        if (ti.peek(tm2, tn2)) load_keep(tm2, tn2);
+      }
+      const int buf = tall ? 0 : (it & 1);
       if constexpr (EPI >= 0 && (EPI & 1) != 0) {
         if (ti.tn != cur_tn) {
           // stage this n-tile's bias (fp32 + packed half) for all epilogue warps; once per CTA under the
@@ -316,52 +327,43 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           cur_tn = ti.tn;
         }
       }
-      if (tall) {
-        // weight-gradient tile of 256 rows: accumulator h holds rows [128 h, 128 h + 128)
-        if constexpr (EPI < 0) {
-          mbar_wait(&tmem_full[0], it & 1);
-          tc_fence_after();
-          const int n_base = ti.tn * BN + part * CW;
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * BN + part * CW;
-            const int m_base = ti.tm * (2 * TC_BLOCK_M) + h * TC_BLOCK_M + q * 32;
-            if (ep.atomic == 2) {
-              const int seg = ep.seg_rows > 0 ? m_base / ep.seg_rows : 0;
-              const CUtensorMap* tr = seg == 0 ? &tmC : (seg == 1 ? &tmPre : &tmX);
-              epilogue_reduce_f32<CW>(tr, taddr, stage, lane, m_base - seg * ep.seg_rows, n_base, N);
-            } else {
-              epilogue_rows<CW, !TF32>(ep, &tmC, &tmPre, taddr, stage, lane, m_base, n_base, M, N);
-            }
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[0]);
-        }
-        continue;
-      }
-      const int m_base = ti.tm * TC_BLOCK_M + q * 32, n_base = ti.tn * BN + part * CW;
-      mbar_wait(&tmem_full[buf], (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + part * CW;
       if constexpr (EPI >= 0) {
+        const int m_base = ti.tm * TC_BLOCK_M + q * 32, n_base = ti.tn * BN + part * CW;
+        mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + part * CW;
         epilogue_bf16_lean<CW, EPI, WIDE>(&tmC, &tmPre, taddr, stage, smem_u32(bias_stage) + part * CW * 4,
                                     smem_u32(bias_stage) + BN * 4 + part * CW * 2, lane, m_base, n_base, keep,
                                     ep.drop_scale);
       } else {
-        if (ep.atomic == 2) {
-          // weight gradients: boxes added into the output by the TMA unit; one tensor map per output segment
-          const int seg = ep.seg_rows > 0 ? m_base / ep.seg_rows : 0;
-          const CUtensorMap* tr = seg == 0 ? &tmC : (seg == 1 ? &tmPre : &tmX);
-          epilogue_reduce_f32<CW>(tr, taddr, stage, lane, m_base - seg * ep.seg_rows, n_base, N);
-        } else if (ep.partial_ws != nullptr) {
-          TcEpilogue pe = ep;                       // this work item's dense partial tile
-          pe.out = ep.partial_ws + (size_t)ti.w * (TC_BLOCK_M * BN);
-          pe.atomic = 0;
-          pe.seg_rows = 0;
-          epilogue_rows<CW, !TF32>(pe, &tmC, &tmPre, taddr, stage, lane, q * 32, part * CW, TC_BLOCK_M, BN);
-        } else {
-          epilogue_rows<CW, !TF32>(ep, &tmC, &tmPre, taddr, stage, lane, m_base, n_base, M, N);
+        // generic epilogues: ONE call site per kernel variant (every inlined copy of epilogue_rows costs registers at
+        // the 96-register cap: two extra copies spilled ~440 bytes and slowed the patch embedding from 117 to 160 us).
+        // A tall tile (256 rows) is two passes over the accumulator pair: h = rows [128 h, 128 h + 128).
+        mbar_wait(&tmem_full[buf], tall ? (it & 1) : ((it >> 1) & 1));
+        tc_fence_after();
+        const int n_base = ti.tn * BN + part * CW;
+#pragma unroll 1
+        for (int h = 0; h < (tall ? 2 : 1); ++h) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (tall ? h : buf) * BN + part * CW;
+          const int m_base = tall ? ti.tm * (2 * TC_BLOCK_M) + h * TC_BLOCK_M + q * 32 : ti.tm * TC_BLOCK_M + q * 32;
+          if constexpr (EPI == EPI_WGRAD) {
+            if (ep.atomic == 2) {
+              // weight gradients: boxes added into the output by the TMA unit; one tensor map per output segment
+              const int seg = ep.seg_rows > 0 ? m_base / ep.seg_rows : 0;
+              const CUtensorMap* tr = seg == 0 ? &tmC : (seg == 1 ? &tmPre : &tmX);
+              epilogue_reduce_f32<CW>(tr, taddr, stage, lane, m_base - seg * ep.seg_rows, n_base, N);
+            } else {
+              // fp32 atomics into the (segmented) output, or this work item's dense partial tile
+              const bool part_ws = ep.partial_ws != nullptr;
+              epilogue_rows<CW, !TF32, false>(ep, &tmC, &tmPre, taddr, stage, lane, part_ws ? q * 32 : m_base,
+                                              part_ws ? part * CW : n_base, part_ws ? TC_BLOCK_M : M, part_ws ? BN : N,
+                                              part_ws ? (void*)(ep.partial_ws + (size_t)ti.w * (TC_BLOCK_M * BN)) : ep.out,
+                                              part_ws ? 0 : ep.atomic, part_ws ? 0 : ep.seg_rows);
+            }
+          } else {
+            epilogue_rows<CW, !TF32, EPI == EPI_GENERIC_DACT>(ep, &tmC, &tmPre, taddr, stage, lane, m_base, n_base, M, N, ep.out,
+                                                              ep.atomic, 0);
+          }
         }
       }
       tc_fence_before();
@@ -522,6 +524,11 @@ int tc_gemm(bool tf32, const void* A, const void* B, int M, int N, int K, const 
     V3_LEAN(128, 0) V3_LEAN(128, 1) V3_LEAN(128, 3) V3_LEAN(128, 7) V3_LEAN(128, 15)
 #undef V3_LEAN
   }
+  if (ep.store_dact) {
+    if (bn == 256) return launch_tc<false, 256, EPI_GENERIC_DACT>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
+    if (bn == 128) return launch_tc<false, 128, EPI_GENERIC_DACT>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
+    return launch_tc<false, 64, EPI_GENERIC_DACT>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
+  }
   if (bn == 256) return launch_tc<false, 256>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
   if (bn == 128) return launch_tc<false, 128>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
   return launch_tc<false, 64>(ta, tb, tc, tp, ep, M, N, K, splits, stationary, st);
@@ -567,9 +574,9 @@ int tc_gemm_wgrad_partial(const void* A, const void* B, float* ws, int Mo, int N
   if (rc != VIT3D_OK) return rc;
   TcEpilogue ep;
   ep.out = ws; ep.out_f32 = 1; ep.partial_ws = ws;
-  if (bn == 256) return launch_tc<false, 256>(ta, tb, ta, ta, ep, Mo, No, Kred, splits, false, st, 0, 1);
-  if (bn == 128) return launch_tc<false, 128>(ta, tb, ta, ta, ep, Mo, No, Kred, splits, false, st, 0, 1);
-  return launch_tc<false, 64>(ta, tb, ta, ta, ep, Mo, No, Kred, splits, false, st, 0, 1);
+  if (bn == 256) return launch_tc<false, 256, EPI_WGRAD>(ta, tb, ta, ta, ep, Mo, No, Kred, splits, false, st, 0, 1);
+  if (bn == 128) return launch_tc<false, 128, EPI_WGRAD>(ta, tb, ta, ta, ep, Mo, No, Kred, splits, false, st, 0, 1);
+  return launch_tc<false, 64, EPI_WGRAD>(ta, tb, ta, ta, ep, Mo, No, Kred, splits, false, st, 0, 1);
 }
 
 int tc_gemm_wgrad_seg(const void* A, const void* B, float* out, float* out1, float* out2, int seg_rows, int Mo, int No,
@@ -631,10 +638,10 @@ int tc_gemm_wgrad_seg(const void* A, const void* B, float* out, float* out1, flo
     }
     ep.atomic = 2;
   }
-  if (tall) return launch_tc<false, 256>(ta, tb, tc, tp, ep, Mo, No, Kred, splits, false, st, 0, 3, &tx);
-  if (bn == 256) return launch_tc<false, 256>(ta, tb, tc, tp, ep, Mo, No, Kred, splits, false, st, 0, 1, &tx);
-  if (bn == 128) return launch_tc<false, 128>(ta, tb, tc, tp, ep, Mo, No, Kred, splits, false, st, 0, 1, &tx);
-  return launch_tc<false, 64>(ta, tb, tc, tp, ep, Mo, No, Kred, splits, false, st, 0, 1, &tx);
+  if (tall) return launch_tc<false, 256, EPI_WGRAD>(ta, tb, tc, tp, ep, Mo, No, Kred, splits, false, st, 0, 3, &tx);
+  if (bn == 256) return launch_tc<false, 256, EPI_WGRAD>(ta, tb, tc, tp, ep, Mo, No, Kred, splits, false, st, 0, 1, &tx);
+  if (bn == 128) return launch_tc<false, 128, EPI_WGRAD>(ta, tb, tc, tp, ep, Mo, No, Kred, splits, false, st, 0, 1, &tx);
+  return launch_tc<false, 64, EPI_WGRAD>(ta, tb, tc, tp, ep, Mo, No, Kred, splits, false, st, 0, 1, &tx);
 }
 
 bool tc_wgrad_supported(int prec, int M, int N, int K) {
@@ -734,9 +741,9 @@ int tc_patch_embed_fwd(const float* x, const float* w, const float* bias, const 
   }
   TcEpilogue ep;
   ep.bias = bias; ep.rowadd = pos; ep.row_group = P; ep.out = tokens; ep.out_f32 = 1; ep.vols_per_tile = vpt;
-  // 256-row tiles (two accumulators over one weight k-block): 64 KB stages of which 32 KB come from HBM, 1024 MMA
-  // cycles each - three stages in flight cover the ~3 k cycles of an HBM read, where four 48 KB stages of 512 cycles
-  // (16 KB from HBM) left the tensor pipe waiting two thirds of the time
+  // optional 256-row tiles (two accumulators over one weight k-block, 64 KB stages of 1024 MMA cycles): measured
+  // 124 us against 117 us for 128-row tiles at batch 1024 (the single accumulator pair cannot overlap a tile's
+  // epilogue with the next tile's MMAs) - off by default
   if (bn == 256 && tuning(VIT3D_TUNE_PATCH_TALL) != 0 && M >= 4 * TC_BLOCK_M * sm_count() / 2)
     return launch_tc<true, 256>(ta, tb, ta, ta, ep, M, N, nkb, 1, false, st, pblocks, 2);
   if (bn == 256) return launch_tc<true, 256>(ta, tb, ta, ta, ep, M, N, nkb, 1, false, st, pblocks);

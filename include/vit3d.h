@@ -81,8 +81,9 @@ unsigned long long vit3d_launch_count(void);
  *                            (volume, 4-head) units; 0: the generic fp32 SIMT kernel.  Env VIT3D_ATTN_TF32.
  *   VIT3D_TUNE_F32_BOX       0 (default): fp32 GEMM outputs as 64-byte row segments stored by the epilogue warps; 1: dense rows
  *                            leave as [32 x 16] TMA boxes (measured equal in TF32 mode).  Env VIT3D_F32_BOX.
- *   VIT3D_TUNE_PATCH_TALL    1 (default): the TF32 patch-embedding GEMM of large batches runs 256-row tiles (two TMEM
- *                            accumulators sharing each weight k-block); 0: 128-row tiles.  Env VIT3D_PATCH_TALL.
+ *   VIT3D_TUNE_PATCH_TALL    0 (default): 128-row tiles; 1: the TF32 patch-embedding GEMM of large batches runs 256-row
+ *                            tiles (two TMEM accumulators sharing each weight k-block; measured 124 vs 117 us at
+ *                            batch 1024).  Env VIT3D_PATCH_TALL.
  *   VIT3D_TUNE_ATTN_BWD      1 (default): attention backward in (volume, 4-head) units, 4-warp CTAs, TMA boxes; 0: one
  *                            16-warp CTA per volume with per-row bulk copies.  Env VIT3D_ATTN_BWD. */
 enum { VIT3D_TUNE_EPI_PANEL = 0, VIT3D_TUNE_ATTN_THREADS = 1, VIT3D_TUNE_EPI_LEAN = 2, VIT3D_TUNE_STORE_WIDE = 3,

@@ -79,7 +79,7 @@ def test_tc_patch_embedding_matches_oracle(B, H, tall):
         with torch.no_grad():
             got = emb(x.to(DEV)).cpu().double()
     finally:
-        lib().vit3d_set_tuning(11, 1)
+        lib().vit3d_set_tuning(11, 0)
     ref = O.embeddings({k: v.double() for k, v in sd.items()}, cfg, x.double())
     scale = float(ref.abs().max())
     err = float((got - ref).abs().max())
