@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libvit3d_sm100.so")
 
 PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
 ACT_NONE, ACT_GELU = 0, 1
+SHADOW_TILE = 64          # include/vit3d.h VIT3D_SHADOW_TILE: tile edge of the vit3d_refresh_shadows job table
 
 
 class Vit3dError(RuntimeError):

@@ -486,7 +486,9 @@ int launch_colsum(const void* dy, int f32, float* db, int M, int N, cudaStream_t
   const int V = f32 ? 4 : 8;
   if (N % V == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
     const int gx = ceil_div(N, 32 * V);
-    int gy = (8 * sm_count()) / gx;
+    // two blocks per SM: every block ends in one atomic per column, and the L2 serialises the atomics of a column
+    // (512 blocks on 256 columns - the patch-embedding bias gradient - spent most of their 43 us there)
+    int gy = (2 * sm_count()) / gx;
     if (gy < 1) gy = 1;
     int rpb = ceil_div(M, gy);
     if (rpb < 32) rpb = 32;

@@ -69,8 +69,7 @@ __device__ __forceinline__ uint32_t gelu_h2(__half2 x) {
   uint32_t ti;
   asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
   const __half2 th = *reinterpret_cast<const __half2*>(&ti);
-  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
-  const __half2 y = __hfma2(hx, th, hx);
+  const __half2 y = __hfma2(x, th, x);        // 2 gelu(x): the factor 1/2 is applied to the fc2 accumulator (exact)
   return *reinterpret_cast<const uint32_t*>(&y);
 }
 

@@ -422,14 +422,18 @@ struct ShadowJob {
   const float* src;     // [rows, cols] fp32, dense
   void* dst;            // element (r, c) at dst[r * ld + c] (kind 1: dst[c * ld + r])
   int rows, cols, ld, kind;
-  int tile0;            // first 32 x 32 tile of this job in the launch
+  int tile0;            // first 64 x 64 tile (VIT3D_SHADOW_TILE) of this job in the launch
   int tiles_c;          // tiles per row of tiles
 };
 static_assert(sizeof(ShadowJob) == VIT3D_SHADOW_JOB_BYTES, "ShadowJob layout is part of the C ABI");
 
+// One CTA = one 64 x 64 tile (VIT3D_SHADOW_TILE): four 16-byte loads in flight per thread, 128-byte output rows
+// (16 bytes per thread).  (32 x 32 tiles with scalar loads and 64-byte output rows ran at 1.3 TB/s: 83 us for the 118 MB
+// of the conf-18 model; several of those tiles per CTA was slower still - the bound was bytes in flight, not CTA turnover.)
+constexpr int SH_T = VIT3D_SHADOW_TILE;
 __global__ void __launch_bounds__(256) refresh_shadows_kernel(const ShadowJob* __restrict__ jobs, int njobs,
                                                               unsigned* __restrict__ step_dev) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[SH_T][SH_T + 1];
   if (blockIdx.x == 0 && threadIdx.x == 0 && step_dev) *step_dev += 1u;
   const int t = blockIdx.x;
   int lo = 0, hi = njobs - 1;
@@ -439,33 +443,89 @@ __global__ void __launch_bounds__(256) refresh_shadows_kernel(const ShadowJob* _
   }
   const ShadowJob jb = jobs[lo];
   const int local = t - jb.tile0;
-  const int r0 = (local / jb.tiles_c) * 32, c0 = (local % jb.tiles_c) * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = r0 + ty + 8 * i, c = c0 + tx;
-    tile[ty + 8 * i][tx] = (r < jb.rows && c < jb.cols) ? jb.src[(size_t)r * jb.cols + c] : 0.f;
-  }
-  __syncthreads();
-  if (jb.kind == 1) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(jb.dst);
+  const int r0 = (local / jb.tiles_c) * SH_T, c0 = (local % jb.tiles_c) * SH_T;
+  const bool vec_in = (jb.cols & 3) == 0 && (reinterpret_cast<uintptr_t>(jb.src) & 15) == 0;
+  {
+    const int c4 = (threadIdx.x & 15) * 4, rr = threadIdx.x >> 4;       // 16 threads per row, 16 rows per pass
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int c = c0 + ty + 8 * i, r = r0 + tx;
-      if (c < jb.cols && r < jb.rows) o[(size_t)c * jb.ld + r] = __float2bfloat16(tile[tx][ty + 8 * i]);
+      const int r = r0 + rr + 16 * i, c = c0 + c4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < jb.rows) {
+        if (vec_in && c + 3 < jb.cols) {
+          v = *reinterpret_cast<const float4*>(jb.src + (size_t)r * jb.cols + c);
+        } else {
+          const float* p = jb.src + (size_t)r * jb.cols;
+          if (c < jb.cols) v.x = p[c];
+          if (c + 1 < jb.cols) v.y = p[c + 1];
+          if (c + 2 < jb.cols) v.z = p[c + 2];
+          if (c + 3 < jb.cols) v.w = p[c + 3];
+        }
+      }
+      float* d = &tile[rr + 16 * i][c4];
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+  }
+  __syncthreads();
+  const bool half_out = jb.kind == 0 || jb.kind == 1 || jb.kind == 2;
+  if (half_out) {
+    // 8 consecutive output elements per thread: rows of the tile (kinds 0, 2) or its columns (kind 1: transposed)
+    const bool tr = jb.kind == 1;
+    const int orows = tr ? jb.cols : jb.rows, ocols = tr ? jb.rows : jb.cols;      // extent of the output matrix
+    const int or0 = tr ? c0 : r0, oc0 = tr ? r0 : c0;
+    const bool vec_out = (jb.ld & 7) == 0 && (reinterpret_cast<uintptr_t>(jb.dst) & 15) == 0;
+    const int ch = (threadIdx.x & 7) * 8, rr = threadIdx.x >> 3;        // 8 threads per output row, 32 rows per pass
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int lr = rr + 32 * i;
+      const int orow = or0 + lr, ocol = oc0 + ch;
+      if (orow >= orows || ocol >= ocols) continue;
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = tr ? tile[ch + k][lr] : tile[lr][ch + k];
+      uint16_t* o = reinterpret_cast<uint16_t*>(jb.dst) + (size_t)orow * jb.ld + ocol;
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (jb.kind == 2) {
+          const __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+          w[k] = *reinterpret_cast<const uint32_t*>(&h);
+        } else {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+          w[k] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+      }
+      if (vec_out && ocol + 7 < ocols) {
+        *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (ocol + k < ocols) o[k] = (uint16_t)(w[k >> 1] >> (16 * (k & 1)));
+      }
     }
     return;
   }
+  // fp32 outputs (kind 3: rounded to tf32, kind 4: copy): 4 consecutive elements per thread
+  {
+    const bool vec_out = (jb.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(jb.dst) & 15) == 0;
+    const int c4 = (threadIdx.x & 15) * 4, rr = threadIdx.x >> 4;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = r0 + ty + 8 * i, c = c0 + tx;
-    if (r >= jb.rows || c >= jb.cols) continue;
-    const float v = tile[ty + 8 * i][tx];
-    const size_t o = (size_t)r * jb.ld + c;
-    if (jb.kind == 0) reinterpret_cast<__nv_bfloat16*>(jb.dst)[o] = __float2bfloat16(v);
-    else if (jb.kind == 2) reinterpret_cast<__half*>(jb.dst)[o] = __float2half_rn(v);
-    else if (jb.kind == 3) reinterpret_cast<float*>(jb.dst)[o] = round_tf32(v);
-    else reinterpret_cast<float*>(jb.dst)[o] = v;
+    for (int i = 0; i < 4; ++i) {
+      const int lr = rr + 16 * i;
+      const int r = r0 + lr, c = c0 + c4;
+      if (r >= jb.rows || c >= jb.cols) continue;
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = jb.kind == 3 ? round_tf32(tile[lr][c4 + k]) : tile[lr][c4 + k];
+      float* o = reinterpret_cast<float*>(jb.dst) + (size_t)r * jb.ld + c;
+      if (vec_out && c + 3 < jb.cols) {
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (c + k < jb.cols) o[k] = v[k];
+      }
+    }
   }
 }
 

@@ -169,9 +169,9 @@ class TrainPlan:
         for i, (src, (dst, rows, cols, ld, kind)) in enumerate(zip(self._job_src, self._job_rest)):
             if not src.is_contiguous() or src.dtype != torch.float32:
                 raise _lib.Vit3dError("fused training needs contiguous fp32 parameters")
-            tiles_c = (cols + 31) // 32
+            tiles_c = (cols + _lib.SHADOW_TILE - 1) // _lib.SHADOW_TILE
             arr[i] = (src.data_ptr(), dst, rows, cols, ld, kind, t0, tiles_c)
-            t0 += tiles_c * ((rows + 31) // 32)
+            t0 += tiles_c * ((rows + _lib.SHADOW_TILE - 1) // _lib.SHADOW_TILE)
         self.total_tiles = t0
         self.njobs = len(arr)
         host = torch.from_numpy(arr.view(np.uint8).copy())

@@ -273,6 +273,7 @@ int vit3d_adam_step(float* p, const float* g, float* m, float* v, long long n, f
  * sums, packed q|k|v weight gradients that land in three parameters, one-launch weight-shadow refresh. */
 #define VIT3D_MAX_DROP_SEGS 40
 #define VIT3D_SHADOW_JOB_BYTES 40
+#define VIT3D_SHADOW_TILE 64
 /* cudaMemsetAsync(p, 0, bytes) on `stream` (gradient arena zeroing without a framework fill kernel) */
 int vit3d_memset_zero(void* p, size_t bytes, vit3d_stream_t stream);
 /* 1 if the fused training step serves this model shape (B volumes of S tokens, hidden H, mlp width d) */
@@ -321,7 +322,8 @@ int vit3d_head_bwd(const float* dlogits, const float* encoded, const float* w, f
  *   { const float* src; void* dst; int rows, cols, ld, kind, tile0, tiles_c; }
  * src [rows, cols] dense fp32; element (r, c) goes to dst[r*ld + c] as bf16 (kind 0), fp16 (2), fp32 rounded to
  * TF32 (3) or fp32 (4), or to dst[c*ld + r] as bf16 (kind 1, transposed: the dgrad operand).  tile0 = index of the
- * job's first 32 x 32 tile in the launch, tiles_c = ceil(cols/32); total_tiles = sum over jobs.  step_dev (optional
+ * job's first VIT3D_SHADOW_TILE x VIT3D_SHADOW_TILE (64 x 64) tile in the launch, tiles_c = ceil(cols/64); total_tiles = sum
+ * over jobs.  step_dev (optional
  * device counter) is incremented by one: the dropout step of a CUDA-graph replay. */
 int vit3d_refresh_shadows(const void* jobs, int njobs, int total_tiles, unsigned* step_dev, vit3d_stream_t stream);
 /* training fc1 (modeling.py:119-121): act = Dropout(gelu(xn w1^T + b1)) (bf16) and, instead of the pre-activation,

@@ -73,6 +73,8 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(L, name), f"{name} declared in include/vit3d.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     assert _lib.lib().vit3d_version() == 100
+    # ABI constants the Python side mirrors
+    assert int(re.search(r"#define VIT3D_SHADOW_TILE (\d+)", hdr).group(1)) == _lib.SHADOW_TILE
 
 
 def test_no_cpu_fallback():

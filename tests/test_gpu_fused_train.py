@@ -225,6 +225,61 @@ def _gelu_fit(x):
     return 0.5 * x * (1 + t), 0.5 * (1 + t) + 0.5 * x * (1 - t * t) * (c0 + 3 * c1 * x2 + 5 * c2 * x2 * x2)
 
 
+def test_refresh_shadows_all_kinds_and_ragged_shapes():
+    """vit3d_refresh_shadows: one launch over a job table rewrites bf16 / transposed-bf16 / fp16 / tf32-rounded / fp32
+    copies of fp32 masters (64 x 64 tiles, vectorised where rows allow) - full tiles, ragged edges, row strides wider
+    than the matrix (the packed q|k|v shadow), unaligned destinations - and bumps the device step counter."""
+    import numpy as np
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    shapes = [(256, 3072, 0), (3072, 256, 1), (100, 70, 0), (100, 70, 1), (65, 33, 2), (256, 5120, 3), (1, 256, 4),
+              (130, 257, 3), (256, 256, 0), (77, 128, 1)]
+    srcs, dsts, refs, rows_ = [], [], [], []
+    arr = np.zeros(len(shapes) + 2, dtype=fused_train._JOB_DTYPE)
+    t0 = 0
+    T = _lib.SHADOW_TILE
+
+    def add(i, src, dst_ptr, rows, cols, ld, kind):
+        nonlocal t0
+        tc = (cols + T - 1) // T
+        arr[i] = (src.data_ptr(), dst_ptr, rows, cols, ld, kind, t0, tc)
+        t0 += tc * ((rows + T - 1) // T)
+
+    for i, (rows, cols, kind) in enumerate(shapes):
+        src = torch.randn(rows, cols, device=DEV, generator=gen)
+        if kind == 1:
+            ld = rows + (8 if rows % 8 == 0 else 3)
+            dst = torch.full((cols, ld), 7.0, device=DEV, dtype=torch.bfloat16)
+            ref = src.t().to(torch.bfloat16)
+            view = dst[:, :rows]
+        else:
+            ld = cols + (16 if cols % 8 == 0 else 5)
+            dt = {0: torch.bfloat16, 2: torch.float16, 3: torch.float32, 4: torch.float32}[kind]
+            dst = torch.full((rows, ld), 7.0, device=DEV, dtype=dt)
+            ref = src.to(dt)
+            if kind == 3:
+                b = src.view(torch.int32)
+                ref = (((b + 0x1000) & ~0x1FFF).view(torch.float32))            # round to nearest, ties away (cvt.rna)
+            view = dst[:, :cols]
+        add(i, src, dst.data_ptr(), rows, cols, ld, kind)
+        srcs.append(src); dsts.append((dst, view, ld)); refs.append(ref)
+    # the packed q|k|v shadow: two jobs into row blocks of ONE [512, 256] buffer
+    packed = torch.full((512, 256), 7.0, device=DEV, dtype=torch.bfloat16)
+    for j in range(2):
+        src = torch.randn(256, 256, device=DEV, generator=gen)
+        add(len(shapes) + j, src, packed.data_ptr() + j * 256 * 256 * 2, 256, 256, 256, 0)
+        srcs.append(src)
+    jobs = torch.from_numpy(arr.view(np.uint8).copy()).to(DEV)
+    step = torch.tensor([41], device=DEV, dtype=torch.int32)
+    _lib.call("vit3d_refresh_shadows", jobs.data_ptr(), len(arr), t0, step.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert int(step) == 42
+    for (dst, view, ld), ref, (rows, cols, kind) in zip(dsts, refs, shapes):
+        assert torch.equal(view, ref), (rows, cols, kind)
+        pad = dst[:, (rows if kind == 1 else cols):]
+        assert bool((pad == 7.0).all()), ("padding columns were written", rows, cols, kind)
+    assert torch.equal(packed[:256], srcs[-2].to(torch.bfloat16)) and torch.equal(packed[256:], srcs[-1].to(torch.bfloat16))
+
+
 @pytest.mark.parametrize("pair", [1, 0])
 @pytest.mark.parametrize("M,K,drop", [(16640, 3072, True), (256, 1024, False), (19500 + 76, 2048, True), (130, 3072, True), (1000, 256, True)])
 def test_linear_residual_dropout_layernorm_training_forward(M, K, drop, pair):
