@@ -388,6 +388,19 @@ def backward(model, saved, dloss: Optional[torch.Tensor] = None):
     """Gradients of every parameter from `saved` (see forward).  Accumulates into the parameters' `.grad`
     (flat arena) where possible; returns the tuple autograd expects (None where accumulated in place), in
     `model.parameters()` order."""
+    gen = backward_steps(model, saved, dloss, ())
+    while True:
+        try:
+            next(gen)
+        except StopIteration as e:
+            return e.value
+
+
+def backward_steps(model, saved, dloss: Optional[torch.Tensor] = None, cuts=()):
+    """`backward` as a generator: yields the Block index i after the backward of Block i when i is in `cuts` - every
+    gradient of the head, encoder_norm and Blocks >= i is complete at that point (data-parallel steps all-reduce that
+    part of the flat arena while the rest of the backward runs, graphs.GraphedTrainStep).  The generator's return value
+    is `backward`'s."""
     plan = plan_of(model)
     tr = model.transformer
     emb, enc = tr.embeddings, tr.encoder
@@ -469,6 +482,8 @@ def backward(model, saved, dloss: Optional[torch.Tensor] = None):
         if not wg.partial:
             for p_ in blk.parameters():
                 F._grad_done(p_)
+            if i in cuts and i > 0:
+                yield i
     wg.finish(st)                      # one launch: partial tiles of all 4 L weight-gradient GEMMs -> the gradients
     if wg.partial:
         for blk in reversed(list(enc.layer)):
@@ -508,6 +523,25 @@ class VitTrainFn(torch.autograd.Function):
 def loss(model, x, labels, pos_weight):
     """Autograd entry: `model(x, labels, weights)` in BF16 mode routes here when `supported`."""
     return VitTrainFn.apply(model, x, labels, pos_weight, *model.parameters())
+
+
+def loss_and_grads_steps(model, x, labels, pos_weight, cuts):
+    """`loss_and_grads` as a generator over the segments `backward_steps(cuts=...)` defines: yields the (static) loss
+    tensor after the forward + first backward segment and after every further segment but the last; returns it."""
+    with torch.no_grad():
+        lo, saved = forward(model, x, labels, pos_weight)
+        gen = backward_steps(model, saved, None, cuts)
+        while True:
+            try:
+                next(gen)
+            except StopIteration as e:
+                grads = e.value
+                break
+            yield lo
+    if any(g is not None for g in grads):
+        raise _lib.Vit3dError("loss_and_grads needs every parameter's .grad to be an fp32 buffer it can accumulate into "
+                              "(build an optim.FusedSGD / FusedAdam over model.parameters() first)")
+    return lo
 
 
 def loss_and_grads(model, x, labels, pos_weight):

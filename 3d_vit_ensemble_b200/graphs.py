@@ -172,18 +172,24 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model: torch.nn.Module, optimizer, warmup: int = 3, grad_scale: float = 1.0,
-                 data_parallel: bool = False, group=None):
+                 data_parallel: bool = False, group=None, overlap: bool = False):
         """data_parallel=True (torch.distributed initialised): the graph holds zero_grad + forward + backward;
-        each replay is followed by ONE all-reduce of the flat gradient arena (60 MB at conf 18 is ~0.2 ms over
-        NVLink, far below the ~8 ms step, so bucket overlap buys nothing here) and the fused optimizer step with
-        grad_scale = 1/world_size.  Pass the GLOBAL-batch pos_weight (dist.global_pos_weight)."""
+        each replay is followed by the all-reduce of the flat gradient arena (60 MB at conf 18: ~0.3 ms over NVLink
+        against a 3.4 ms step) and the fused optimizer step with grad_scale = 1/world_size.  overlap=True (fused BF16
+        step, >= 4 Blocks): the step is captured as two graphs cut in the middle of the backward and the upper half of
+        the arena is all-reduced while the second graph runs - equivalent (tools/check_multi_gpu.py) and measured
+        EQUAL at N = 2 (3.61 ms either way, tools/dp_overlap_timing.py): the backward's kernels fill every SM's shared
+        memory, NCCL's CTAs only get in between kernels; off by default.  Pass the GLOBAL-batch pos_weight
+        (dist.global_pos_weight)."""
         self.model = model
         self.opt = optimizer
         self.warmup = max(1, warmup)
         self.grad_scale = grad_scale
         self.dp = bool(data_parallel)
         self.group = group
+        self.overlap = bool(overlap)
         self._graph = None
+        self._graphs = None
         self.launches_per_replay = 0
         self.replays = 0
         dev = optimizer.arena.flat.device
@@ -233,6 +239,52 @@ class GraphedTrainStep:
         dist.all_reduce(self.opt.arena.flat_grad, group=self.group)
         self.opt.step(grad_scale=self.grad_scale / ws)
 
+    # ---- data-parallel overlap: the step is captured as TWO graphs cut inside the backward; the gradients of the
+    # upper half of the model (head, encoder_norm, Blocks >= L/2 - the tail of the flat arena, parameters are laid out
+    # in model order) are all-reduced on NCCL's stream while the second graph computes the lower half
+    def _dp_cut(self):
+        if not (self.dp and self.fused) or F._STATE.get("wgrad_partial") or not self.overlap:
+            return None
+        layers = list(self.model.transformer.encoder.layer)
+        if len(layers) < 4:
+            return None
+        cut = len(layers) // 2
+        first = next(layers[cut].parameters())
+        off = 0
+        for p_ in self.opt.arena.params:
+            if p_ is first:
+                return cut, off
+            off += p_.numel()
+        return None
+
+    def _capture_segments(self, cut):
+        pw = self.pw_dev if self.use_pw else None
+        pool = torch.cuda.graph_pool_handle()
+        gen = fused_train.loss_and_grads_steps(self.model, self.x, self.y, pw, (cut,))
+        self._graphs = [torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()]
+        with torch.cuda.graph(self._graphs[0], pool=pool):
+            fused_train.plan_of(self.model).refresh(self.step_dev, force=True)
+            self.opt.zero_grad()
+            self.loss = next(gen)
+        with torch.cuda.graph(self._graphs[1], pool=pool):
+            try:
+                next(gen)
+                raise RuntimeError("backward yielded more segments than graphs")
+            except StopIteration:
+                pass
+
+    def _replay_segments(self):
+        import torch.distributed as dist
+        ws = dist.get_world_size(self.group)
+        fg = self.opt.arena.flat_grad
+        self._graphs[0].replay()
+        w0 = dist.all_reduce(fg[self._cut_off:], group=self.group, async_op=True)
+        self._graphs[1].replay()
+        w1 = dist.all_reduce(fg[:self._cut_off], group=self.group, async_op=True)
+        w0.wait()
+        w1.wait()
+        self.opt.step(grad_scale=self.grad_scale / ws)
+
     def _one(self):
         loss = self._fwd_bwd()
         if self.dp:
@@ -259,14 +311,19 @@ class GraphedTrainStep:
             F.invalidate_weight_shadows()       # the captured step must re-derive the bf16 shadows itself
             self._graph = torch.cuda.CUDAGraph()
             n0 = _lib.lib().vit3d_launch_count()
-            with torch.cuda.graph(self._graph):
-                self.loss = self._fwd_bwd() if self.dp else self._one()
+            cut = self._dp_cut()
+            if cut is not None:
+                self._cut_off = cut[1]
+                self._capture_segments(cut[0])
+            else:
+                self._graphs = None
+                with torch.cuda.graph(self._graph):
+                    self.loss = self._fwd_bwd() if self.dp else self._one()
             self.launches_per_replay = _lib.lib().vit3d_launch_count() - n0
             if not self.dp:
                 self.opt._steps -= 1            # the capture recorded the optimizer launch, it did not run it
             F.invalidate_weight_shadows()       # shadows made during capture live in the graph's pool
-            self._graph.replay()                # capture records, it does not execute: run the step now
-            self._after_replay()
+            self._replay()                      # capture records, it does not execute: run the step now
             return self.loss
         if (pos_weight is not None) != self.use_pw:
             raise ValueError("GraphedTrainStep was captured %s pos_weight" % ("with" if self.use_pw else "without"))
@@ -276,9 +333,17 @@ class GraphedTrainStep:
             self.y.copy_(y, non_blocking=True)
         if self.use_pw:
             self._put_scalar(self.pw_dev, float(pos_weight))
+        self._replay()
+        return self.loss
+
+    def _replay(self):
+        if self._graphs is not None:
+            self.replays += 1
+            self._replay_segments()             # two graphs, the all-reduces of the two arena halves between / after them
+            F.invalidate_weight_shadows()
+            return
         self._graph.replay()
         self._after_replay()
-        return self.loss
 
     def _after_replay(self):
         self.replays += 1

@@ -1,6 +1,7 @@
 """Multi-GPU correctness (run under torchrun, one rank per GPU):
   * DP-N gradients (GradReducer + global_pos_weight, in-place arena accumulation) == single-process gradients on the
     concatenated batch (SURVEY.md test plan v);
+  * graphed DP steps with the overlapped (two-graph) gradient all-reduce == the single all-reduce schedule;
   * ShardedEnsemble output == TransformerEnsemble output on one GPU."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -52,6 +53,38 @@ for prec, rtol in (("fp32", 2e-3), ("bf16", 6e-2)):
     if rank == 0:
         print(f"DP-{world} {prec}: grads match single-process big batch, worst rel err {worst:.2e}")
     red.remove()
+# graphed data-parallel steps: two graphs with the all-reduce of the upper arena half overlapped == one graph + one
+# all-reduce (same dropout masks: both runs start from the same seed / step counter)
+from vit3d_b200.graphs import GraphedTrainStep
+cfg = vit3d_b200.get_config(16, 512, 4, 256, 8, dropout_rate=0.1)
+sd = O.init_state_dict(cfg, seed=11)
+B = 8 * world
+x = O.synth_volumes(B, seed=9).to(dev)[rank::world].contiguous()
+y = O.synth_labels(B).to(dev)[rank::world].contiguous()
+F.enable_direct_grads(True)
+final = {}
+for overlap in (True, False, "again"):          # "again": the single all-reduce schedule a second time = run-to-run floor
+    torch.manual_seed(123)
+    F._STATE["step"] = 0
+    m = VisionTransformer(cfg, 128, zero_head=True, num_classes=1, precision="bf16").to(dev)
+    m.load_state_dict(sd); m.train()
+    opt = FusedSGD(m.parameters(), lr=0.05, momentum=0.9)
+    step = GraphedTrainStep(m, opt, warmup=1, data_parallel=True, overlap=overlap is True)
+    for _ in range(4):
+        loss = step(x, y, 1.3)
+    torch.cuda.synchronize()
+    final[overlap] = (opt.arena.flat.clone(), float(loss), step._graphs is not None)
+d = float((final[True][0] - final[False][0]).abs().max())
+floor = float((final["again"][0] - final[False][0]).abs().max())     # split-K reductions are not order-deterministic
+scale = float(final[False][0].abs().max())
+same_everywhere = final[True][0].clone()
+dist.broadcast(same_everywhere, 0)
+drift = float((same_everywhere - final[True][0]).abs().max())
+if not final[True][2] or final[False][2] or d > 3 * floor + 1e-6 * scale or drift != 0.0 or not (final[True][1] == final[True][1]):
+    ok = False
+if rank == 0:
+    print(f"graphed DP-{world}: overlapped two-graph step vs single all-reduce after 4+1 steps: max weight diff {d:.2e} "
+          f"(run-to-run floor of the single schedule {floor:.2e}, scale {scale:.2e}), ranks identical: {drift == 0.0}, segmented: {final[True][2]}")
 # sharded ensemble
 cfgs = [vit3d_b200.north_star_config(c) for c in (5, 9, 11)]
 members = [VisionTransformer(c, 128, zero_head=True, num_classes=1, precision="bf16") for c in cfgs]
