@@ -57,6 +57,7 @@ static void tuning_defaults() {
     set(VIT3D_TUNE_ATTN_TF32, env("VIT3D_ATTN_TF32", 1));
     set(VIT3D_TUNE_F32_BOX, env("VIT3D_F32_BOX", 0));
     set(VIT3D_TUNE_PATCH_TALL, env("VIT3D_PATCH_TALL", 0));
+    set(VIT3D_TUNE_PATCH_CLUSTER, env("VIT3D_PATCH_CLUSTER", 0));
     set(VIT3D_TUNE_ATTN_THREADS, env("VIT3D_ATTN_THREADS", 0));
   });
 }

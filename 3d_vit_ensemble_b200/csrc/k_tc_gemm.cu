@@ -154,7 +154,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmB);
     for (int s = 0; s < MAXST; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], ep.cluster);     // the commit of every CTA of the cluster frees a multicast slot
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
@@ -168,6 +168,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const int cl = ep.cluster;
+  const uint32_t crank = cl > 1 ? cluster_ctarank() : 0u;
+  if (cl > 1) cluster_sync_all();   // every CTA's barriers exist before any multicast signal
   pdl_trigger();     // the next kernel may begin its own prologue on SMs this grid frees
   pdl_wait();        // everything above overlapped the previous kernel's tail; global memory from here on
 
@@ -202,7 +205,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
               tma_load_5d(sa, &tmA, &full_bar[stage], c0, 0, i, 0, ti.tm * ep.vols_per_tile);
             }
-            tma_load_3d(sa + a_bytes, &tmB, &full_bar[stage], c0, i, ti.tn * BN);
+            if (cl > 1)       // this CTA's share of the filters, into the same slot of every CTA of the cluster
+              tma_load_3d_mcast(sa + a_bytes + (int)crank * (Cfg::B_BYTES / cl), &tmB, &full_bar[stage], c0, i,
+                                ti.tn * BN + (int)crank * (BN / cl), (uint16_t)((1u << cl) - 1u));
+            else
+              tma_load_3d(sa + a_bytes, &tmB, &full_bar[stage], c0, i, ti.tn * BN);
           } else if (mnm) {
             // both operands MN-major (weight gradients: dW = dY^T X reduces over the token rows): a stage
             // holds 64 reduction rows; each 64-column block is one {64 cols x 64 rows} box = 8 KB
@@ -268,7 +275,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               umma<TF32>(d_tmem + BN, ad + (uint64_t)(Cfg::A_BYTES >> 4) + k * kstep, bd + k * kstep, idesc,
                          (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+          if (cl > 1) umma_commit_mcast(&empty_bar[stage], (uint16_t)((1u << cl) - 1u));
+          else umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[buf]);       // accumulator ready for the epilogue
@@ -374,6 +382,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (cl > 1) cluster_sync_all();   // nobody leaves while a partner may still multicast into this CTA
   if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
@@ -451,6 +460,18 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     int cpn = sms / tiles_n;            // CTAs per n-tile
     if (cpn > tiles_m) cpn = tiles_m;
     grid = cpn * tiles_n;
+  }
+  if (ep.grid_limit > 0 && grid > ep.grid_limit) grid = ep.grid_limit;
+  if (ep.cluster > 1) {
+    // the cluster's CTAs walk the tile list in lock step (shared ring slots): equal tile counts within every cluster
+    if (grid % ep.cluster || (total > grid && (total % grid) % ep.cluster) || stationary || splits != 1) {
+      set_error("tc_gemm: cluster multicast needs grid and tail tile counts that are multiples of the cluster size");
+      return VIT3D_ERR_INVALID;
+    }
+    V3_CUDA(launch_pdl_cluster(kern, dim3(grid), dim3(Cfg::THREADS), (size_t)Lay::SMEM_BYTES, st, ep.cluster, ta, tb, tc, tp,
+                               tx ? *tx : tp, ep, M, N, K, tiles_m, tiles_n, splits, stationary ? 1 : 0, patch_blocks, mn_major));
+    V3_LAUNCH_CHECK();
+    return VIT3D_OK;
   }
   V3_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), (size_t)Lay::SMEM_BYTES, st, ta, tb, tc, tp, tx ? *tx : tp, ep, M, N, K, tiles_m,
                      tiles_n, splits, stationary ? 1 : 0, patch_blocks, mn_major));
@@ -741,10 +762,49 @@ int tc_patch_embed_fwd(const float* x, const float* w, const float* bias, const 
   }
   TcEpilogue ep;
   ep.bias = bias; ep.rowadd = pos; ep.row_group = P; ep.out = tokens; ep.out_f32 = 1; ep.vols_per_tile = vpt;
+  // Optional (VIT3D_PATCH_CLUSTER, off): the filter bank (1.3 MB, re-streamed for every row tile: 32 KB per k-block
+  // beside 16 KB of volume data) fetched ONCE per cluster - each CTA loads 1/cl of the filters and multicasts them.
+  // The cluster's CTAs share ring slots, so they must walk equally many tiles: the grid is cut to whole co-resident
+  // clusters whose tail (total % grid) is a multiple of the cluster size (B200: 74 pairs, but only 33 clusters of 4).
+  // Measured at batch 1024: 117.7-119 us with pairs, 116.7-119.5 us without - not bound by L2 operand delivery
+  // (ncu: the MMA thread waits for operands 31 % of its time, TF32 tensor pipe 51 % busy, 80 of 148 CTAs idle during
+  // the fourth tile round of 512 tiles).
+  if (bn == 256 && N == 256 && tuning(VIT3D_TUNE_PATCH_CLUSTER) != 0 && tm >= 2 * sms) {
+    for (int cl = tuning(VIT3D_TUNE_PATCH_CLUSTER) >= 4 ? 4 : 2; cl >= 2 && ep.cluster == 1; cl -= 2) {
+      int nmax = 0;
+      {
+        using Lay = TcLayout<256, false>;
+        auto kern = tc_gemm_kernel<true, 256, EPI_GENERIC, false>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay::SMEM_BYTES);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(sms - sms % cl);
+        cfg.blockDim = dim3(TcCfg<256>::THREADS);
+        cfg.dynamicSmemBytes = Lay::SMEM_BYTES;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&nmax, kern, &cfg) != cudaSuccess) { cudaGetLastError(); nmax = 0; }
+      }
+      int g = nmax * cl < sms ? nmax * cl : sms - sms % cl;
+      for (int tries = 0; tries < 8 && g >= cl; ++tries, g -= cl)
+        if (tm <= g || (tm % g) % cl == 0) break;
+      if (g >= cl && g * 10 >= sms * 9 && (tm <= g || (tm % g) % cl == 0)) {      // keep >= 90 % of the SMs busy
+        ep.cluster = cl;
+        ep.grid_limit = g;
+        cuuint64_t wd[3] = {(cuuint64_t)inner, (cuuint64_t)p0, (cuuint64_t)H};
+        cuuint64_t ws[2] = {(cuuint64_t)inner * 4, (cuuint64_t)p0 * inner * 4};
+        cuuint32_t wb[3] = {32, 1, (cuuint32_t)(bn / cl)};
+        int rc = make_tmap_nd(&tb, w, 3, wd, ws, wb);
+        if (rc != VIT3D_OK) return rc;
+      }
+    }
+  }
   // optional 256-row tiles (two accumulators over one weight k-block, 64 KB stages of 1024 MMA cycles): measured
   // 124 us against 117 us for 128-row tiles at batch 1024 (the single accumulator pair cannot overlap a tile's
   // epilogue with the next tile's MMAs) - off by default
-  if (bn == 256 && tuning(VIT3D_TUNE_PATCH_TALL) != 0 && M >= 4 * TC_BLOCK_M * sm_count() / 2)
+  if (bn == 256 && ep.cluster == 1 && tuning(VIT3D_TUNE_PATCH_TALL) != 0 && M >= 4 * TC_BLOCK_M * sm_count() / 2)
     return launch_tc<true, 256>(ta, tb, ta, ta, ep, M, N, nkb, 1, false, st, pblocks, 2);
   if (bn == 256) return launch_tc<true, 256>(ta, tb, ta, ta, ep, M, N, nkb, 1, false, st, pblocks);
   if (bn == 128) return launch_tc<true, 128>(ta, tb, ta, ta, ep, M, N, nkb, 1, false, st, pblocks);

@@ -20,6 +20,8 @@ struct TcEpilogue {
   int out_f32 = 1;
   int act = 0;
   int row_group = 0;                // >0: out row = m + m / row_group + 1
+  int cluster = 1;                  // patch mode: CTAs of a cluster share every filter-bank k-block by TMA multicast
+  int grid_limit = 0;               // > 0: launch at most this many CTAs (cluster launches: whole co-resident clusters)
   int f32_box = 0;                  // fp32 output leaves as [32 x 16] TMA boxes through tmC (dense rows, no row remap / atomics)
   int atomic = 0;                   // accumulate (split-K): 1 = fp32 vector atomics, 2 = TMA reduce-add boxes (tmC / tmPre / tmX per segment)
   int vols_per_tile = 0;            // patch-embedding mode: volumes per 128-row tile

@@ -58,13 +58,18 @@ def test_tc_linear_matches_fp64(prec, shape, mode):
         assert errp <= tol, (errp, tol)
 
 
-@pytest.mark.parametrize("tall", [1, 0])
-@pytest.mark.parametrize("B", [1, 2, 3, 37, 597, 600])
+@pytest.mark.parametrize("variant", ["cluster4", "cluster2", "tall", "plain"])
+@pytest.mark.parametrize("B", [1, 2, 3, 37, 597, 600, 1024])
 @pytest.mark.parametrize("H", [256, 64])
-def test_tc_patch_embedding_matches_oracle(B, H, tall):
-    """TMA-im2col TF32 patch embedding (+bias, +position rows, cls rows) vs the fp64 oracle; batches of >= 592 volumes
-    take 256-row tiles (tall=1; 597 volumes leave the last tile's second half ragged)."""
-    lib().vit3d_set_tuning(11, tall)
+def test_tc_patch_embedding_matches_oracle(B, H, variant):
+    """TMA-im2col TF32 patch embedding (+bias, +position rows, cls rows) vs the fp64 oracle.  Batches of >= 592 volumes
+    can run on clusters of 4 / 2 CTAs sharing the filter bank by TMA multicast (taken when the tile count lets every CTA
+    of a cluster walk equally many tiles: 600 and 1024 volumes, not 597) or on 256-row tiles (597 volumes leave the
+    last tile's second half ragged)."""
+    if B == 1024 and (H != 256 or variant in ("tall", "plain")):
+        pytest.skip("large case only for the cluster variants")
+    lib().vit3d_set_tuning(11, 1 if variant == "tall" else 0)
+    lib().vit3d_set_tuning(12, {"cluster4": 4, "cluster2": 2}.get(variant, 0))
     from oracle import vit3d_oracle as O
     from vit3d_b200.models.modeling import Embeddings
     cfg = vit3d_b200.get_config(16, 128, 1, H, 4)
@@ -80,6 +85,7 @@ def test_tc_patch_embedding_matches_oracle(B, H, tall):
             got = emb(x.to(DEV)).cpu().double()
     finally:
         lib().vit3d_set_tuning(11, 0)
+        lib().vit3d_set_tuning(12, 0)
     ref = O.embeddings({k: v.double() for k, v in sd.items()}, cfg, x.double())
     scale = float(ref.abs().max())
     err = float((got - ref).abs().max())

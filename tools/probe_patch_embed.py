@@ -1,5 +1,5 @@
 """Times the patch embedding (TMA im2col TF32 GEMM + cls rows) alone at the conf-5 geometry, CUDA events over 20
-launches on three rotating input batches (1 GB in total: larger than L2), 256-row vs 128-row tiles.
+launches on three rotating input batches (1 GB in total: larger than L2), 128-row tiles, 256-row tiles, clusters of 2 / 4 CTAs sharing the filter bank by TMA multicast.
 
     python tools/probe_patch_embed.py [--batch 1024]
 """
@@ -27,8 +27,9 @@ def main():
     emb.to(dev).eval()
     xs = [torch.randn(args.batch, 1, 128, 128, 5, device=dev) for _ in range(3)]
     nbytes = xs[0].numel() * 4 + args.batch * 65 * 256 * 4
-    for tall in (0, 1, 0, 1):
+    for tall, cluster in ((0, 0), (1, 0), (0, 2), (0, 4), (0, 0), (0, 4)):
         lib().vit3d_set_tuning(11, tall)
+        lib().vit3d_set_tuning(12, cluster)
         with torch.no_grad():
             for i in range(5):
                 emb(xs[i % 3])
@@ -40,8 +41,9 @@ def main():
             e1.record()
             torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / 20 * 1e3
-        print(f"patch embedding B={args.batch} tall={tall}: {us:7.1f} us  {nbytes / us / 1e3:6.0f} GB/s (volume read + token write)")
+        print(f"patch embedding B={args.batch} tall={tall} cluster={cluster}: {us:7.1f} us  {nbytes / us / 1e3:6.0f} GB/s (volume read + token write)")
     lib().vit3d_set_tuning(11, 0)
+    lib().vit3d_set_tuning(12, 0)
 
 
 if __name__ == "__main__":
