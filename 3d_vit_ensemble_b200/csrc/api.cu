@@ -58,6 +58,7 @@ static void tuning_defaults() {
     set(VIT3D_TUNE_F32_BOX, env("VIT3D_F32_BOX", 0));
     set(VIT3D_TUNE_PATCH_TALL, env("VIT3D_PATCH_TALL", 0));
     set(VIT3D_TUNE_PATCH_CLUSTER, env("VIT3D_PATCH_CLUSTER", 0));
+    set(VIT3D_TUNE_PATCH_TF32, env("VIT3D_PATCH_TF32", 1));
     set(VIT3D_TUNE_ATTN_THREADS, env("VIT3D_ATTN_THREADS", 0));
   });
 }
@@ -131,6 +132,18 @@ int vit3d_patch_embed_fwd(const float* x, const float* w, const float* bias, con
     return launch_cls_rows(cls, pos, tokens, B, S, H, st);
   }
   V3_REQUIRE(ws && ws_bytes >= vit3d_patch_embed_ws_bytes(B, X, Y, Z, p0, p1, p2, H, prec), "patch_embed_fwd: workspace too small");
+  if (prec == VIT3D_PREC_TF32 && tuning(VIT3D_TUNE_PATCH_TF32) != 0 && tc_patch_embed_supported(B, X, Y, Z, p0, p1, p2, H) &&
+      (size_t)B * X * Y * Z * sizeof(float) <= ws_bytes) {
+    // TF32 mode: the volume is rounded to nearest TF32 into the workspace first (the tensor core would truncate the raw
+    // input), then takes the same TMA-im2col tensor-core GEMM as BF16 mode: every GEMM operand of this mode is an
+    // RN-rounded TF32 value.  (The SIMT fp32 embedding was 1.78 of the 6.3 ms of a conf-5 batch of 1024.)
+    float* xr = reinterpret_cast<float*>(ws);
+    int rc = launch_round_tf32(x, xr, (long long)B * X * Y * Z, st);
+    if (rc != VIT3D_OK) return rc;
+    rc = tc_patch_embed_fwd(xr, w, bias, pos, tokens, B, X, Y, Z, p0, p1, p2, H, st);
+    if (rc != VIT3D_OK) return rc;
+    return launch_cls_rows(cls, pos, tokens, B, S, H, st);
+  }
   float* patches = reinterpret_cast<float*>(ws);
   int rc = launch_patch_gather(x, patches, 1, B, X, Y, Z, p0, p1, p2, st);
   if (rc != VIT3D_OK) return rc;

@@ -132,9 +132,9 @@ class PatchEmbedFn(torch.autograd.Function):
         pid = PREC[prec]
         wsb = _lib.lib().vit3d_patch_embed_ws_bytes(B, X, Y, Z, p0, p1, p2, H, pid)
         ws = torch.empty(wsb, device=x.device, dtype=torch.uint8)
-        # BF16 mode runs the embedding on the tensor cores in TF32: give it round-to-nearest weights
-        # (fp32 / TF32 modes use the exact fp32 embedding, see vit3d_patch_embed_fwd)
-        w_use = lp_weight(w, "tf32") if (prec == "bf16" and w.is_contiguous()) else _c(w)
+        # BF16 and TF32 modes run the embedding on the tensor cores in TF32: give it round-to-nearest weights
+        # (TF32 mode also rounds the volume first; fp32 mode uses the exact fp32 embedding, see vit3d_patch_embed_fwd)
+        w_use = lp_weight(w, "tf32") if (prec in ("bf16", "tf32") and w.is_contiguous()) else _c(w)
         call("vit3d_patch_embed_fwd", ptr(x), ptr(w_use), ptr(_c(bias)), ptr(_c(cls)), ptr(_c(pos)), ptr(tokens),
              B, X, Y, Z, p0, p1, p2, H, pid, ptr(ws), wsb, stream())
         ctx.save_for_backward(x)
