@@ -59,6 +59,7 @@ static void tuning_defaults() {
     set(VIT3D_TUNE_PATCH_TALL, env("VIT3D_PATCH_TALL", 0));
     set(VIT3D_TUNE_PATCH_CLUSTER, env("VIT3D_PATCH_CLUSTER", 0));
     set(VIT3D_TUNE_PATCH_TF32, env("VIT3D_PATCH_TF32", 1));
+    set(VIT3D_TUNE_ATTN_FWD_UNIT, env("VIT3D_ATTN_FWD_UNIT", 0));
     set(VIT3D_TUNE_ATTN_THREADS, env("VIT3D_ATTN_THREADS", 0));
   });
 }

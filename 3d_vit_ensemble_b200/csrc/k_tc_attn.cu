@@ -347,6 +347,7 @@ static int attn_threads(int D, bool vis) {
   return (D <= 32 && vis) ? 512 : 640;
 }
 
+int tc_attn_fwd_unit(const void* qkv, void* ctx, float* probs, int probs_ld, int B, int D, cudaStream_t st);
 int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int probs_ld, int B, int S, int heads, int D, cudaStream_t st) {
   if (!tc_attn_supported(S, heads, D)) V3_UNSUPPORTED("tc attention: unsupported shape S=%d heads=%d D=%d", S, heads, D);
   if (B <= 0) return VIT3D_OK;
@@ -358,6 +359,10 @@ int tc_attn_fwd(const void* qkv, void* ctx, float* probs, int probs_ld, int B, i
       (reinterpret_cast<uintptr_t>(probs) & 7)) {
     set_error("tc attention: qkv/ctx must be 16-byte aligned, probs 8-byte aligned");
     return VIT3D_ERR_INVALID;
+  }
+  {
+    const int mode = tuning(VIT3D_TUNE_ATTN_FWD_UNIT);      // 0: one volume per CTA; 1: units when no probabilities; 2: always
+    if (mode == 2 || (mode == 1 && probs == nullptr)) return tc_attn_fwd_unit(qkv, ctx, probs, probs_ld, B, D, st);
   }
   if (attn_threads(D, probs != nullptr) == 640) {
     if (D == 16) return launch_attn<16, 640>(qkv, ctx, probs, probs_ld, B, st);
@@ -1013,6 +1018,228 @@ static int launch_attn_bwd_unit(const void* dctx, const void* qkv, void* dqkv, f
   return VIT3D_OK;
 }
 
+
+// ---------------------------------------------------------------------------- forward, unit kernel (bf16)
+// The forward in the backward's unit form: a CTA of 4 warps takes (volume, 4 heads), q | k | v column blocks arrive as
+// 65-row x 128-byte TMA boxes (SWIZZLE_128B), one warp owns one head, the context tile overwrites the Q tile and
+// leaves as boxes.  18-55 KB of shared memory: 4 CTAs per SM at D <= 32.  Compute body = attn_fwd_tc_kernel's.
+template <int D> struct AvCfg {
+  static constexpr int UC = 4 * D;                    // bf16 columns per unit row and matrix (4 heads)
+  static constexpr int NB = UC / 64;
+  static constexpr int MAT = NB * AU_TILE;
+  static constexpr int SMEM = 3 * MAT + 64 + 1024;
+  static constexpr int CTAS = D == 64 ? 2 : 4;
+};
+
+template <int D, int VIS>
+__global__ void __launch_bounds__(128, AvCfg<D>::CTAS)
+attn_fwd_unit_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmCtx,
+                     float* __restrict__ probs, int units, int groups, float scale_log2e, int pld) {
+  using Cfg = AvCfg<D>;
+  constexpr int HEADS = AT_A / D;
+  constexpr int KSTEPS = D / 16;
+  constexpr int NT = 10;
+  constexpr int DT = D / 8;
+  constexpr int MAT = Cfg::MAT, NB = Cfg::NB, UC = Cfg::UC;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sq = smem_u32(smem), sk = sq + MAT, sv = sk + MAT;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 3 * MAT);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQkv);
+    prefetch_tmap(&tmCtx);
+    mbar_init(full, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_trigger();
+  pdl_wait();
+  const int hq = blockIdx.x % groups;
+  const int c0 = hq * UC;
+  const int hc = warp * D * 2;
+  const int h = hq * 4 + warp;
+
+  int it = 0;
+  for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+    const int b = u / groups;
+    const int row_g = b * AT_S;
+    if (threadIdx.x == 0) {
+      bulk_wait_read0();
+      mbar_arrive_expect_tx(full, 3 * NB * AT_S * 128);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        tma_load_2d(smem + j * AU_TILE, &tmQkv, full, c0 + 64 * j, row_g);
+        tma_load_2d(smem + MAT + j * AU_TILE, &tmQkv, full, AT_A + c0 + 64 * j, row_g);
+        tma_load_2d(smem + 2 * MAT + j * AU_TILE, &tmQkv, full, 2 * AT_A + c0 + 64 * j, row_g);
+      }
+    }
+    mbar_wait(full, it & 1);
+
+#pragma unroll 1
+    for (int rt = 0; rt < 5; ++rt) {
+      const int r0 = rt * 16;
+      uint32_t qa[KSTEPS][4];
+      {
+        const int row = min(r0 + (lane & 7) + ((lane >> 3) & 1) * 8, AT_S - 1);
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks)
+          ldsm_x4(au_addr(sq, row, hc + ks * 32 + (lane >> 4) * 16), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+      }
+      float s[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        if (nt < 9) {
+          const int key = min(nt * 8 + (lane & 7), AT_S - 1);
+#pragma unroll
+          for (int ks = 0; ks < KSTEPS; ++ks) {
+            uint32_t b0, b1;
+            ldsm_x2(au_addr(sk, key, hc + ks * 32 + ((lane >> 3) & 1) * 16), b0, b1);
+            mma_bf16(s[nt], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
+          }
+        }
+      }
+      const bool tail = t == 0;
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      if (tail) { mx0 = fmaxf(mx0, s[8][0]); mx1 = fmaxf(mx1, s[8][2]); }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float m0 = mx0 * scale_log2e, m1 = mx1 * scale_log2e;
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = ex2_approx(fmaf(s[nt][0], scale_log2e, -m0));
+        s[nt][1] = ex2_approx(fmaf(s[nt][1], scale_log2e, -m0));
+        s[nt][2] = ex2_approx(fmaf(s[nt][2], scale_log2e, -m1));
+        s[nt][3] = ex2_approx(fmaf(s[nt][3], scale_log2e, -m1));
+        sum0 += s[nt][0] + s[nt][1];
+        sum1 += s[nt][2] + s[nt][3];
+      }
+      s[8][0] = tail ? ex2_approx(fmaf(s[8][0], scale_log2e, -m0)) : 0.f;
+      s[8][2] = tail ? ex2_approx(fmaf(s[8][2], scale_log2e, -m1)) : 0.f;
+      s[8][1] = s[8][3] = 0.f;
+      sum0 += s[8][0];
+      sum1 += s[8][2];
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+      const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+      const int row0 = r0 + g, row1 = r0 + g + 8;
+      const bool fullt = rt < 4;
+      const bool w0 = fullt || g == 0, w1 = fullt;
+      if constexpr (VIS != 0) {
+#pragma unroll
+        for (int nt = 0; nt < 9; ++nt) {
+          s[nt][0] *= inv0; s[nt][1] *= inv0;
+          s[nt][2] *= inv1; s[nt][3] *= inv1;
+        }
+      }
+      if constexpr (VIS == 2) {
+        float* p0 = probs + ((size_t)(b * HEADS + h) * AT_S + row0) * pld + 2 * t;
+        float* p1 = p0 + 8 * (size_t)pld;
+#pragma unroll
+        for (int nt = 0; nt < 9; ++nt) {
+          st_global_f2_if(w0, p0 + nt * 8, s[nt][0], s[nt][1]);
+          st_global_f2_if(w1, p1 + nt * 8, s[nt][2], s[nt][3]);
+        }
+      }
+      if constexpr (VIS == 1) {
+        const int bh = b * HEADS + h;
+        const bool odd = ((bh + row0) & 1) != 0;
+        float* p0 = probs + ((size_t)bh * AT_S + row0) * AT_S + 2 * t + (odd ? 1 : 0);
+        float* p1 = p0 + 8 * AT_S;
+        const int src = (lane & ~3) | ((t + 1) & 3);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const float n0 = __shfl_sync(0xffffffffu, tail ? s[nt + 1][0] : s[nt][0], src);
+          const float n1 = __shfl_sync(0xffffffffu, tail ? s[nt + 1][2] : s[nt][2], src);
+          const float2 v0 = make_float2(odd ? s[nt][1] : s[nt][0], odd ? n0 : s[nt][1]);
+          const float2 v1 = make_float2(odd ? s[nt][3] : s[nt][2], odd ? n1 : s[nt][3]);
+          st_global_f2_if(w0, p0 + nt * 8, v0.x, v0.y);
+          st_global_f2_if(w1, p1 + nt * 8, v1.x, v1.y);
+        }
+        const int off = odd ? -1 : 64;
+        st_global_f1_if(tail && w0, p0 + off, odd ? s[0][0] : s[8][0]);
+        st_global_f1_if(tail && w1, p1 + off, odd ? s[0][2] : s[8][2]);
+      }
+      float o[DT][4];
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) {
+        const uint32_t a0 = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+        const uint32_t a1 = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+        const uint32_t a2 = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        const uint32_t a3 = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        const int key = min(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, AT_S - 1);
+#pragma unroll
+        for (int dt = 0; dt < DT; ++dt) {
+          uint32_t b0, b1;
+          ldsm_x2_t(au_addr(sv, key, hc + dt * 16), b0, b1);
+          mma_bf16(o[dt], a0, a1, a2, a3, b0, b1);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) {
+        const int colb = hc + (dt * 8 + 2 * t) * 2;
+        const float c0f = VIS != 0 ? 1.f : inv0, c1f = VIS != 0 ? 1.f : inv1;
+        if (w0) st_shared_u32(au_addr(sq, row0, colb), pack_bf16(o[dt][0] * c0f, o[dt][1] * c0f));
+        if (w1) st_shared_u32(au_addr(sq, row1, colb), pack_bf16(o[dt][2] * c1f, o[dt][3] * c1f));
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) au_store_box(&tmCtx, sq + j * AU_TILE, c0 + 64 * j, row_g);
+      bulk_commit();
+    }
+  }
+  if (threadIdx.x == 0) bulk_wait0();
+}
+
+template <int D, int VIS>
+static int launch_attn_unit_v(const void* qkv, void* ctx, float* probs, int pld, int B, cudaStream_t st) {
+  using Cfg = AvCfg<D>;
+  auto kern = attn_fwd_unit_kernel<D, VIS>;
+  V3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  CUtensorMap tq, tc;
+  int rc = make_tmap_2d(&tq, qkv, 2, (long long)B * AT_S, 3 * AT_A, 3 * AT_A, AT_S, 64, 128);
+  if (rc != VIT3D_OK) return rc;
+  rc = make_tmap_2d(&tc, ctx, 2, (long long)B * AT_S, AT_A, AT_A, AT_S, 64, 128);
+  if (rc != VIT3D_OK) return rc;
+  const int groups = AT_A / Cfg::UC;
+  const int units = B * groups;
+  int grid = sm_count() * Cfg::CTAS;
+  if (grid > units) grid = units;
+  grid -= grid % groups;
+  const float scale_log2e = 1.4426950408889634f / sqrtf((float)D);
+  V3_CUDA(launch_pdl(kern, dim3(grid), dim3(128), (size_t)Cfg::SMEM, st, tq, tc, probs, units, groups, scale_log2e, pld));
+  V3_LAUNCH_CHECK();
+  return VIT3D_OK;
+}
+template <int D>
+static int launch_attn_unit(const void* qkv, void* ctx, float* probs, int pld, int B, cudaStream_t st) {
+  if (!probs) return launch_attn_unit_v<D, 0>(qkv, ctx, probs, pld, B, st);
+  if (pld == AT_S) return launch_attn_unit_v<D, 1>(qkv, ctx, probs, pld, B, st);
+  return launch_attn_unit_v<D, 2>(qkv, ctx, probs, pld, B, st);
+}
+int tc_attn_fwd_unit(const void* qkv, void* ctx, float* probs, int probs_ld, int B, int D, cudaStream_t st) {
+  if (D == 16) return launch_attn_unit<16>(qkv, ctx, probs, probs_ld, B, st);
+  if (D == 32) return launch_attn_unit<32>(qkv, ctx, probs, probs_ld, B, st);
+  return launch_attn_unit<64>(qkv, ctx, probs, probs_ld, B, st);
+}
 
 // ---------------------------------------------------------------------------- forward, TF32 mode (fp32 activations)
 // The 1e-3 accuracy mode keeps q | k | v, the probabilities and the context in fp32; its attention ran on a generic

@@ -89,12 +89,14 @@ unsigned long long vit3d_launch_count(void);
  *                            equal).  Env VIT3D_PATCH_CLUSTER.
  *   VIT3D_TUNE_PATCH_TF32    1 (default): TF32 mode rounds the volume to nearest TF32 and runs the tensor-core patch
  *                            embedding; 0: exact fp32 gather + SIMT GEMM.  Env VIT3D_PATCH_TF32.
+ *   VIT3D_TUNE_ATTN_FWD_UNIT bf16 attention forward: 0 one volume per CTA (bulk-copy staged); 1 (volume, 4-head) units with
+ *                            TMA boxes when no probabilities are written; 2 always.  Env VIT3D_ATTN_FWD_UNIT.
  *   VIT3D_TUNE_ATTN_BWD      1 (default): attention backward in (volume, 4-head) units, 4-warp CTAs, TMA boxes; 0: one
  *                            16-warp CTA per volume with per-row bulk copies.  Env VIT3D_ATTN_BWD. */
 enum { VIT3D_TUNE_EPI_PANEL = 0, VIT3D_TUNE_ATTN_THREADS = 1, VIT3D_TUNE_EPI_LEAN = 2, VIT3D_TUNE_STORE_WIDE = 3,
        VIT3D_TUNE_L2_AHEAD = 4, VIT3D_TUNE_MLP_PAIR = 5, VIT3D_TUNE_WGRAD_RED = 6, VIT3D_TUNE_ATTN_BWD = 7,
        VIT3D_TUNE_RES_PAIR = 8, VIT3D_TUNE_ATTN_TF32 = 9, VIT3D_TUNE_F32_BOX = 10, VIT3D_TUNE_PATCH_TALL = 11,
-       VIT3D_TUNE_PATCH_CLUSTER = 12, VIT3D_TUNE_PATCH_TF32 = 13, VIT3D_TUNE_COUNT = 14 };
+       VIT3D_TUNE_PATCH_CLUSTER = 12, VIT3D_TUNE_PATCH_TF32 = 13, VIT3D_TUNE_ATTN_FWD_UNIT = 14, VIT3D_TUNE_COUNT = 15 };
 int vit3d_set_tuning(int key, int value);
 int vit3d_get_tuning(int key);
 /* bytes per "act" element for a precision mode */

@@ -24,8 +24,12 @@ def ref_attention(qkv, heads):
 @pytest.mark.parametrize("heads", [4, 8, 16])
 @pytest.mark.parametrize("B", [1, 3, 149, 700])
 @pytest.mark.parametrize("vis", [True, False])
-@pytest.mark.parametrize("threads", [0, 640, 512])
+@pytest.mark.parametrize("threads", [0, 640, 512, "unit"])
 def test_attention_bf16(heads, B, vis, threads):
+    """threads: CTA size of the one-volume-per-CTA kernel, or "unit" = the (volume, 4-head) unit kernel."""
+    unit = threads == "unit"
+    threads = 0 if unit else threads
+    lib().vit3d_set_tuning(14, 2 if unit else 0)
     torch.manual_seed(B * 31 + heads)
     S, A = 65, 256
     qkv = (torch.randn(B, S, 3 * A, device=DEV) * 1.5).to(torch.bfloat16)
@@ -37,6 +41,7 @@ def test_attention_bf16(heads, B, vis, threads):
         torch.cuda.synchronize()
     finally:
         lib().vit3d_set_tuning(1, 0)
+        lib().vit3d_set_tuning(14, 0)
     rc, rp = ref_attention(qkv, heads)
     err = float((ctx.double() - rc).abs().max())
     assert np.isfinite(err) and err < 0.03, err                 # bf16 P and bf16 output rounding
