@@ -500,7 +500,10 @@ int tc_mlp2_fwd(const void* xn, const void* w1, const float* b1, const void* w2_
                 cudaStream_t st) {
   if (!tc_mlp2_supported(M, H, d)) V3_UNSUPPORTED("fused MLP: unsupported shape M=%d H=%d d=%d", M, H, d);
   if (ln_f32 && !ln_out) { set_error("fused MLP: fp32 LayerNorm output requested without a buffer"); return VIT3D_ERR_INVALID; }
-  const int pair_mode = M > 128 ? tuning(VIT3D_TUNE_MLP_PAIR) : 0;       // 1: multicast pairs (cta_group::1), 2: cta_group::2
+  if (tuning(VIT3D_TUNE_MLP_PAIR) == 3 && tc_mlp3_supported(M, H, d))      // 128-column chunks, double-buffered (k_tc_mlp3.cu)
+    return tc_mlp3(xn, w1, b1, w2_h, b2, residual, y, gamma, beta, eps, ln_out, ln_f32, M, H, d, st);
+  const int pm = tuning(VIT3D_TUNE_MLP_PAIR);
+  const int pair_mode = (M > 128 && pm != 3) ? pm : 0;                   // 1: multicast pairs (cta_group::1), 2: cta_group::2
   const bool pair = pair_mode != 0;
   CUtensorMap tx, tw1, tw2, ty, tr, tl;
   int rc = make_tmap_2d(&tx, xn, 2, M, H, H, 128, 64, 128);

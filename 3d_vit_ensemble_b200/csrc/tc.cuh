@@ -47,6 +47,12 @@ bool tc_patch_embed_supported(int B, int X, int Y, int Z, int p0, int p1, int p2
 int tc_patch_embed_fwd(const float* x, const float* w, const float* bias, const float* pos, float* tokens, int B, int X,
                        int Y, int Z, int p0, int p1, int p2, int H, cudaStream_t st);
 
+// k_tc_mlp3.cu: the fused MLP block with 128-column chunks, fc1 accumulator and GELU tile double buffered (same contract
+// as tc_mlp2_fwd)
+bool tc_mlp3_supported(int M, int H, int d);
+int tc_mlp3(const void* xn, const void* w1, const float* b1, const void* w2_h, const float* b2, const float* residual,
+            float* y, const float* gamma, const float* beta, float eps, void* ln_out, int ln_f32, int M, int H, int d,
+            cudaStream_t st);
 // k_tc_mlp2.cu: chunked fused MLP (256 fc1 columns per chunk, optional CTA pairs), + residual, + fused LayerNorm
 bool tc_mlp2_supported(int M, int H, int d);
 int tc_mlp2_fwd(const void* xn, const void* w1, const float* b1, const void* w2_h, const float* b2, const float* residual,

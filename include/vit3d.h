@@ -69,7 +69,9 @@ unsigned long long vit3d_launch_count(void);
  *                            write-saturated HBM is not an L2 miss).  Env VIT3D_L2_AHEAD.
  *   VIT3D_TUNE_MLP_PAIR      0 (default): one CTA per 128-row tile of the fused MLP; 1: clusters of two CTAs that
  *                            share every weight k-block by TMA multicast (half the L2 reads; measured equal -
- *                            the kernel is bound by its GELU / final epilogue, not by L2).  Env VIT3D_MLP_PAIR.
+ *                            the kernel is bound by its GELU / final epilogue, not by L2); 2: cta_group::2 pairs; 3: the
+ *                            128-column-chunk kernel with double-buffered fc1 accumulator and GELU tile (k_tc_mlp3.cu,
+ *                            measured equal).  Env VIT3D_MLP_PAIR.
  *   VIT3D_TUNE_WGRAD_RED     1 (default): split-K weight-gradient tiles are added into the gradient buffer by the
  *                            TMA unit (cp.reduce.async.bulk.tensor, fp32 add at the L2); 0: red.global.add.v4.f32
  *                            from the epilogue warps (~1 element per clock and SM); 2: as 1 with 256-row tiles for the large
